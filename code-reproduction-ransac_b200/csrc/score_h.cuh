@@ -1,0 +1,174 @@
+// K3 — hypotheses x points reprojection-and-threshold kernel for 3x3 (homography) models.
+//
+// Replaces the H x N loop of OpenCV's HomographyEstimatorCallback::computeError + findInliers that
+// cv2.findHomography(..., cv2.RANSAC, thr) runs per RANSAC iteration (reference call sites:
+// main_v1.py:312, process.py:200, testpro.py:350; semantics restated in SURVEY.md A.5).
+//
+// Mapping: one thread owns 2*NPAIR hypotheses, held as NPAIR x 8 packed (fp32x2) coefficient
+// registers for the whole kernel.  A CTA stages one tile of points in shared memory with a single
+// 1-D TMA bulk copy (cp.async.bulk + mbarrier), then every warp walks the tile with broadcast
+// LDS.128 loads: no cross-lane traffic, counts stay in registers, one RED.ADD per hypothesis per
+// tile at the end.  Points are stored "pair-duplicated" (PointH below) so that a point can be
+// multiplied against two hypotheses with one FFMA2/FMUL2/FADD2.
+//
+// Arithmetic modes
+//   EXACT: the reference's un-fused fp32 sequence, operation for operation (A.5):
+//            ww = 1.f/((h6*X + h7*Y) + 1.f)
+//            dx = ((h0*X + h1*Y) + h2)*ww - u ;  dy = ((h3*X + h4*Y) + h5)*ww - v
+//            inlier  <=>  dx*dx + dy*dy <= thr     (NaN -> outlier)
+//          every product/sum individually rounded (mul.rn/add.rn.f32x2 are never contracted),
+//          reciprocal correctly rounded.  Bit-exact with cv2's mask by construction.
+//   FAST:  same formula with FMA contraction and MUFU.RCP (10 FMA-pipe ops + 1 MUFU per eval).
+#pragma once
+#include "f32x2.cuh"
+
+namespace b2r {
+
+// One correspondence.  u and v are stored NEGATED: a - b and a + (-b) are the same IEEE operation,
+// and add/fma have no negate modifier in packed form.  A point multiplies two hypotheses at once
+// through the scalar-broadcast operand form of FFMA2/FMUL2/FADD2 (SASS "Rn.F32"), which ptxas
+// selects for f2_dup(x) and which costs one 32-bit register read instead of a 64-bit pair: the
+// register file (2 x 32-bit reads/clk/SMSP, measured with tools/regprobe.cu) is what bounds this kernel.
+struct __align__(16) PointH {
+    float X, Y;    // source point (pos2 in the reference)
+    float nu, nv;  // minus the destination pixel
+};
+
+constexpr int K3_THREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// -- mbarrier / 1-D TMA helpers (SASS: SYNCS.*, UBLKCP) ---------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <bool EXACT>
+struct HEval {
+    // Returns the packed squared reprojection error of one point against two hypotheses.
+    __device__ __forceinline__ static f2_t err(const f2_t (&h)[8], f2_t X, f2_t Y, f2_t nu, f2_t nv, f2_t one) {
+        if (EXACT) {
+            f2_t w = f2_add(f2_add(f2_mul(h[6], X), f2_mul(h[7], Y)), one);
+            float w0, w1;
+            f2_unpack(w, w0, w1);
+            f2_t ww;
+            if (__builtin_expect(rcp_rn_in_fast_range(w0) && rcp_rn_in_fast_range(w1), 1)) {
+                f2_t y = f2_pack(rcp_approx(w0), rcp_approx(w1));
+                // e = 1 - w*y computed as -(w*y - 1): the sign flip is exact, so y + y*e is evaluated
+                // as fma(-y... ) is avoided by negating e through the (exact) product sign instead.
+                float y0, y1;
+                f2_unpack(y, y0, y1);
+                float e0 = __fmaf_rn(-w0, y0, 1.0f), e1 = __fmaf_rn(-w1, y1, 1.0f);
+                ww = f2_fma(y, f2_pack(e0, e1), y);
+            } else {
+                ww = f2_pack(__frcp_rn(w0), __frcp_rn(w1));
+            }
+            f2_t sx = f2_add(f2_add(f2_mul(h[0], X), f2_mul(h[1], Y)), h[2]);
+            f2_t sy = f2_add(f2_add(f2_mul(h[3], X), f2_mul(h[4], Y)), h[5]);
+            f2_t dx = f2_add(f2_mul(sx, ww), nu);
+            f2_t dy = f2_add(f2_mul(sy, ww), nv);
+            return f2_add(f2_mul(dx, dx), f2_mul(dy, dy));
+        } else {
+            f2_t w = f2_fma(h[6], X, f2_fma(h[7], Y, one));
+            float w0, w1;
+            f2_unpack(w, w0, w1);
+            f2_t ww = f2_pack(rcp_approx(w0), rcp_approx(w1));
+            f2_t sx = f2_fma(h[0], X, f2_fma(h[1], Y, h[2]));
+            f2_t sy = f2_fma(h[3], X, f2_fma(h[4], Y, h[5]));
+            f2_t dx = f2_fma(sx, ww, nu);
+            f2_t dy = f2_fma(sy, ww, nv);
+            return f2_fma(dx, dx, f2_mul(dy, dy));
+        }
+    }
+};
+
+// models : [H][8] fp32 (h0..h7, h8 == 1 implied), 32-byte aligned rows
+// pts    : [N] PointH
+// counts : [H] int32, must be zeroed by the caller; each CTA adds its tile's inlier counts
+// grid   : x = ceil(H / (K3_THREADS*2*NPAIR)), y = ceil(N / tile_pts); dynamic smem = 128 + tile_pts*16
+template <int NPAIR, bool EXACT>
+__global__ void __launch_bounds__(K3_THREADS, 2)
+k3_score_h(const float4* __restrict__ models, int H, const PointH* __restrict__ pts, int N, float thr,
+           int* __restrict__ counts, int tile_pts) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    const float4* tile = reinterpret_cast<const float4*>(smem_raw + 128);
+
+    const int p_begin = blockIdx.y * tile_pts;
+    const int np = min(tile_pts, N - p_begin);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, (uint32_t)np * 16u);
+        tma_load_1d(smem_raw + 128, pts + p_begin, (uint32_t)np * 16u, bar);
+    }
+
+    // While the bulk copy is in flight: fetch this thread's hypotheses and pack them in pairs.
+    const int h_base = blockIdx.x * (K3_THREADS * 2 * NPAIR) + threadIdx.x;
+    f2_t h[NPAIR][8];
+#pragma unroll
+    for (int j = 0; j < NPAIR; ++j) {
+        const int ha = h_base + (2 * j) * K3_THREADS, hb = ha + K3_THREADS;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+        if (ha < H) { a0 = __ldg(models + 2 * ha); a1 = __ldg(models + 2 * ha + 1); }
+        if (hb < H) { b0 = __ldg(models + 2 * hb); b1 = __ldg(models + 2 * hb + 1); }
+        h[j][0] = f2_pack(a0.x, b0.x); h[j][1] = f2_pack(a0.y, b0.y);
+        h[j][2] = f2_pack(a0.z, b0.z); h[j][3] = f2_pack(a0.w, b0.w);
+        h[j][4] = f2_pack(a1.x, b1.x); h[j][5] = f2_pack(a1.y, b1.y);
+        h[j][6] = f2_pack(a1.z, b1.z); h[j][7] = f2_pack(a1.w, b1.w);
+    }
+    int cnt[2 * NPAIR];
+#pragma unroll
+    for (int j = 0; j < 2 * NPAIR; ++j) cnt[j] = 0;
+    const f2_t one = f2_dup(1.0f);
+
+    mbar_wait(bar, 0);
+
+#pragma unroll 2
+    for (int p = 0; p < np; ++p) {
+        const float4 pt = tile[p];  // broadcast LDS.128
+        const f2_t X = f2_dup(pt.x), Y = f2_dup(pt.y), nu = f2_dup(pt.z), nv = f2_dup(pt.w);
+#pragma unroll
+        for (int j = 0; j < NPAIR; ++j) {
+            float e0, e1;
+            f2_unpack(HEval<EXACT>::err(h[j], X, Y, nu, nv, one), e0, e1);
+            cnt[2 * j] += (e0 <= thr) ? 1 : 0;
+            cnt[2 * j + 1] += (e1 <= thr) ? 1 : 0;
+        }
+    }
+
+#pragma unroll
+    for (int j = 0; j < 2 * NPAIR; ++j) {
+        const int hh = h_base + j * K3_THREADS;
+        if (hh < H) atomicAdd(counts + hh, cnt[j]);
+    }
+}
+
+}  // namespace b2r
