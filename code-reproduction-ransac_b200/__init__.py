@@ -1,0 +1,13 @@
+"""ransac_b200 — B200-native (sm_100a) RANSAC camera-location hot path.
+
+Drop-in for the two OpenCV calls the reference makes (cv2.findHomography(..., cv2.RANSAC, thr) at
+main_v1.py:312 and cv2.solvePnPRansac at main_v1.py:497) and for the Python loops around them.  The directory
+name contains hyphens, so it is imported through the alias module `ransac_b200.py` at the repo root.
+"""
+from . import _build  # noqa: F401
+from .api import (ARITH_EXACT, ARITH_FAST, MASK_CV413, MASK_LEGACY, SAMPLER_CV_REPLAY, SAMPLER_PHILOX, Context,
+                  HomographyProblem, RansacB200Error, default_context, make_params)
+
+__all__ = ["Context", "HomographyProblem", "RansacB200Error", "default_context", "make_params", "ARITH_EXACT", "ARITH_FAST",
+           "MASK_CV413", "MASK_LEGACY", "SAMPLER_CV_REPLAY", "SAMPLER_PHILOX"]
+__version__ = "0.1.0"

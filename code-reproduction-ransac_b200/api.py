@@ -1,0 +1,254 @@
+"""Host-side API over the C ABI: one `Context` per GPU, NumPy in / NumPy out.
+
+Mirrors the call the reference makes, `cv2.findHomography(src, dst, cv2.RANSAC, thr)` (main_v1.py:312), plus the
+batched form of the loop around it (`find_homographies`, main_v1.py:254-297) and the individual kernels for the
+parity tests.  All arithmetic runs in libransac_b200.so on the GPU."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import HInfo, HParams
+
+SAMPLER_CV_REPLAY, SAMPLER_PHILOX = 0, 1
+ARITH_EXACT, ARITH_FAST = 0, 1
+MASK_CV413, MASK_LEGACY = 0, 1
+OK, NO_MODEL = 0, 1
+
+
+class RansacB200Error(RuntimeError):
+    pass
+
+
+def _ptr(a, ct):
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+def _f64(a, cols):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1, cols))
+
+
+def _f32(a, cols):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1, cols))
+
+
+def make_params(thr, max_iters=2000, confidence=0.995, sampler=SAMPLER_CV_REPLAY, seed=0, arith=ARITH_EXACT,
+                mask_semantics=MASK_CV413, refine=True, hyp_begin=0):
+    p = HParams()
+    p.thr = float(thr)
+    p.max_iters = int(max_iters)
+    p.confidence = float(confidence)
+    p.sampler = int(sampler)
+    p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    p.arith = int(arith)
+    p.mask_semantics = int(mask_semantics)
+    p.refine = 1 if refine else 0
+    p.hyp_begin = int(hyp_begin)
+    return p
+
+
+def _info_dict(i):
+    return dict(status=i.status, iters_run=i.iters_run, best_iter=i.best_iter, best_count=i.best_count,
+                sample=[int(x) for x in i.sample], n_inliers=i.n_inliers, lm_iters=i.lm_iters)
+
+
+class HomographyProblem:
+    """Q homography-RANSAC problems of n correspondences each, resident in HBM (b2r_h_problem)."""
+
+    def __init__(self, ctx, src, dst, dst_shared=None):
+        src = np.asarray(src, dtype=np.float64)
+        dst = np.asarray(dst, dtype=np.float64)
+        if src.ndim == 2:
+            src = src[None]
+        if dst_shared is None:
+            dst_shared = dst.ndim == 2
+        if not dst_shared and dst.ndim == 2:
+            dst = dst[None]
+        self.Q, self.n = int(src.shape[0]), int(src.shape[1])
+        src = np.ascontiguousarray(src)
+        dst = np.ascontiguousarray(dst)
+        if dst.shape[-2] != self.n or src.shape[-1] != 2 or dst.shape[-1] != 2:
+            raise ValueError("src must be (Q,n,2) and dst (n,2) or (Q,n,2)")
+        self.ctx = ctx
+        self.h2d_bytes = src.nbytes + dst.nbytes
+        self._h = ctx._L.b2r_h_problem_upload(ctx._c, _ptr(src, C.c_double), _ptr(dst, C.c_double), 1 if dst_shared else 0,
+                                              self.Q, self.n)
+        if not self._h:
+            raise RansacB200Error(_lib.last_error())
+
+    def run(self, params):
+        self.ctx._check(self.ctx._L.b2r_h_problem_run(self.ctx._c, self._h, C.byref(params)))
+
+    def score_shard(self, params):
+        """Stage 1 on this rank's hypothesis-id shard; returns the packed (count, id) keys, uint64 (Q,)."""
+        keys = np.zeros(self.Q, dtype=np.uint64)
+        self.ctx._check(self.ctx._L.b2r_h_problem_score_shard(self.ctx._c, self._h, C.byref(params), _ptr(keys, C.c_uint64)))
+        return keys
+
+    def finish(self, params, keys):
+        keys = np.ascontiguousarray(np.asarray(keys, dtype=np.uint64).reshape(self.Q))
+        self.ctx._check(self.ctx._L.b2r_h_problem_finish(self.ctx._c, self._h, C.byref(params), _ptr(keys, C.c_uint64)))
+
+    def fetch(self, want_mask=True):
+        H = np.zeros((self.Q, 3, 3))
+        mask = np.zeros((self.Q, self.n), dtype=np.uint8) if want_mask else None
+        info = (HInfo * self.Q)()
+        self.ctx._check(self.ctx._L.b2r_h_problem_fetch(self.ctx._c, self._h, _ptr(H, C.c_double),
+                                                        _ptr(mask, C.c_uint8) if want_mask else None, info))
+        return H, mask, [_info_dict(i) for i in info]
+
+    def stage_ms(self):
+        ms = (C.c_float * 5)()
+        self.ctx._check(self.ctx._L.b2r_h_problem_stage_ms(self.ctx._c, self._h, ms))
+        return dict(sample_solve=ms[0], score=ms[1], select=ms[2], finalize=ms[3], total=ms[4])
+
+    def free(self):
+        if self._h:
+            self.ctx._L.b2r_h_problem_free(self.ctx._c, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU context (own CUDA stream and workspaces).  Not thread-safe."""
+
+    def __init__(self, device=0):
+        self._L = _lib.load()
+        self._c = self._L.b2r_ctx_create(int(device))
+        if not self._c:
+            raise RansacB200Error(_lib.last_error())
+        self.device = int(device)
+
+    def close(self):
+        if self._c:
+            self._L.b2r_ctx_destroy(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise RansacB200Error(f"ransac_b200 error {rc}: {_lib.last_error()}")
+        return rc
+
+    @property
+    def stream(self):
+        """cudaStream_t of this context as an int (usable with torch.cuda.ExternalStream)."""
+        return int(self._L.b2r_ctx_stream(self._c) or 0)
+
+    def synchronize(self):
+        self._check(self._L.b2r_ctx_synchronize(self._c))
+
+    def launch_count(self):
+        return int(self._L.b2r_ctx_launch_count(self._c))
+
+    # ---- the reference's call ------------------------------------------------------------------------
+    def find_homography(self, src, dst, thr, max_iters=2000, confidence=0.995, **kw):
+        """cv2.findHomography(src, dst, cv2.RANSAC, thr, maxIters=..., confidence=...) on the GPU.
+
+        Returns (H (3,3) float64 or None, mask (n,1) uint8, info dict) — cv2's convention plus diagnostics."""
+        s, d = _f64(src, 2), _f64(dst, 2)
+        if len(s) != len(d):
+            raise ValueError("src and dst must have the same number of points")
+        n = len(s)
+        p = make_params(thr, max_iters, confidence, **kw)
+        H = np.zeros(9)
+        mask = np.zeros(max(n, 1), dtype=np.uint8)
+        info = HInfo()
+        rc = self._check(self._L.b2r_find_homography(self._c, _ptr(s, C.c_double), _ptr(d, C.c_double), n, C.byref(p),
+                                                     _ptr(H, C.c_double), _ptr(mask, C.c_uint8), C.byref(info)))
+        return (H.reshape(3, 3) if rc == OK else None), mask[:n].reshape(n, 1), _info_dict(info)
+
+    def find_homography_batch(self, src, dst, thr, max_iters=2000, confidence=0.995, **kw):
+        """Q independent problems in one call: src (Q,n,2); dst (n,2) shared or (Q,n,2).
+
+        Returns (H (Q,3,3), ok (Q,) bool, mask (Q,n) uint8, infos list)."""
+        src = np.ascontiguousarray(np.asarray(src, dtype=np.float64))
+        dst = np.ascontiguousarray(np.asarray(dst, dtype=np.float64))
+        Q, n = src.shape[0], src.shape[1]
+        shared = dst.ndim == 2
+        p = make_params(thr, max_iters, confidence, **kw)
+        H = np.zeros((Q, 3, 3))
+        mask = np.zeros((Q, n), dtype=np.uint8)
+        info = (HInfo * Q)()
+        self._check(self._L.b2r_find_homography_batch(self._c, _ptr(src, C.c_double), _ptr(dst, C.c_double), 1 if shared else 0,
+                                                      Q, n, C.byref(p), _ptr(H, C.c_double), _ptr(mask, C.c_uint8), info))
+        infos = [_info_dict(i) for i in info]
+        ok = np.array([i["status"] == OK for i in infos])
+        return H, ok, mask, infos
+
+    def upload(self, src, dst, dst_shared=None):
+        return HomographyProblem(self, src, dst, dst_shared)
+
+    # ---- single kernels (parity tests) -------------------------------------------------------------------
+    def score_h(self, models8, src_f32, dst_f32, thr_sq, arith=ARITH_EXACT):
+        m = _f32(models8, 8)
+        s, d = _f32(src_f32, 2), _f32(dst_f32, 2)
+        counts = np.zeros(len(m), dtype=np.int32)
+        self._check(self._L.b2r_score_h(self._c, _ptr(m, C.c_float), len(m), _ptr(s, C.c_float), _ptr(d, C.c_float), len(s),
+                                        C.c_float(np.float32(thr_sq)), int(arith), _ptr(counts, C.c_int32)))
+        return counts
+
+    def solve_h4(self, src_f32, dst_f32, idx):
+        s, d = _f32(src_f32, 2), _f32(dst_f32, 2)
+        idx = np.ascontiguousarray(np.asarray(idx, dtype=np.int32).reshape(-1, 4))
+        k = len(idx)
+        H = np.zeros((k, 3, 3))
+        ok = np.zeros(k, dtype=np.uint8)
+        sub = np.zeros(k, dtype=np.uint8)
+        self._check(self._L.b2r_solve_h4(self._c, _ptr(s, C.c_float), _ptr(d, C.c_float), len(s), _ptr(idx, C.c_int32), k,
+                                         _ptr(H, C.c_double), _ptr(ok, C.c_uint8), _ptr(sub, C.c_uint8)))
+        return H, ok.astype(bool), sub.astype(bool)
+
+    def sample_cv(self, src_f32, dst_f32, n_iters):
+        s, d = _f32(src_f32, 2), _f32(dst_f32, 2)
+        idx = np.full((n_iters, 4), -1, dtype=np.int32)
+        gen = C.c_int32(0)
+        self._check(self._L.b2r_sample_cv(self._c, _ptr(s, C.c_float), _ptr(d, C.c_float), len(s), n_iters,
+                                          _ptr(idx, C.c_int32), C.byref(gen)))
+        return idx[:gen.value]
+
+    def sample_philox(self, src_f32, dst_f32, seed, hyp_begin, n_hyp):
+        s, d = _f32(src_f32, 2), _f32(dst_f32, 2)
+        idx = np.full((n_hyp, 4), -1, dtype=np.int32)
+        self._check(self._L.b2r_sample_philox(self._c, _ptr(s, C.c_float), _ptr(d, C.c_float), len(s),
+                                              int(seed) & 0xFFFFFFFFFFFFFFFF, 0, int(hyp_begin), n_hyp, _ptr(idx, C.c_int32)))
+        return idx
+
+    def refine_h(self, src_f32, dst_f32, mask, H0):
+        s, d = _f32(src_f32, 2), _f32(dst_f32, 2)
+        m = np.ascontiguousarray(np.asarray(mask, dtype=np.uint8).reshape(-1))
+        H = np.ascontiguousarray(np.asarray(H0, dtype=np.float64).reshape(9)).copy()
+        it = C.c_int32(0)
+        self._check(self._L.b2r_refine_h(self._c, _ptr(s, C.c_float), _ptr(d, C.c_float), len(s), _ptr(m, C.c_uint8),
+                                         _ptr(H, C.c_double), C.byref(it)))
+        return H.reshape(3, 3), it.value
+
+    def selftest_rcp(self):
+        bad, tested = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._L.b2r_selftest_rcp(self._c, C.byref(bad), C.byref(tested)))
+        return int(bad.value), int(tested.value)
+
+    def probe_fp32_peak(self):
+        """(scalar FFMA, packed FFMA2) fp32 FMA lane-operations per second, register resident."""
+        a, b = C.c_double(0), C.c_double(0)
+        self._check(self._L.b2r_probe_fp32_peak(self._c, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

@@ -1,0 +1,695 @@
+// C ABI of libransac_b200.so (declared in include/ransac_b200.h).  Host-side orchestration only: every
+// arithmetic step of the hot path runs in the kernels of pipeline_h.cuh / score_h.cuh.  There is no CPU
+// fallback: each entry point fails with B2R_ERR_CUDA when no device is usable.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+// the library is built with -fvisibility=hidden; exactly the symbols of the public header are exported
+#pragma GCC visibility push(default)
+#include "../../include/ransac_b200.h"
+#pragma GCC visibility pop
+#include "pipeline_h.cuh"
+
+using namespace b2r;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+    char buf[512];
+    snprintf(buf, sizeof(buf), fmt, a, b);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) return fail(B2R_ERR_CUDA, "CUDA error: %s  [%s]", cudaGetErrorString(e_), #call); \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct b2r_h_problem {
+    int Q = 0, n = 0;
+    DevBuf pts;       // [Q][n] PointH
+    DevBuf samples;   // [Q][H][4] int32
+    DevBuf models;    // [Q][H][8] fp32
+    DevBuf counts;    // [Q][H] int32
+    DevBuf ngen;      // [Q] int32
+    DevBuf keys;      // [Q] u64
+    DevBuf sel;       // [Q] HSelect
+    DevBuf H;         // [Q][9] fp64
+    DevBuf mask;      // [Q][n] u8
+    DevBuf rmask;     // [Q][n] u8
+    DevBuf info;      // [Q][12] int32
+    int H_last = 0;
+    float stage_ms[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void release() {
+        pts.release(); samples.release(); models.release(); counts.release(); ngen.release(); keys.release();
+        sel.release(); H.release(); mask.release(); rmask.release(); info.release();
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e), e = nullptr;
+    }
+};
+
+struct b2r_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf in_a, in_b, scratch0, scratch1, scratch2, scratch3;  // staging for the host-pointer entry points
+    PinnedBuf pin_in, pin_out;
+    b2r_h_problem* cached = nullptr;  // reusable problem storage of b2r_find_homography[_batch]
+    int launches = 0;
+};
+
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                \
+    do {                                                           \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+        (ctx)->launches++;                                         \
+    } while (0)
+
+extern "C" {
+
+int b2r_version(void) { return 100; }
+const char* b2r_last_error(void) { return g_err.c_str(); }
+
+int b2r_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+b2r_ctx* b2r_ctx_create(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        fail(B2R_ERR_CUDA, "no usable CUDA device (%s); ransac_b200 has no CPU fallback%s",
+             e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (device < 0 || device >= n) {
+        fail(B2R_ERR_ARG, "device index out of range%s%s");
+        return nullptr;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        fail(B2R_ERR_CUDA, "cudaSetDevice: %s%s", cudaGetErrorString(e));
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        fail(B2R_ERR_CUDA, "cudaGetDeviceProperties: %s%s", cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (prop.major != 10) {
+        char cc[32];
+        snprintf(cc, sizeof(cc), "%d.%d", prop.major, prop.minor);
+        fail(B2R_ERR_CUDA, "device %s has compute capability %s; this library is built for sm_100a only", prop.name, cc);
+        return nullptr;
+    }
+    b2r_ctx* c = new b2r_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        fail(B2R_ERR_CUDA, "cudaStreamCreate: %s%s", cudaGetErrorString(e));
+        delete c;
+        return nullptr;
+    }
+    return c;
+}
+
+void b2r_ctx_destroy(b2r_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->cached) {
+        c->cached->release();
+        delete c->cached;
+    }
+    c->in_a.release(); c->in_b.release(); c->scratch0.release(); c->scratch1.release(); c->scratch2.release();
+    c->scratch3.release(); c->pin_in.release(); c->pin_out.release();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void* b2r_ctx_stream(b2r_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int b2r_ctx_synchronize(b2r_ctx* c) {
+    if (!c) return fail(B2R_ERR_ARG, "null context%s%s");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2R_OK;
+}
+
+int b2r_ctx_launch_count(b2r_ctx* c) { return c ? c->launches : 0; }
+
+void b2r_default_h_params(b2r_h_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->thr = 3.0;
+    p->max_iters = 2000;
+    p->confidence = 0.995;
+    p->sampler = B2R_SAMPLER_CV_REPLAY;
+    p->seed = 0;
+    p->arith = B2R_ARITH_EXACT;
+    p->mask_semantics = B2R_MASK_CV413;
+    p->refine = 1;
+    p->hyp_begin = 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+static int check_params(const b2r_h_params* p) {
+    if (!p) return fail(B2R_ERR_ARG, "null params%s%s");
+    if (!(p->thr >= 0)) return fail(B2R_ERR_ARG, "thr must be >= 0%s%s");
+    if (p->sampler != B2R_SAMPLER_CV_REPLAY && p->sampler != B2R_SAMPLER_PHILOX) return fail(B2R_ERR_ARG, "bad sampler%s%s");
+    if (p->arith != B2R_ARITH_EXACT && p->arith != B2R_ARITH_FAST) return fail(B2R_ERR_ARG, "bad arith%s%s");
+    if (p->max_iters > (1 << 30)) return fail(B2R_ERR_ARG, "max_iters too large%s%s");
+    return B2R_OK;
+}
+
+template <int NPAIR>
+static int launch_k3(b2r_ctx* c, const float4* models, int H, const PointH* pts, int n, float thr_sq, int* counts, int Q,
+                     int arith) {
+    // tile: as many points per CTA as keeps >= ~4 CTAs per SM slot in flight, capped by 2048 (32 KB)
+    int tile = 1024;
+    const long long hyp_blocks = (H + K3_THREADS * 2 * NPAIR - 1) / (K3_THREADS * 2 * NPAIR);
+    while (tile > 128 && hyp_blocks * ((n + tile - 1) / tile) * Q < 8LL * c->sm_count) tile >>= 1;
+    if (tile > n) tile = ((n + 7) / 8) * 8;
+    const size_t smem = 128 + (size_t)tile * 16;
+    dim3 grid((unsigned)hyp_blocks, (unsigned)((n + tile - 1) / tile), (unsigned)Q);
+    if (arith == B2R_ARITH_EXACT)
+        LAUNCH(c, (k3_score_h<NPAIR, true>), grid, K3_THREADS, smem, models, H, pts, n, thr_sq, counts, tile);
+    else
+        LAUNCH(c, (k3_score_h<NPAIR, false>), grid, K3_THREADS, smem, models, H, pts, n, thr_sq, counts, tile);
+    CU(cudaGetLastError());
+    return B2R_OK;
+}
+
+static int score_models(b2r_ctx* c, const float4* models, int H, const PointH* pts, int n, float thr_sq, int* counts,
+                        int Q, int arith) {
+    CU(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)Q * H, c->stream));
+    // few hypotheses per problem: 2 pairs per thread keeps more CTAs in flight; otherwise 4 pairs (fewer LDS per eval)
+    if ((long long)H * Q <= 2048LL * c->sm_count) return launch_k3<2>(c, models, H, pts, n, thr_sq, counts, Q, arith);
+    return launch_k3<4>(c, models, H, pts, n, thr_sq, counts, Q, arith);
+}
+
+static int problem_reserve(b2r_h_problem* pr, int Q, int n, int H) {
+    CU(pr->pts.reserve(sizeof(PointH) * (size_t)Q * n));
+    CU(pr->samples.reserve(sizeof(int) * 4 * (size_t)Q * H));
+    CU(pr->models.reserve(sizeof(float) * 8 * (size_t)Q * H));
+    CU(pr->counts.reserve(sizeof(int) * (size_t)Q * H));
+    CU(pr->ngen.reserve(sizeof(int) * (size_t)Q));
+    CU(pr->keys.reserve(sizeof(unsigned long long) * (size_t)Q));
+    CU(pr->sel.reserve(sizeof(HSelect) * (size_t)Q));
+    CU(pr->H.reserve(sizeof(double) * 9 * (size_t)Q));
+    CU(pr->mask.reserve((size_t)Q * n));
+    CU(pr->rmask.reserve((size_t)Q * n));
+    CU(pr->info.reserve(sizeof(int) * 12 * (size_t)Q));
+    for (auto& e : pr->ev)
+        if (!e) CU(cudaEventCreate(&e));
+    return B2R_OK;
+}
+
+static int upload_points(b2r_ctx* c, b2r_h_problem* pr, const double* src, const double* dst, int dst_shared, int Q, int n) {
+    const size_t sb = sizeof(double) * 2 * (size_t)Q * n, db = sizeof(double) * 2 * (size_t)(dst_shared ? 1 : Q) * n;
+    CU(c->in_a.reserve(sb));
+    CU(c->in_b.reserve(db));
+    CU(cudaMemcpyAsync(c->in_a.p, src, sb, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->in_b.p, dst, db, cudaMemcpyHostToDevice, c->stream));
+    const size_t total = (size_t)Q * n;
+    LAUNCH(c, k_pack_points_h, (unsigned)((total + 255) / 256), 256, 0, c->in_a.as<double>(), c->in_b.as<double>(),
+           dst_shared, Q, n, pr->pts.as<PointH>());
+    CU(cudaGetLastError());
+    pr->Q = Q;
+    pr->n = n;
+    return B2R_OK;
+}
+
+// stage 1: sample + solve + score (+ per-problem argmax key for PHILOX)
+static int run_score(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p) {
+    const int Q = pr->Q, n = pr->n, H = p->max_iters > 1 ? p->max_iters : 1;
+    int rc = problem_reserve(pr, Q, n, H);
+    if (rc) return rc;
+    pr->H_last = H;
+    const float thr_sq = (float)(p->thr * p->thr);
+    CU(cudaEventRecord(pr->ev[0], c->stream));
+    if (n > 4) {
+        if (p->sampler == B2R_SAMPLER_PHILOX) {
+            dim3 grid((unsigned)((H + 127) / 128), (unsigned)Q);
+            LAUNCH(c, k_philox_sample_solve_h, grid, 128, 0, pr->pts.as<PointH>(), n, H, (long long)p->hyp_begin, p->seed,
+                   pr->samples.as<int>(), pr->models.as<float4>(), 1);
+        } else {
+            LAUNCH(c, k_cv_sample_h, (unsigned)((Q + 31) / 32), 32, 0, pr->pts.as<PointH>(), n, H, pr->samples.as<int>(),
+                   pr->ngen.as<int>(), Q);
+            dim3 grid((unsigned)((H + 127) / 128), (unsigned)Q);
+            LAUNCH(c, k_solve_h4, grid, 128, 0, pr->pts.as<PointH>(), n, pr->samples.as<int>(), H, pr->ngen.as<int>(),
+                   pr->models.as<float4>(), (double*)nullptr, (uint8_t*)nullptr, (uint8_t*)nullptr);
+        }
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(pr->ev[1], c->stream));
+    if (n > 4) {
+        rc = score_models(c, pr->models.as<float4>(), H, pr->pts.as<PointH>(), n, thr_sq, pr->counts.as<int>(), Q, p->arith);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(pr->ev[2], c->stream));
+    if (n > 4 && p->sampler == B2R_SAMPLER_PHILOX) {
+        CU(cudaMemsetAsync(pr->keys.p, 0, sizeof(unsigned long long) * Q, c->stream));
+        int gx = (H + 255) / 256;
+        if (gx > 4 * c->sm_count) gx = 4 * c->sm_count;
+        LAUNCH(c, k_argmax_key, dim3((unsigned)gx, (unsigned)Q), 256, 0, pr->counts.as<int>(), H,
+               (unsigned long long)p->hyp_begin, pr->keys.as<unsigned long long>());
+        CU(cudaGetLastError());
+    }
+    return B2R_OK;
+}
+
+__global__ void k_select_n4(HSelect* sel, int* samples, int Q) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    HSelect s;
+    s.best = 0; s.best_count = 4; s.iters_run = 0; s.pad = 0;
+    sel[q] = s;
+    reinterpret_cast<int4*>(samples)[q] = make_int4(0, 1, 2, 3);
+}
+
+// The winner may live on another rank: rebuild its sample from the global hypothesis id into slot 0 of `samples`.
+__global__ void k_resample_winner(const PointH* __restrict__ pts, int n, const unsigned long long* __restrict__ keys,
+                                  uint64_t seed, int Hs, int* __restrict__ samples, HSelect* __restrict__ sel, int H_total,
+                                  int Q) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const unsigned long long key = keys[q];
+    const int count = (int)(key >> 32);
+    const unsigned long long gid = 0xFFFFFFFFull - (key & 0xFFFFFFFFull);
+    HSelect s;
+    s.best = -1; s.best_count = 0; s.iters_run = H_total; s.pad = 0;
+    if (count > 3) {
+        const PointH* P = pts + (size_t)q * n;
+        int idx[4];
+        float ms1[8], ms2[8];
+        bool found = false;
+        for (int attempt = 0; attempt < PHILOX_MAX_ATTEMPTS && !found; ++attempt) {
+            const Philox4 r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)attempt, (uint32_t)q,
+                                            (uint32_t)seed, (uint32_t)(seed >> 32));
+            distinct4(r, (uint32_t)n, idx);
+            gather4(P, idx, ms1, ms2);
+            found = h_check_subset4(ms1, ms2);
+        }
+        if (found) {
+            reinterpret_cast<int4*>(samples)[(size_t)q * Hs] = make_int4(idx[0], idx[1], idx[2], idx[3]);
+            s.best = 0;
+            s.best_count = count;
+        }
+    }
+    sel[q] = s;
+}
+
+// stage 2: select + finalize.  keys_host != nullptr: use these (globally reduced) keys instead of the local ones.
+static int run_finish(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p, const uint64_t* keys_host) {
+    const int Q = pr->Q, n = pr->n, H = pr->H_last;
+    const float thr_sq = (float)(p->thr * p->thr);
+    if (n == 4) {
+        LAUNCH(c, k_select_n4, (unsigned)((Q + 127) / 128), 128, 0, pr->sel.as<HSelect>(), pr->samples.as<int>(), Q);
+    } else if (p->sampler == B2R_SAMPLER_PHILOX) {
+        if (keys_host) {
+            CU(cudaMemcpyAsync(pr->keys.p, keys_host, sizeof(uint64_t) * Q, cudaMemcpyHostToDevice, c->stream));
+            LAUNCH(c, k_resample_winner, (unsigned)((Q + 127) / 128), 128, 0, pr->pts.as<PointH>(), n,
+                   pr->keys.as<unsigned long long>(), p->seed, H, pr->samples.as<int>(), pr->sel.as<HSelect>(), H, Q);
+        } else {
+            LAUNCH(c, k_select_from_keys, (unsigned)((Q + 127) / 128), 128, 0, pr->keys.as<unsigned long long>(),
+                   (unsigned long long)p->hyp_begin, H, 4, pr->sel.as<HSelect>(), Q);
+        }
+    } else {
+        LAUNCH(c, k_select_cv, (unsigned)((Q + 127) / 128), 128, 0, pr->counts.as<int>(), pr->ngen.as<int>(), H, n,
+               p->max_iters, p->confidence, 4, pr->sel.as<HSelect>(), Q);
+    }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(pr->ev[3], c->stream));
+    const int Hs = n == 4 ? 1 : H;
+    if (n >= 4096)
+        LAUNCH(c, k_finalize_h<1024>, (unsigned)Q, 1024, 0, pr->pts.as<PointH>(), n, pr->samples.as<int>(), Hs,
+               pr->sel.as<HSelect>(), thr_sq, p->mask_semantics, p->refine, pr->H.as<double>(), pr->mask.as<uint8_t>(),
+               pr->rmask.as<uint8_t>(), pr->info.as<int>(), (const uint8_t*)nullptr, (const double*)nullptr);
+    else
+        LAUNCH(c, k_finalize_h<128>, (unsigned)Q, 128, 0, pr->pts.as<PointH>(), n, pr->samples.as<int>(), Hs,
+               pr->sel.as<HSelect>(), thr_sq, p->mask_semantics, p->refine, pr->H.as<double>(), pr->mask.as<uint8_t>(),
+               pr->rmask.as<uint8_t>(), pr->info.as<int>(), (const uint8_t*)nullptr, (const double*)nullptr);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(pr->ev[4], c->stream));
+    return B2R_OK;
+}
+
+static int fetch(b2r_ctx* c, b2r_h_problem* pr, double* H_out, uint8_t* mask_out, b2r_h_info* info_out) {
+    const int Q = pr->Q, n = pr->n;
+    const size_t hb = sizeof(double) * 9 * (size_t)Q, mb = (size_t)Q * n, ib = sizeof(int) * 12 * (size_t)Q;
+    CU(c->pin_out.reserve(hb + mb + ib + 64));
+    char* base = (char*)c->pin_out.p;
+    CU(cudaMemcpyAsync(base, pr->H.p, hb, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(base + hb, pr->info.p, ib, cudaMemcpyDeviceToHost, c->stream));
+    if (mask_out) CU(cudaMemcpyAsync(base + hb + ib, pr->mask.p, mb, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (H_out) memcpy(H_out, base, hb);
+    if (info_out) memcpy(info_out, base + hb, ib);
+    if (mask_out) memcpy(mask_out, base + hb + ib, mb);
+    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&pr->stage_ms[i], pr->ev[i], pr->ev[i + 1]);
+    cudaEventElapsedTime(&pr->stage_ms[4], pr->ev[0], pr->ev[4]);
+    cudaGetLastError();
+    return B2R_OK;
+}
+
+static_assert(sizeof(b2r_h_info) == 12 * sizeof(int32_t), "b2r_h_info layout");
+
+extern "C" {
+
+b2r_h_problem* b2r_h_problem_upload(b2r_ctx* c, const double* src, const double* dst, int32_t dst_shared, int32_t Q,
+                                    int32_t n) {
+    if (!c || !src || !dst || Q < 1 || n < 4) {
+        fail(B2R_ERR_ARG, "b2r_h_problem_upload: need Q >= 1 and n >= 4 points (cv2.findHomography raises below 4)%s%s");
+        return nullptr;
+    }
+    if (cudaSetDevice(c->device) != cudaSuccess) {
+        fail(B2R_ERR_CUDA, "cudaSetDevice failed%s%s");
+        return nullptr;
+    }
+    b2r_h_problem* pr = new b2r_h_problem();
+    if (pr->pts.reserve(sizeof(PointH) * (size_t)Q * n) != cudaSuccess || upload_points(c, pr, src, dst, dst_shared, Q, n) ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        if (g_err.empty()) fail(B2R_ERR_CUDA, "upload failed%s%s");
+        pr->release();
+        delete pr;
+        return nullptr;
+    }
+    return pr;
+}
+
+void b2r_h_problem_free(b2r_ctx* c, b2r_h_problem* pr) {
+    if (!pr) return;
+    if (c) cudaSetDevice(c->device);
+    pr->release();
+    delete pr;
+}
+
+int b2r_h_problem_run(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p) {
+    if (!c || !pr) return fail(B2R_ERR_ARG, "null argument%s%s");
+    int rc = check_params(p);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    if ((rc = run_score(c, pr, p))) return rc;
+    return run_finish(c, pr, p, nullptr);
+}
+
+int b2r_h_problem_score_shard(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p, uint64_t* keys_out) {
+    if (!c || !pr || !keys_out) return fail(B2R_ERR_ARG, "null argument%s%s");
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (p->sampler != B2R_SAMPLER_PHILOX) return fail(B2R_ERR_ARG, "hypothesis sharding needs the PHILOX sampler%s%s");
+    if (pr->n <= 4) return fail(B2R_ERR_ARG, "sharding needs n > 4%s%s");
+    CU(cudaSetDevice(c->device));
+    if ((rc = run_score(c, pr, p))) return rc;
+    CU(cudaMemcpyAsync(keys_out, pr->keys.p, sizeof(uint64_t) * pr->Q, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2R_OK;
+}
+
+int b2r_h_problem_finish(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p, const uint64_t* keys) {
+    if (!c || !pr || !keys) return fail(B2R_ERR_ARG, "null argument%s%s");
+    int rc = check_params(p);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    return run_finish(c, pr, p, keys);
+}
+
+int b2r_h_problem_fetch(b2r_ctx* c, b2r_h_problem* pr, double* H_out, uint8_t* mask_out, b2r_h_info* info_out) {
+    if (!c || !pr) return fail(B2R_ERR_ARG, "null argument%s%s");
+    CU(cudaSetDevice(c->device));
+    return fetch(c, pr, H_out, mask_out, info_out);
+}
+
+int b2r_h_problem_stage_ms(b2r_ctx* c, b2r_h_problem* pr, float ms_out[5]) {
+    if (!c || !pr || !ms_out) return fail(B2R_ERR_ARG, "null argument%s%s");
+    memcpy(ms_out, pr->stage_ms, sizeof(float) * 5);
+    return B2R_OK;
+}
+
+int b2r_find_homography_batch(b2r_ctx* c, const double* src, const double* dst, int32_t dst_shared, int32_t Q, int32_t n,
+                              const b2r_h_params* p, double* H_out, uint8_t* mask_out, b2r_h_info* info_out) {
+    if (!c || !src || !dst || !H_out) return fail(B2R_ERR_ARG, "null argument%s%s");
+    if (Q < 1) return fail(B2R_ERR_ARG, "Q must be >= 1%s%s");
+    if (n < 4) return fail(B2R_ERR_ARG, "findHomography needs at least 4 point pairs (cv2 raises cv2.error)%s%s");
+    int rc = check_params(p);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    if (!c->cached) c->cached = new b2r_h_problem();
+    b2r_h_problem* pr = c->cached;
+    CU(pr->pts.reserve(sizeof(PointH) * (size_t)Q * n));
+    if ((rc = upload_points(c, pr, src, dst, dst_shared, Q, n))) return rc;
+    if ((rc = run_score(c, pr, p))) return rc;
+    if ((rc = run_finish(c, pr, p, nullptr))) return rc;
+    return fetch(c, pr, H_out, mask_out, info_out);
+}
+
+int b2r_find_homography(b2r_ctx* c, const double* src, const double* dst, int32_t n, const b2r_h_params* p, double* H_out,
+                        uint8_t* mask_out, b2r_h_info* info_out) {
+    b2r_h_info info;
+    int rc = b2r_find_homography_batch(c, src, dst, 1, 1, n, p, H_out, mask_out, &info);
+    if (rc) return rc;
+    if (info_out) *info_out = info;
+    return info.status;
+}
+
+// ---- building blocks ------------------------------------------------------------------------------------------------
+static int upload_f32_points(b2r_ctx* c, const float* src, const float* dst, int n, DevBuf& out) {
+    CU(c->in_a.reserve(sizeof(float) * 2 * (size_t)n));
+    CU(c->in_b.reserve(sizeof(float) * 2 * (size_t)n));
+    CU(out.reserve(sizeof(PointH) * (size_t)n));
+    CU(cudaMemcpyAsync(c->in_a.p, src, sizeof(float) * 2 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->in_b.p, dst, sizeof(float) * 2 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_pack_points_h_f32, (unsigned)((n + 255) / 256), 256, 0, c->in_a.as<float>(), c->in_b.as<float>(), n,
+           out.as<PointH>());
+    CU(cudaGetLastError());
+    return B2R_OK;
+}
+
+int b2r_score_h(b2r_ctx* c, const float* models, int32_t n_models, const float* src, const float* dst, int32_t n,
+                float thr_sq, int32_t arith, int32_t* counts_out) {
+    if (!c || !models || !src || !dst || !counts_out || n_models < 1 || n < 1) return fail(B2R_ERR_ARG, "bad argument%s%s");
+    CU(cudaSetDevice(c->device));
+    int rc = upload_f32_points(c, src, dst, n, c->scratch0);
+    if (rc) return rc;
+    CU(c->scratch1.reserve(sizeof(float) * 8 * (size_t)n_models));
+    CU(c->scratch2.reserve(sizeof(int) * (size_t)n_models));
+    CU(cudaMemcpyAsync(c->scratch1.p, models, sizeof(float) * 8 * (size_t)n_models, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = score_models(c, c->scratch1.as<float4>(), n_models, c->scratch0.as<PointH>(), n, thr_sq, c->scratch2.as<int>(),
+                           1, arith)))
+        return rc;
+    CU(cudaMemcpyAsync(counts_out, c->scratch2.p, sizeof(int) * (size_t)n_models, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2R_OK;
+}
+
+int b2r_solve_h4(b2r_ctx* c, const float* src, const float* dst, int32_t n, const int32_t* idx, int32_t n_samples,
+                 double* H_out, uint8_t* ok_out, uint8_t* subset_ok_out) {
+    if (!c || !src || !dst || !idx || !H_out || n < 4 || n_samples < 1) return fail(B2R_ERR_ARG, "bad argument%s%s");
+    for (size_t i = 0; i < (size_t)n_samples * 4; ++i)
+        if (idx[i] < 0 || idx[i] >= n) return fail(B2R_ERR_ARG, "sample index out of range%s%s");
+    CU(cudaSetDevice(c->device));
+    int rc = upload_f32_points(c, src, dst, n, c->scratch0);
+    if (rc) return rc;
+    CU(c->scratch1.reserve(sizeof(int) * 4 * (size_t)n_samples));
+    CU(c->scratch2.reserve(sizeof(double) * 9 * (size_t)n_samples));
+    CU(c->scratch3.reserve(2 * (size_t)n_samples));
+    CU(cudaMemcpyAsync(c->scratch1.p, idx, sizeof(int) * 4 * (size_t)n_samples, cudaMemcpyHostToDevice, c->stream));
+    uint8_t* ok_d = c->scratch3.as<uint8_t>();
+    uint8_t* sub_d = ok_d + n_samples;
+    LAUNCH(c, k_solve_h4, dim3((unsigned)((n_samples + 127) / 128), 1), 128, 0, c->scratch0.as<PointH>(), n,
+           c->scratch1.as<int>(), n_samples, (const int*)nullptr, (float4*)nullptr, c->scratch2.as<double>(), ok_d, sub_d);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(H_out, c->scratch2.p, sizeof(double) * 9 * (size_t)n_samples, cudaMemcpyDeviceToHost, c->stream));
+    if (ok_out) CU(cudaMemcpyAsync(ok_out, ok_d, (size_t)n_samples, cudaMemcpyDeviceToHost, c->stream));
+    if (subset_ok_out) CU(cudaMemcpyAsync(subset_ok_out, sub_d, (size_t)n_samples, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2R_OK;
+}
+
+int b2r_sample_cv(b2r_ctx* c, const float* src, const float* dst, int32_t n, int32_t n_iters, int32_t* idx_out,
+                  int32_t* n_generated_out) {
+    if (!c || !src || !dst || !idx_out || n < 5 || n_iters < 1) return fail(B2R_ERR_ARG, "bad argument (need n > 4)%s%s");
+    CU(cudaSetDevice(c->device));
+    int rc = upload_f32_points(c, src, dst, n, c->scratch0);
+    if (rc) return rc;
+    CU(c->scratch1.reserve(sizeof(int) * 4 * (size_t)n_iters));
+    CU(c->scratch2.reserve(sizeof(int)));
+    LAUNCH(c, k_cv_sample_h, 1, 32, 0, c->scratch0.as<PointH>(), n, n_iters, c->scratch1.as<int>(), c->scratch2.as<int>(), 1);
+    CU(cudaGetLastError());
+    int gen = 0;
+    CU(cudaMemcpyAsync(&gen, c->scratch2.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyAsync(idx_out, c->scratch1.p, sizeof(int) * 4 * (size_t)gen, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (n_generated_out) *n_generated_out = gen;
+    return B2R_OK;
+}
+
+int b2r_sample_philox(b2r_ctx* c, const float* src, const float* dst, int32_t n, uint64_t seed, int32_t q, int64_t hyp_begin,
+                      int32_t n_hyp, int32_t* idx_out) {
+    if (!c || !src || !dst || !idx_out || n < 5 || n_hyp < 1 || q != 0)
+        return fail(B2R_ERR_ARG, "bad argument (need n > 4; only problem index 0 is exposed here)%s%s");
+    CU(cudaSetDevice(c->device));
+    int rc = upload_f32_points(c, src, dst, n, c->scratch0);
+    if (rc) return rc;
+    CU(c->scratch1.reserve(sizeof(int) * 4 * (size_t)n_hyp));
+    LAUNCH(c, k_philox_sample_solve_h, dim3((unsigned)((n_hyp + 127) / 128), 1), 128, 0, c->scratch0.as<PointH>(), n, n_hyp,
+           (long long)hyp_begin, seed, c->scratch1.as<int>(), (float4*)nullptr, 0);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(idx_out, c->scratch1.p, sizeof(int) * 4 * (size_t)n_hyp, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2R_OK;
+}
+
+}  // extern "C"
+
+__global__ void k_select_dummy(HSelect* sel) {
+    HSelect s;
+    s.best = 0; s.best_count = 0; s.iters_run = 0; s.pad = 0;
+    sel[0] = s;
+}
+
+extern "C" {
+
+// refine-only entry: a finalize launch whose winning sample is replaced by a caller-supplied model and mask
+int b2r_refine_h(b2r_ctx* c, const float* src, const float* dst, int32_t n, const uint8_t* mask, double* H_io,
+                 int32_t* lm_iters_out) {
+    if (!c || !src || !dst || !mask || !H_io || n < 5) return fail(B2R_ERR_ARG, "bad argument (need n > 4)%s%s");
+    int k = 0;
+    for (int i = 0; i < n; ++i) k += mask[i] != 0;
+    if (k < 4) return fail(B2R_ERR_ARG, "refinement needs at least 4 masked points%s%s");
+    CU(cudaSetDevice(c->device));
+    int rc = upload_f32_points(c, src, dst, n, c->scratch0);
+    if (rc) return rc;
+    // scratch1: [mask n][rmask n][mask_out n] ; scratch2: [H_in 9][H_out 9] doubles + sel + info
+    CU(c->scratch1.reserve(3 * (size_t)n));
+    CU(c->scratch2.reserve(sizeof(double) * 18 + sizeof(HSelect) + sizeof(int) * 12 + 64));
+    uint8_t* m_in = c->scratch1.as<uint8_t>();
+    double* H_in = c->scratch2.as<double>();
+    double* H_out = H_in + 9;
+    HSelect* sel = reinterpret_cast<HSelect*>(H_out + 9);
+    int* info = reinterpret_cast<int*>(sel + 1);
+    CU(cudaMemcpyAsync(m_in, mask, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(H_in, H_io, sizeof(double) * 9, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_select_dummy, 1, 1, 0, sel);
+    if (n >= 4096)
+        LAUNCH(c, k_finalize_h<1024>, 1, 1024, 0, c->scratch0.as<PointH>(), n, (const int*)nullptr, 1, sel, 0.f,
+               B2R_MASK_LEGACY, 1, H_out, m_in + 2 * (size_t)n, m_in + (size_t)n, info, m_in, H_in);
+    else
+        LAUNCH(c, k_finalize_h<128>, 1, 128, 0, c->scratch0.as<PointH>(), n, (const int*)nullptr, 1, sel, 0.f,
+               B2R_MASK_LEGACY, 1, H_out, m_in + 2 * (size_t)n, m_in + (size_t)n, info, m_in, H_in);
+    CU(cudaGetLastError());
+    int info_h[12];
+    CU(cudaMemcpyAsync(H_io, H_out, sizeof(double) * 9, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(info_h, info, sizeof(info_h), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (lm_iters_out) *lm_iters_out = info_h[9];
+    return B2R_OK;
+}
+
+int b2r_selftest_rcp(b2r_ctx* c, uint64_t* mismatches_out, uint64_t* tested_out) {
+    if (!c || !mismatches_out || !tested_out) return fail(B2R_ERR_ARG, "null argument%s%s");
+    CU(cudaSetDevice(c->device));
+    CU(c->scratch0.reserve(16));
+    CU(cudaMemsetAsync(c->scratch0.p, 0, 16, c->stream));
+    LAUNCH(c, k_selftest_rcp, (unsigned)(c->sm_count * 8), 256, 0, c->scratch0.as<unsigned long long>(),
+           c->scratch0.as<unsigned long long>() + 1);
+    CU(cudaGetLastError());
+    unsigned long long h[2];
+    CU(cudaMemcpyAsync(h, c->scratch0.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *mismatches_out = h[0];
+    *tested_out = h[1];
+    return B2R_OK;
+}
+
+int b2r_probe_fp32_peak(b2r_ctx* c, double* fma_per_s_out, double* ffma2_per_s_out) {
+    if (!c || !fma_per_s_out) return fail(B2R_ERR_ARG, "null argument%s%s");
+    CU(cudaSetDevice(c->device));
+    const int ctas = c->sm_count * 8, threads = 256, iters = 8192;
+    CU(c->scratch0.reserve(sizeof(float) * (size_t)ctas * threads));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    for (int packed = 0; packed < 2; ++packed) {
+        float best = 1e30f;
+        for (int r = 0; r < 8; ++r) {
+            CU(cudaEventRecord(e0, c->stream));
+            if (packed)
+                LAUNCH(c, k_probe_fma<1>, ctas, threads, 0, c->scratch0.as<float>(), iters, 1.0001f, 0.5f);
+            else
+                LAUNCH(c, k_probe_fma<0>, ctas, threads, 0, c->scratch0.as<float>(), iters, 1.0001f, 0.5f);
+            CU(cudaEventRecord(e1, c->stream));
+            CU(cudaEventSynchronize(e1));
+            float ms;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            if (r >= 3 && ms < best) best = ms;
+        }
+        const double lane_fma = (double)iters * 4 * 8 * (packed ? 2 : 1) * (double)ctas * threads;
+        if (packed) {
+            if (ffma2_per_s_out) *ffma2_per_s_out = lane_fma / (best * 1e-3);
+        } else {
+            *fma_per_s_out = lane_fma / (best * 1e-3);
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return B2R_OK;
+}
+
+}  // extern "C"

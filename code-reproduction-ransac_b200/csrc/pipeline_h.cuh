@@ -1,0 +1,662 @@
+// Kernels around K3 for the homography path: pack (A.1), K1 samplers, K2 batched solve, selection
+// (A.6) and K4 finalize = RANSAC-stage mask + refit + LM(10) + OpenCV-4.13 mask (A.7).
+// Reference call site for all of it: cv2.findHomography(..., cv2.RANSAC, thr), main_v1.py:312.
+#pragma once
+#include "sampler.cuh"
+#include "score_h.cuh"
+
+namespace b2r {
+
+// ---- S0: pack ----------------------------------------------------------------------------------------
+// (Q,n,2) fp64 src + ((n,2) | (Q,n,2)) fp64 dst  ->  (Q,n) PointH.  The fp64 -> fp32 conversion is OpenCV's
+// input quantisation: everything downstream sees the fp32 values.
+__global__ void k_pack_points_h(const double* __restrict__ src, const double* __restrict__ dst, int dst_shared, int Q,
+                                int n, PointH* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)Q * n) return;
+    const size_t j = dst_shared ? (i % n) : i;
+    PointH p;
+    p.X = (float)src[2 * i];
+    p.Y = (float)src[2 * i + 1];
+    p.nu = -(float)dst[2 * j];
+    p.nv = -(float)dst[2 * j + 1];
+    out[i] = p;
+}
+
+__global__ void k_pack_points_h_f32(const float* __restrict__ src, const float* __restrict__ dst, int n,
+                                    PointH* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PointH p;
+    p.X = src[2 * i];
+    p.Y = src[2 * i + 1];
+    p.nu = -dst[2 * i];
+    p.nv = -dst[2 * i + 1];
+    out[i] = p;
+}
+
+__device__ __forceinline__ void gather4(const PointH* __restrict__ pts, const int* idx, float* ms1, float* ms2) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(pts + idx[k]));
+        ms1[2 * k] = v.x;
+        ms1[2 * k + 1] = v.y;
+        ms2[2 * k] = -v.z;
+        ms2[2 * k + 1] = -v.w;
+    }
+}
+
+__device__ __forceinline__ void store_model(float4* __restrict__ models, size_t slot, const double* H, bool ok) {
+    float4 a, b;
+    if (ok) {
+        a = make_float4((float)H[0], (float)H[1], (float)H[2], (float)H[3]);
+        b = make_float4((float)H[4], (float)H[5], (float)H[6], (float)H[7]);
+    } else {
+        const float q = __int_as_float(0x7fc00000);  // NaN model: every error is NaN, count stays 0
+        a = make_float4(q, q, q, q);
+        b = a;
+    }
+    models[2 * slot] = a;
+    models[2 * slot + 1] = b;
+}
+
+// ---- K1 (Philox) + K2 fused: one thread per (problem, hypothesis) ----------------------------------------
+// samples : [Q][H][4] int32 (all -1: no acceptable subset in PHILOX_MAX_ATTEMPTS attempts)
+__global__ void __launch_bounds__(128)
+k_philox_sample_solve_h(const PointH* __restrict__ pts, int n, int H, long long hyp_begin, uint64_t seed,
+                        int* __restrict__ samples, float4* __restrict__ models, int solve) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.y;
+    if (g >= H) return;
+    const PointH* P = pts + (size_t)q * n;
+    const unsigned long long gid = (unsigned long long)(hyp_begin + g);
+    int idx[4] = {-1, -1, -1, -1};
+    float ms1[8], ms2[8];
+    bool found = false;
+    for (int attempt = 0; attempt < PHILOX_MAX_ATTEMPTS && !found; ++attempt) {
+        const Philox4 r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)attempt, (uint32_t)q,
+                                        (uint32_t)seed, (uint32_t)(seed >> 32));
+        distinct4(r, (uint32_t)n, idx);
+        gather4(P, idx, ms1, ms2);
+        found = h_check_subset4(ms1, ms2);
+    }
+    const size_t slot = (size_t)q * H + g;
+    if (!found) idx[0] = idx[1] = idx[2] = idx[3] = -1;
+    reinterpret_cast<int4*>(samples)[slot] = make_int4(idx[0], idx[1], idx[2], idx[3]);
+    if (solve) {
+        double Hm[9];
+        const bool ok = found && h_solve4(ms1, ms2, Hm) > 0;
+        store_model(models, slot, Hm, ok);
+    }
+}
+
+// ---- K1 (replay of cv::RNG): one thread per problem, sequential ------------------------------------------
+// samples : [Q][n_iters][4]; n_generated[q] = iterations for which a subset was produced
+__global__ void k_cv_sample_h(const PointH* __restrict__ pts, int n, int n_iters, int* __restrict__ samples,
+                              int* __restrict__ n_generated, int Q) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const PointH* P = pts + (size_t)q * n;
+    int* S = samples + (size_t)q * n_iters * 4;
+    CvRng rng;
+    rng.state = 0xffffffffffffffffull;
+    int it = 0;
+    for (; it < n_iters; ++it) {
+        int idx[4];
+        float ms1[8], ms2[8];
+        bool found = false;
+        for (int attempts = 0; attempts < CV_MAX_ATTEMPTS; ++attempts) {
+            for (int i = 0; i < 4; ++i) {
+                int idx_i;
+                bool dup;
+                do {
+                    idx_i = (int)(rng.next() % (uint32_t)n);
+                    dup = false;
+                    for (int t = 0; t < i; ++t) dup |= (idx[t] == idx_i);
+                } while (dup);
+                idx[i] = idx_i;
+            }
+            gather4(P, idx, ms1, ms2);
+            if (h_check_subset4(ms1, ms2)) {
+                found = true;
+                break;
+            }
+        }
+        if (!found) break;
+        reinterpret_cast<int4*>(S)[it] = make_int4(idx[0], idx[1], idx[2], idx[3]);
+    }
+    n_generated[q] = it;
+}
+
+// ---- K2: batched 4-point solves from stored samples -------------------------------------------------------
+// H64 (optional): [Q][H][9] fp64 models, ok (optional): [Q][H] flags, subset_ok (optional): checkSubset result
+__global__ void __launch_bounds__(128)
+k_solve_h4(const PointH* __restrict__ pts, int n, const int* __restrict__ samples, int H, const int* __restrict__ n_valid,
+           float4* __restrict__ models, double* __restrict__ H64, uint8_t* __restrict__ ok_out,
+           uint8_t* __restrict__ subset_ok) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.y;
+    if (g >= H) return;
+    const size_t slot = (size_t)q * H + g;
+    const int4 s = reinterpret_cast<const int4*>(samples)[slot];
+    const bool have = (n_valid == nullptr || g < n_valid[q]) && s.x >= 0;
+    double Hm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    bool ok = false;
+    if (have) {
+        const int idx[4] = {s.x, s.y, s.z, s.w};
+        float ms1[8], ms2[8];
+        gather4(pts + (size_t)q * n, idx, ms1, ms2);
+        if (subset_ok) subset_ok[slot] = h_check_subset4(ms1, ms2) ? 1 : 0;
+        ok = h_solve4(ms1, ms2, Hm) > 0;
+    } else if (subset_ok) {
+        subset_ok[slot] = 0;
+    }
+    if (models) store_model(models, slot, Hm, ok);
+    if (H64)
+        for (int i = 0; i < 9; ++i) H64[slot * 9 + i] = ok ? Hm[i] : 0.0;
+    if (ok_out) ok_out[slot] = ok ? 1 : 0;
+}
+
+// ---- selection ----------------------------------------------------------------------------------------------
+struct HSelect {
+    int best;        // winning iteration / local hypothesis index, -1 = none
+    int best_count;  // its RANSAC-stage inlier count
+    int iters_run;   // iterations executed
+    int pad;
+};
+
+__device__ __forceinline__ int ransac_update_num_iters(double p, double ep, int modelPoints, int maxIters) {
+    p = fmax(p, 0.);
+    p = fmin(p, 1.);
+    ep = fmax(ep, 0.);
+    ep = fmin(ep, 1.);
+    double num = fmax(1. - p, DBL_MIN);
+    double denom = 1. - pow(1. - ep, (double)modelPoints);
+    if (denom < DBL_MIN) return 0;
+    num = log(num);
+    denom = log(denom);
+    return denom >= 0 || -num >= maxIters * (-denom) ? maxIters : __double2int_rn(num / denom);
+}
+
+// OpenCV's sequential rule applied to the counts of a scored superset: walk the iterations
+// in order, take a hypothesis when its count beats max(best, modelPoints-1), shrink niters, stop at niters.
+__global__ void k_select_cv(const int* __restrict__ counts, const int* __restrict__ n_generated, int H, int n,
+                            int max_iters, double confidence, int model_points, HSelect* __restrict__ sel, int Q) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const int* C = counts + (size_t)q * H;
+    const int gen = n_generated[q];
+    int niters = max(max_iters, 1), maxGood = 0, best = -1, it = 0;
+    for (; it < niters && it < gen; ++it) {
+        const int good = C[it];
+        if (good > max(maxGood, model_points - 1)) {
+            best = it;
+            maxGood = good;
+            niters = ransac_update_num_iters(confidence, (double)(n - good) / n, model_points, niters);
+        }
+    }
+    HSelect s;
+    s.best = best;
+    s.best_count = maxGood;
+    s.iters_run = it;
+    s.pad = 0;
+    sel[q] = s;
+}
+
+// Fixed-H rule: the lowest-id hypothesis with the maximum count; key = count << 32 | (0xFFFFFFFF - id).
+__global__ void __launch_bounds__(256)
+k_argmax_key(const int* __restrict__ counts, int H, unsigned long long id_base, unsigned long long* __restrict__ keys) {
+    const int q = blockIdx.y;
+    const int* C = counts + (size_t)q * H;
+    unsigned long long best = 0;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < H; g += gridDim.x * blockDim.x) {
+        const unsigned long long key =
+            ((unsigned long long)(uint32_t)C[g] << 32) | (0xFFFFFFFFull - ((id_base + (unsigned long long)g) & 0xFFFFFFFFull));
+        best = key > best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_down_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(keys + q, best);
+}
+
+__global__ void k_select_from_keys(const unsigned long long* __restrict__ keys, unsigned long long id_base, int H,
+                                   int model_points, HSelect* __restrict__ sel, int Q) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const unsigned long long key = keys[q];
+    const int count = (int)(key >> 32);
+    const unsigned long long gid = 0xFFFFFFFFull - (key & 0xFFFFFFFFull);
+    HSelect s;
+    s.best = count > model_points - 1 ? (int)(gid - (id_base & 0xFFFFFFFFull)) : -1;
+    s.best_count = count > model_points - 1 ? count : 0;
+    s.iters_run = H;
+    s.pad = 0;
+    sel[q] = s;
+}
+
+// ---- K4 finalize -----------------------------------------------------------------------------------------------
+// exact fp32 squared reprojection error of one point, scalar form
+__device__ __forceinline__ float h_err_exact(const float* Hf, float X, float Y, float nu, float nv) {
+    const float w = __fadd_rn(__fadd_rn(__fmul_rn(Hf[6], X), __fmul_rn(Hf[7], Y)), 1.f);
+    const float ww = rcp_rn(w);
+    const float dx = __fadd_rn(__fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(Hf[0], X), __fmul_rn(Hf[1], Y)), Hf[2]), ww), nu);
+    const float dy = __fadd_rn(__fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(Hf[3], X), __fmul_rn(Hf[4], Y)), Hf[5]), ww), nv);
+    return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+
+// Deterministic CTA-wide sum of NV doubles per thread; result in out[0..NV) (shared), valid after return.
+template <int THREADS, int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch /* [THREADS/32][NV] */, double* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) scratch[warp * NV + i] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0;
+        for (int w = 0; w < THREADS / 32; ++w) s += scratch[w * NV + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+template <int THREADS>
+__device__ __forceinline__ double block_max(double x, double* scratch, double* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_down_sync(0xffffffffu, x, o));
+    if (lane == 0) scratch[warp] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int w = 0; w < THREADS / 32; ++w) s = fmax(s, scratch[w]);
+        out[0] = s;
+    }
+    __syncthreads();
+    return out[0];
+}
+
+// x = solve(A, b), A symmetric n x n, through its Jacobi eigen-decomposition with OpenCV's
+// back-substitution threshold (cv::solve DECOMP_EIG); optionally the diagonal of A^-1.
+template <int N>
+__device__ void solve_sym_eig(const double* A, const double* b, double* x, double* inv_diag) {
+    double a[N * N], W[N], V[N * N];
+    for (int i = 0; i < N * N; ++i) a[i] = A[i];
+    jacobi_eig<N>(a, W, V);
+    double thr = 0;
+    for (int i = 0; i < N; ++i) thr += fabs(W[i]);
+    thr *= DBL_EPSILON * 2;
+    for (int j = 0; j < N; ++j) {
+        if (x) x[j] = 0;
+        if (inv_diag) inv_diag[j] = 0;
+    }
+    for (int i = 0; i < N; ++i) {
+        if (fabs(W[i]) <= thr) continue;
+        if (x) {
+            double s = 0;
+            for (int j = 0; j < N; ++j) s += V[i * N + j] * b[j];
+            s /= W[i];
+            for (int j = 0; j < N; ++j) x[j] += s * V[i * N + j];
+        }
+        if (inv_diag)
+            for (int j = 0; j < N; ++j) inv_diag[j] += V[i * N + j] * V[i * N + j] / W[i];
+    }
+}
+
+struct HFinalizeShared {
+    double red[64];       // block_sum output
+    double H[9];          // current model (fp64)
+    double x[8], xd[8];   // LM parameter vectors
+    double A[64], v[8], D[8], d[8];
+    double S, Sd, lambda, lc, rmax;
+    float Hf[8];
+    int flag, k, lm_iters, proceed;
+};
+
+// residual/Jacobian accumulation of one inlier for the LM refinement
+__device__ __forceinline__ void lm_point(const double* h, double Mx, double My, double mx, double my, double& rx,
+                                         double& ry, double* Jx, double* Jy) {
+    double ww = h[6] * Mx + h[7] * My + 1.;
+    ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
+    const double xi = (h[0] * Mx + h[1] * My + h[2]) * ww;
+    const double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
+    rx = xi - mx;
+    ry = yi - my;
+    if (Jx) {
+        Jx[0] = Mx * ww; Jx[1] = My * ww; Jx[2] = ww; Jx[3] = -Mx * ww * xi; Jx[4] = -My * ww * xi;
+        Jy[0] = Mx * ww; Jy[1] = My * ww; Jy[2] = ww; Jy[3] = -Mx * ww * yi; Jy[4] = -My * ww * yi;
+    }
+}
+
+// One CTA per problem.
+//   sel        : selection result; best < 0 -> no model
+//   samples    : [Q][Hs][4] minimal samples (index sel.best)
+//   rmask      : [Q][n] workspace/RANSAC-stage mask output
+//   H_out      : [Q][9], mask_out : [Q][n], info : [Q] (b2r_h_info layout = 12 int32)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samples, int Hs,
+             const HSelect* __restrict__ sel, float thr_sq, int mask_semantics, int refine,
+             double* __restrict__ H_out, uint8_t* __restrict__ mask_out, uint8_t* __restrict__ rmask_out,
+             int* __restrict__ info, const uint8_t* __restrict__ ext_mask, const double* __restrict__ ext_H) {
+    __shared__ HFinalizeShared sh;
+    __shared__ double scratch[(THREADS / 32) * 45];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const PointH* P = pts + (size_t)q * n;
+    uint8_t* rmask = rmask_out + (size_t)q * n;
+    uint8_t* mask = mask_out + (size_t)q * n;
+    const HSelect s = sel[q];
+    int* inf = info + (size_t)q * 12;
+
+    if (s.best < 0) {  // no model: cv2 returns (None, zeros)
+        for (int i = tid; i < n; i += THREADS) { mask[i] = 0; rmask[i] = 0; }
+        if (tid < 9) H_out[(size_t)q * 9 + tid] = 0;
+        if (tid == 0) {
+            inf[0] = 1; inf[1] = s.iters_run; inf[2] = -1; inf[3] = 0;
+            inf[4] = inf[5] = inf[6] = inf[7] = -1; inf[8] = 0; inf[9] = 0; inf[10] = 0; inf[11] = 0;
+        }
+        return;
+    }
+    const int4 smp = ext_mask ? make_int4(-1, -1, -1, -1) : reinterpret_cast<const int4*>(samples)[(size_t)q * Hs + s.best];
+    if (tid == 0) {
+        double Hm[9];
+        if (ext_mask) {  // refine-only entry (b2r_refine_h): the caller supplies the model and the inlier mask
+            for (int i = 0; i < 9; ++i) Hm[i] = ext_H[(size_t)q * 9 + i];
+        } else {
+            const int idx[4] = {smp.x, smp.y, smp.z, smp.w};
+            float ms1[8], ms2[8];
+            gather4(P, idx, ms1, ms2);
+            h_solve4(ms1, ms2, Hm);
+        }
+        for (int i = 0; i < 9; ++i) sh.H[i] = Hm[i];
+        for (int i = 0; i < 8; ++i) sh.Hf[i] = (float)Hm[i];
+        sh.lm_iters = 0;
+    }
+    __syncthreads();
+
+    // RANSAC-stage mask with the winning minimal model
+    int k_local = 0;
+    for (int i = tid; i < n; i += THREADS) {
+        uint8_t f;
+        if (ext_mask) {
+            f = ext_mask[(size_t)q * n + i] ? 1 : 0;
+        } else {
+            const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
+            f = h_err_exact(sh.Hf, p.x, p.y, p.z, p.w) <= thr_sq ? 1 : 0;
+        }
+        rmask[i] = f;
+        k_local += f;
+    }
+    {
+        double kv[1] = {(double)k_local};
+        block_sum<THREADS, 1>(kv, scratch, sh.red);
+        if (tid == 0) sh.k = (int)sh.red[0];
+        __syncthreads();
+    }
+    const int k = sh.k;
+
+    if (refine && n > 4 && k >= 4) {
+        // ---- refit on the inliers: normalisation statistics, L^T L, eigenvector -------------------------
+        HNorm nm;
+        {
+            double c[4] = {0, 0, 0, 0};
+            for (int i = tid; i < n; i += THREADS)
+                if (rmask[i]) {
+                    const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
+                    c[0] += (double)(-p.z); c[1] += (double)(-p.w); c[2] += (double)p.x; c[3] += (double)p.y;
+                }
+            block_sum<THREADS, 4>(c, scratch, sh.red);
+            nm.cmx = sh.red[0] / k; nm.cmy = sh.red[1] / k; nm.cMx = sh.red[2] / k; nm.cMy = sh.red[3] / k;
+            __syncthreads();
+            double a[4] = {0, 0, 0, 0};
+            for (int i = tid; i < n; i += THREADS)
+                if (rmask[i]) {
+                    const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
+                    a[0] += fabs((double)(-p.z) - nm.cmx); a[1] += fabs((double)(-p.w) - nm.cmy);
+                    a[2] += fabs((double)p.x - nm.cMx); a[3] += fabs((double)p.y - nm.cMy);
+                }
+            block_sum<THREADS, 4>(a, scratch, sh.red);
+            nm.smx = sh.red[0]; nm.smy = sh.red[1]; nm.sMx = sh.red[2]; nm.sMy = sh.red[3];
+            __syncthreads();
+        }
+        const bool degenerate = fabs(nm.smx) < DBL_EPSILON || fabs(nm.smy) < DBL_EPSILON ||
+                                fabs(nm.sMx) < DBL_EPSILON || fabs(nm.sMy) < DBL_EPSILON;
+        if (!degenerate) {
+            nm.smx = k / nm.smx; nm.smy = k / nm.smy; nm.sMx = k / nm.sMx; nm.sMy = k / nm.sMy;
+            // 45 unique entries of the symmetric 9x9; only 2x2 products of (X, Y, 1, x, y) are needed
+            double L[45];
+#pragma unroll
+            for (int j = 0; j < 45; ++j) L[j] = 0;
+            for (int i = tid; i < n; i += THREADS)
+                if (rmask[i]) {
+                    const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
+                    const double x = ((double)(-p.z) - nm.cmx) * nm.smx, y = ((double)(-p.w) - nm.cmy) * nm.smy;
+                    const double X = ((double)p.x - nm.cMx) * nm.sMx, Y = ((double)p.y - nm.cMy) * nm.sMy;
+                    const double Lx[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x};
+                    const double Ly[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
+                    int e = 0;
+#pragma unroll
+                    for (int j = 0; j < 9; ++j)
+#pragma unroll
+                        for (int kk = j; kk < 9; ++kk) L[e++] += Lx[j] * Lx[kk] + Ly[j] * Ly[kk];
+                }
+            block_sum<THREADS, 45>(L, scratch, sh.red);
+            if (tid == 0) {
+                double LtL[81];
+                int e = 0;
+                for (int j = 0; j < 9; ++j)
+                    for (int kk = j; kk < 9; ++kk) LtL[j * 9 + kk] = sh.red[e++];
+                double Hm[9];
+                h_from_LtL(LtL, nm, Hm);
+                for (int i = 0; i < 9; ++i) sh.H[i] = Hm[i];
+            }
+            __syncthreads();
+        }
+
+        // ---- Levenberg-Marquardt, max 10 iterations, eps = FLT_EPSILON (cv::LMSolver) ---------------------
+        // accumulators per thread: S, 36 unique entries of J^T J, 8 of J^T r
+        auto eval = [&](const double* h, bool want_J) {
+            double acc[45];
+#pragma unroll
+            for (int j = 0; j < 45; ++j) acc[j] = 0;
+            double rmax = 0;
+            for (int i = tid; i < n; i += THREADS)
+                if (rmask[i]) {
+                    const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
+                    double rx, ry, Jx[5], Jy[5];
+                    lm_point(h, (double)p.x, (double)p.y, (double)(-p.z), (double)(-p.w), rx, ry, want_J ? Jx : nullptr,
+                             want_J ? Jy : nullptr);
+                    acc[0] += rx * rx + ry * ry;
+                    rmax = fmax(rmax, fmax(fabs(rx), fabs(ry)));
+                    if (want_J) {
+                        // full rows: Jx = [a0 a1 a2 0 0 0 a3 a4], Jy = [0 0 0 b0 b1 b2 b3 b4]
+                        const double jx[8] = {Jx[0], Jx[1], Jx[2], 0, 0, 0, Jx[3], Jx[4]};
+                        const double jy[8] = {0, 0, 0, Jy[0], Jy[1], Jy[2], Jy[3], Jy[4]};
+                        int e = 1;
+#pragma unroll
+                        for (int a = 0; a < 8; ++a)
+#pragma unroll
+                            for (int b = a; b < 8; ++b) acc[e++] += jx[a] * jx[b] + jy[a] * jy[b];
+#pragma unroll
+                        for (int a = 0; a < 8; ++a) acc[37 + a] += jx[a] * rx + jy[a] * ry;
+                    }
+                }
+            block_sum<THREADS, 45>(acc, scratch, sh.red);
+            const double S = sh.red[0];
+            if (want_J && tid == 0) {
+                int e = 1;
+                for (int a = 0; a < 8; ++a)
+                    for (int b = a; b < 8; ++b) {
+                        sh.A[a * 8 + b] = sh.red[e];
+                        sh.A[b * 8 + a] = sh.red[e];
+                        ++e;
+                    }
+                for (int a = 0; a < 8; ++a) sh.v[a] = sh.red[37 + a];
+            }
+            __syncthreads();
+            const double rm = block_max<THREADS>(rmax, scratch, &sh.red[63]);
+            return make_double2(S, rm);
+        };
+
+        if (tid == 0)
+            for (int i = 0; i < 8; ++i) sh.x[i] = sh.H[i];
+        __syncthreads();
+        {
+            const double2 e0 = eval(sh.x, true);
+            if (tid == 0) {
+                sh.S = e0.x; sh.rmax = e0.y;
+                for (int i = 0; i < 8; ++i) sh.D[i] = sh.A[i * 8 + i];
+                sh.lambda = 1; sh.lc = 0.75;
+            }
+            __syncthreads();
+        }
+        for (int iter = 0;;) {
+            if (tid == 0) {
+                double Ap[64];
+                for (int i = 0; i < 64; ++i) Ap[i] = sh.A[i];
+                for (int i = 0; i < 8; ++i) Ap[i * 8 + i] += sh.lambda * sh.D[i];
+                solve_sym_eig<8>(Ap, sh.v, sh.d, nullptr);
+                for (int i = 0; i < 8; ++i) sh.xd[i] = sh.x[i] - sh.d[i];
+            }
+            __syncthreads();
+            const double2 ed = eval(sh.xd, false);
+            if (tid == 0) {
+                const double Sd = ed.x, S = sh.S;
+                double dS = 0;
+                for (int i = 0; i < 8; ++i) {
+                    double t = 0;
+                    for (int j = 0; j < 8; ++j) t += sh.A[i * 8 + j] * sh.d[j];
+                    dS += sh.d[i] * (2 * sh.v[i] - t);
+                }
+                const double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
+                if (R > 0.75) {
+                    sh.lambda *= 0.5;
+                    if (sh.lambda < sh.lc) sh.lambda = 0;
+                } else if (R < 0.25) {
+                    double t = 0;
+                    for (int i = 0; i < 8; ++i) t += sh.d[i] * sh.v[i];
+                    double nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1) + 2;
+                    nu = fmin(fmax(nu, 2.), 10.);
+                    if (sh.lambda == 0) {
+                        double diag[8], maxval = DBL_EPSILON;
+                        solve_sym_eig<8>(sh.A, nullptr, nullptr, diag);
+                        for (int i = 0; i < 8; ++i) maxval = fmax(maxval, fabs(diag[i]));
+                        sh.lambda = sh.lc = 1. / maxval;
+                        nu *= 0.5;
+                    }
+                    sh.lambda *= nu;
+                }
+                sh.flag = Sd < S;
+                if (sh.flag) {
+                    sh.S = Sd;
+                    for (int i = 0; i < 8; ++i) sh.x[i] = sh.xd[i];
+                }
+            }
+            __syncthreads();
+            if (sh.flag) {
+                const double2 e1 = eval(sh.x, true);
+                if (tid == 0) sh.rmax = e1.y;
+            }
+            ++iter;
+            if (tid == 0) {
+                double dmax = 0;
+                for (int i = 0; i < 8; ++i) dmax = fmax(dmax, fabs(sh.d[i]));
+                sh.proceed = iter < 10 && dmax >= (double)FLT_EPSILON && sh.rmax >= (double)FLT_EPSILON;
+                sh.lm_iters = iter;
+            }
+            __syncthreads();
+            if (!sh.proceed) break;
+        }
+        if (tid == 0) {
+            for (int i = 0; i < 8; ++i) sh.H[i] = sh.x[i];
+            for (int i = 0; i < 8; ++i) sh.Hf[i] = (float)sh.x[i];
+        }
+        __syncthreads();
+    }
+
+    // ---- outputs ---------------------------------------------------------------------------------------------
+    int n_inl = 0;
+    if (mask_semantics == 0 && n > 4 && refine) {
+        for (int i = tid; i < n; i += THREADS) {
+            const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
+            const uint8_t f = h_err_exact(sh.Hf, p.x, p.y, p.z, p.w) <= thr_sq ? 1 : 0;
+            mask[i] = f;
+            n_inl += f;
+        }
+    } else {
+        for (int i = tid; i < n; i += THREADS) {
+            const uint8_t f = rmask[i];
+            mask[i] = f;
+            n_inl += f;
+        }
+    }
+    {
+        double kv[1] = {(double)n_inl};
+        block_sum<THREADS, 1>(kv, scratch, sh.red);
+    }
+    if (tid < 9) H_out[(size_t)q * 9 + tid] = sh.H[tid];
+    if (tid == 0) {
+        inf[0] = 0; inf[1] = s.iters_run; inf[2] = s.best; inf[3] = k;
+        inf[4] = smp.x; inf[5] = smp.y; inf[6] = smp.z; inf[7] = smp.w;
+        inf[8] = (int)sh.red[0]; inf[9] = sh.lm_iters; inf[10] = 0; inf[11] = 0;
+    }
+}
+
+// ---- self tests / probes -----------------------------------------------------------------------------------------
+__global__ void k_selftest_rcp(unsigned long long* mismatches, unsigned long long* tested) {
+    unsigned long long bad = 0, cnt = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < (1ull << 32); b += stride) {
+        const float x = __uint_as_float((uint32_t)b);
+        if (!rcp_rn_in_fast_range(x)) continue;
+        const float r0 = rcp_rn_fast_range(x), r1 = __frcp_rn(x);
+        ++cnt;
+        if (__float_as_uint(r0) != __float_as_uint(r1)) ++bad;
+    }
+    atomicAdd(mismatches, bad);
+    atomicAdd(tested, cnt);
+}
+
+template <int PACKED>
+__global__ void __launch_bounds__(256) k_probe_fma(float* out, int iters, float a, float b) {
+    constexpr int ILP = 8;
+    float acc = 0.f;
+    if (PACKED) {
+        f2_t x[ILP];
+        const f2_t a2 = f2_pack(a, a * 1.0001f), b2 = f2_pack(b, b * 0.999f);
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) x[i] = f2_pack(a + (float)(threadIdx.x + i), b + (float)i);
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < ILP; ++i) x[i] = f2_fma(x[i], a2, b2);
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            float lo, hi;
+            f2_unpack(x[i], lo, hi);
+            acc += lo + hi;
+        }
+    } else {
+        float x[ILP];
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) x[i] = a + (float)(threadIdx.x + i);
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < ILP; ++i) x[i] = __fmaf_rn(x[i], a, b);
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) acc += x[i];
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+}  // namespace b2r

@@ -67,31 +67,40 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
         : "memory");
 }
 
+// a + b where a (and possibly b) is the result of a packed multiply: scalar adds, never contracted
+__device__ __forceinline__ f2_t f2_sum_of_products(f2_t a, f2_t b) {
+    float a0, a1, b0, b1;
+    f2_unpack(a, a0, a1);
+    f2_unpack(b, b0, b1);
+    return f2_pack(__fadd_rn(a0, b0), __fadd_rn(a1, b1));
+}
+
 template <bool EXACT>
 struct HEval {
     // Returns the packed squared reprojection error of one point against two hypotheses.
     __device__ __forceinline__ static f2_t err(const f2_t (&h)[8], f2_t X, f2_t Y, f2_t nu, f2_t nv, f2_t one) {
         if (EXACT) {
-            f2_t w = f2_add(f2_add(f2_mul(h[6], X), f2_mul(h[7], Y)), one);
+            // ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false (the scalar
+            // mul.rn.f32 / add.rn.f32 pair is never contracted).  So: products are packed (FMUL2), every sum that
+            // consumes a product directly is done with scalar __fadd_rn on the two halves, and only sums of sums
+            // are packed (FADD2).  tests/test_gpu_parity_h.py holds the counts to the un-fused CPU sequence.
+            const f2_t w = f2_add(f2_sum_of_products(f2_mul(h[6], X), f2_mul(h[7], Y)), one);
             float w0, w1;
             f2_unpack(w, w0, w1);
             f2_t ww;
             if (__builtin_expect(rcp_rn_in_fast_range(w0) && rcp_rn_in_fast_range(w1), 1)) {
-                f2_t y = f2_pack(rcp_approx(w0), rcp_approx(w1));
-                // e = 1 - w*y computed as -(w*y - 1): the sign flip is exact, so y + y*e is evaluated
-                // as fma(-y... ) is avoided by negating e through the (exact) product sign instead.
-                float y0, y1;
-                f2_unpack(y, y0, y1);
-                float e0 = __fmaf_rn(-w0, y0, 1.0f), e1 = __fmaf_rn(-w1, y1, 1.0f);
-                ww = f2_fma(y, f2_pack(e0, e1), y);
+                // one Newton step on the MUFU seed: y + y*(1 - w*y), correctly rounded in the fast range
+                const float y0 = rcp_approx(w0), y1 = rcp_approx(w1);
+                const float e0 = __fmaf_rn(-w0, y0, 1.0f), e1 = __fmaf_rn(-w1, y1, 1.0f);
+                ww = f2_pack(__fmaf_rn(y0, e0, y0), __fmaf_rn(y1, e1, y1));
             } else {
                 ww = f2_pack(__frcp_rn(w0), __frcp_rn(w1));
             }
-            f2_t sx = f2_add(f2_add(f2_mul(h[0], X), f2_mul(h[1], Y)), h[2]);
-            f2_t sy = f2_add(f2_add(f2_mul(h[3], X), f2_mul(h[4], Y)), h[5]);
-            f2_t dx = f2_add(f2_mul(sx, ww), nu);
-            f2_t dy = f2_add(f2_mul(sy, ww), nv);
-            return f2_add(f2_mul(dx, dx), f2_mul(dy, dy));
+            const f2_t sx = f2_add(f2_sum_of_products(f2_mul(h[0], X), f2_mul(h[1], Y)), h[2]);
+            const f2_t sy = f2_add(f2_sum_of_products(f2_mul(h[3], X), f2_mul(h[4], Y)), h[5]);
+            const f2_t dx = f2_sum_of_products(f2_mul(sx, ww), nu);
+            const f2_t dy = f2_sum_of_products(f2_mul(sy, ww), nv);
+            return f2_sum_of_products(f2_mul(dx, dx), f2_mul(dy, dy));
         } else {
             f2_t w = f2_fma(h[6], X, f2_fma(h[7], Y, one));
             float w0, w1;
@@ -106,14 +115,17 @@ struct HEval {
     }
 };
 
-// models : [H][8] fp32 (h0..h7, h8 == 1 implied), 32-byte aligned rows
-// pts    : [N] PointH
-// counts : [H] int32, must be zeroed by the caller; each CTA adds its tile's inlier counts
-// grid   : x = ceil(H / (K3_THREADS*2*NPAIR)), y = ceil(N / tile_pts); dynamic smem = 128 + tile_pts*16
+// models : [Q][H][8] fp32 (h0..h7, h8 == 1 implied), 32-byte aligned rows
+// pts    : [Q][N] PointH
+// counts : [Q][H] int32, must be zeroed by the caller; each CTA adds its tile's inlier counts
+// grid   : x = ceil(H / (K3_THREADS*2*NPAIR)), y = ceil(N / tile_pts), z = Q; dynamic smem = 128 + tile_pts*16
 template <int NPAIR, bool EXACT>
 __global__ void __launch_bounds__(K3_THREADS, 2)
 k3_score_h(const float4* __restrict__ models, int H, const PointH* __restrict__ pts, int N, float thr,
            int* __restrict__ counts, int tile_pts) {
+    models += (size_t)blockIdx.z * H * 2;
+    pts += (size_t)blockIdx.z * N;
+    counts += (size_t)blockIdx.z * H;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     const float4* tile = reinterpret_cast<const float4*>(smem_raw + 128);

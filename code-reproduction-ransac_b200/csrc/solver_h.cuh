@@ -1,0 +1,241 @@
+// K2 — minimal (4-point) and k-point homography solver, fp64, one thread per hypothesis.
+//
+// Device-side counterpart of OpenCV's HomographyEstimatorCallback::runKernel, the solver that
+// cv2.findHomography(..., cv2.RANSAC, thr) (reference: main_v1.py:312) runs once per RANSAC
+// iteration: per-axis L1-normalised DLT, 9x9 L^T L, symmetric Jacobi eigen-solver (OpenCV's own
+// cyclic-by-max-pivot scheme), smallest eigenvector, de-normalise, scale by
+// 1/H[2][2].  The whole translation unit is compiled with -fmad=false and uses only IEEE
+// + - * / sqrt in fp64, in the reference's operation order, so the 4-point model is bit-identical
+// to the CPU result (tests/test_gpu_parity.py checks that against the oracle).
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+namespace b2r {
+
+__device__ __forceinline__ double cv_hypot(double a, double b) {
+    a = fabs(a);
+    b = fabs(b);
+    if (a > b) {
+        b /= a;
+        return a * sqrt(1 + b * b);
+    }
+    if (b > 0) {
+        a /= b;
+        return b * sqrt(1 + a * a);
+    }
+    return 0;
+}
+
+// Symmetric eigen-decomposition, n <= 9.  A (n*n, row-major, destroyed), W eigenvalues descending,
+// V rows = eigenvectors.  Pivot choice, rotation formulas and tie-breaks follow SURVEY.md A.4.
+template <int N>
+__device__ void jacobi_eig(double* A, double* W, double* V) {
+    int indR[N], indC[N];
+    int i, k, l, m;
+    for (i = 0; i < N * N; i++) V[i] = 0;
+    for (i = 0; i < N; i++) V[i * N + i] = 1;
+    for (k = 0; k < N; k++) {
+        W[k] = A[k * N + k];
+        if (k < N - 1) {
+            double mv = fabs(A[k * N + k + 1]);
+            m = k + 1;
+            for (i = k + 2; i < N; i++) {
+                double val = fabs(A[k * N + i]);
+                if (mv < val) mv = val, m = i;
+            }
+            indR[k] = m;
+        }
+        if (k > 0) {
+            double mv = fabs(A[k]);
+            m = 0;
+            for (i = 1; i < k; i++) {
+                double val = fabs(A[i * N + k]);
+                if (mv < val) mv = val, m = i;
+            }
+            indC[k] = m;
+        }
+    }
+    for (int it = 0; it < N * N * 30; it++) {
+        double mv = fabs(A[indR[0]]);
+        k = 0;
+        for (i = 1; i < N - 1; i++) {
+            double val = fabs(A[i * N + indR[i]]);
+            if (mv < val) mv = val, k = i;
+        }
+        l = indR[k];
+        for (i = 1; i < N; i++) {
+            double val = fabs(A[indC[i] * N + i]);
+            if (mv < val) mv = val, k = indC[i], l = i;
+        }
+        double p = A[k * N + l];
+        if (fabs(p) <= DBL_EPSILON) break;
+        double y = (W[l] - W[k]) * 0.5;
+        double t = fabs(y) + cv_hypot(p, y);
+        double s = cv_hypot(p, t);
+        double c = t / s;
+        s = p / s;
+        t = (p / t) * p;
+        if (y < 0) s = -s, t = -t;
+        A[k * N + l] = 0;
+        W[k] -= t;
+        W[l] += t;
+#define B2R_ROT(v0, v1)            \
+    {                              \
+        double a0 = (v0), b0 = (v1); \
+        (v0) = a0 * c - b0 * s;    \
+        (v1) = a0 * s + b0 * c;    \
+    }
+        for (i = 0; i < k; i++) B2R_ROT(A[i * N + k], A[i * N + l]);
+        for (i = k + 1; i < l; i++) B2R_ROT(A[k * N + i], A[i * N + l]);
+        for (i = l + 1; i < N; i++) B2R_ROT(A[k * N + i], A[l * N + i]);
+        for (i = 0; i < N; i++) B2R_ROT(V[k * N + i], V[l * N + i]);
+#undef B2R_ROT
+        for (int j = 0; j < 2; j++) {
+            int idx = j == 0 ? k : l;
+            if (idx < N - 1) {
+                mv = fabs(A[idx * N + idx + 1]);
+                m = idx + 1;
+                for (i = idx + 2; i < N; i++) {
+                    double val = fabs(A[idx * N + i]);
+                    if (mv < val) mv = val, m = i;
+                }
+                indR[idx] = m;
+            }
+            if (idx > 0) {
+                mv = fabs(A[idx]);
+                m = 0;
+                for (i = 1; i < idx; i++) {
+                    double val = fabs(A[i * N + idx]);
+                    if (mv < val) mv = val, m = i;
+                }
+                indC[idx] = m;
+            }
+        }
+    }
+    for (k = 0; k < N - 1; k++) {
+        m = k;
+        for (i = k + 1; i < N; i++)
+            if (W[m] < W[i]) m = i;
+        if (k != m) {
+            double tmp = W[m];
+            W[m] = W[k];
+            W[k] = tmp;
+            for (i = 0; i < N; i++) {
+                tmp = V[m * N + i];
+                V[m * N + i] = V[k * N + i];
+                V[k * N + i] = tmp;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void mat3_mul(const double* a, const double* b, double* o) {
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double s = 0.0;
+            for (int k = 0; k < 3; k++) s += a[i * 3 + k] * b[k * 3 + j];
+            o[i * 3 + j] = s;
+        }
+}
+
+// Normalisation statistics of a point set: centroids and inverse mean absolute deviations.
+struct HNorm {
+    double cMx, cMy, cmx, cmy;  // centroids of src (M) and dst (m)
+    double sMx, sMy, smx, smy;  // count / sum |coord - centroid|
+};
+
+// L^T L (full 9x9, upper triangle accumulated then mirrored by the caller) -> H.  Returns false when
+// the normalisation is degenerate.  LtL is destroyed.
+__device__ __forceinline__ void h_from_LtL(double* LtL, const HNorm& nm, double* H) {
+    double W[9], V[81];
+    for (int j = 0; j < 9; j++)
+        for (int k = 0; k < j; k++) LtL[j * 9 + k] = LtL[k * 9 + j];
+    jacobi_eig<9>(LtL, W, V);
+    const double invHnorm[9] = {1. / nm.smx, 0, nm.cmx, 0, 1. / nm.smy, nm.cmy, 0, 0, 1};
+    const double Hnorm2[9] = {nm.sMx, 0, -nm.cMx * nm.sMx, 0, nm.sMy, -nm.cMy * nm.sMy, 0, 0, 1};
+    double Ht[9], H0[9];
+    mat3_mul(invHnorm, V + 72, Ht);
+    mat3_mul(Ht, Hnorm2, H0);
+    const double sc = 1. / H0[8];
+    for (int i = 0; i < 9; i++) H[i] = H0[i] * sc;
+}
+
+__device__ __forceinline__ void h_accumulate_LtL(double* LtL, const HNorm& nm, double Mx, double My, double mx,
+                                                 double my) {
+    const double x = (mx - nm.cmx) * nm.smx, y = (my - nm.cmy) * nm.smy;
+    const double X = (Mx - nm.cMx) * nm.sMx, Y = (My - nm.cMy) * nm.sMy;
+    const double Lx[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x};
+    const double Ly[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
+    for (int j = 0; j < 9; j++)
+        for (int k = j; k < 9; k++) LtL[j * 9 + k] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+}
+
+// 4-point solve.  M = src (x,y) x4, m = dst (x,y) x4 as fp32.  Returns 1 model or 0.
+__device__ int h_solve4(const float* M, const float* m, double* H) {
+    HNorm nm = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int count = 4;
+    for (int i = 0; i < count; i++) {
+        nm.cmx += m[2 * i];
+        nm.cmy += m[2 * i + 1];
+        nm.cMx += M[2 * i];
+        nm.cMy += M[2 * i + 1];
+    }
+    nm.cmx /= count;
+    nm.cmy /= count;
+    nm.cMx /= count;
+    nm.cMy /= count;
+    for (int i = 0; i < count; i++) {
+        nm.smx += fabs(m[2 * i] - nm.cmx);
+        nm.smy += fabs(m[2 * i + 1] - nm.cmy);
+        nm.sMx += fabs(M[2 * i] - nm.cMx);
+        nm.sMy += fabs(M[2 * i + 1] - nm.cMy);
+    }
+    if (fabs(nm.smx) < DBL_EPSILON || fabs(nm.smy) < DBL_EPSILON || fabs(nm.sMx) < DBL_EPSILON ||
+        fabs(nm.sMy) < DBL_EPSILON)
+        return 0;
+    nm.smx = count / nm.smx;
+    nm.smy = count / nm.smy;
+    nm.sMx = count / nm.sMx;
+    nm.sMy = count / nm.sMy;
+    double LtL[81];
+    for (int i = 0; i < 81; i++) LtL[i] = 0;
+    for (int i = 0; i < count; i++) h_accumulate_LtL(LtL, nm, M[2 * i], M[2 * i + 1], m[2 * i], m[2 * i + 1]);
+    h_from_LtL(LtL, nm, H);
+    return 1;
+}
+
+// -- degeneracy test of a 4-point sample (checkSubset) -------------------------------
+__device__ __forceinline__ bool have_collinear4(const float* p) {
+    const int i = 3;
+    for (int j = 0; j < i; j++) {
+        const double dx1 = __fsub_rn(p[2 * j], p[2 * i]);
+        const double dy1 = __fsub_rn(p[2 * j + 1], p[2 * i + 1]);
+        for (int k = 0; k < j; k++) {
+            const double dx2 = __fsub_rn(p[2 * k], p[2 * i]);
+            const double dy2 = __fsub_rn(p[2 * k + 1], p[2 * i + 1]);
+            if (fabs(dx2 * dy1 - dy2 * dx1) <= FLT_EPSILON * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2)))
+                return true;
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ double det3_pts(const float* p, int a, int b, int c) {
+    const double a00 = p[2 * a], a01 = p[2 * a + 1], a10 = p[2 * b], a11 = p[2 * b + 1], a20 = p[2 * c],
+                 a21 = p[2 * c + 1];
+    return a00 * (a11 * 1. - a21 * 1.) - a01 * (a10 * 1. - a20 * 1.) + 1. * (a10 * a21 - a20 * a11);
+}
+
+__device__ __forceinline__ bool h_check_subset4(const float* ms1, const float* ms2) {
+    if (have_collinear4(ms1) || have_collinear4(ms2)) return false;
+    int negative = 0;
+    negative += det3_pts(ms1, 0, 1, 2) * det3_pts(ms2, 0, 1, 2) < 0;
+    negative += det3_pts(ms1, 1, 2, 3) * det3_pts(ms2, 1, 2, 3) < 0;
+    negative += det3_pts(ms1, 0, 2, 3) * det3_pts(ms2, 0, 2, 3) < 0;
+    negative += det3_pts(ms1, 0, 1, 3) * det3_pts(ms2, 0, 1, 3) < 0;
+    return negative == 0 || negative == 4;
+}
+
+}  // namespace b2r

@@ -1,0 +1,157 @@
+/*
+ * ransac_b200 — C ABI of the B200 (sm_100a) RANSAC camera-location hot path.
+ *
+ * Drop-in boundary.  The reference (Mendel0408/Code-Reproduction-RANSAC) has no FFI of its own: its hot
+ * path is two calls into the cv2 Python binding of OpenCV calib3d,
+ *
+ *     M, mask = cv2.findHomography(pos2[good == 1], pixels[good == 1], cv2.RANSAC, ransacbound)
+ *                                   /root/reference/main_v1.py:312   (process.py:200, testpro.py:350,
+ *                                                                     test_pro.py:351, test02.py:263)
+ *     ok, rvec, tvec, inliers = cv2.solvePnPRansac(pos3d, pixels, K, dist, iterationsCount=5000,
+ *                                   reprojectionError=30.0, confidence=0.99)
+ *                                   /root/reference/main_v1.py:497-502 (testpro.py:536, test_pro.py:515,
+ *                                                                     testpro-K.py:72-75)
+ *
+ * so the entry points below are what a binding for those two calls (and for the loop around the first one,
+ * find_homographies, main_v1.py:254-297) would bind.  Plain pointers and sizes only; no torch, numpy or
+ * OpenCV types.  INTEGRATION.md shows the ctypes stub that replaces the cv2 attribute lookups.
+ *
+ * Conventions
+ *   - Every function returns B2R_OK (0), B2R_NO_MODEL (1: the call succeeded and there is no model — cv2
+ *     returns None / False), or a negative error (bad argument, CUDA failure); b2r_last_error() then
+ *     returns a message.  There is NO CPU fallback: without a usable CUDA device every compute entry
+ *     point fails with B2R_ERR_CUDA.
+ *   - "host" pointers are ordinary host memory owned by the caller, never written unless documented as an
+ *     output; "dev" pointers are device memory on the context's GPU.  Calls are synchronous: outputs are
+ *     complete on return.  A context is not thread-safe; use one per thread / per GPU.
+ *   - Point arrays are row-major (n, 2) / (n, 3) float64, exactly what the reference passes to cv2.
+ */
+#ifndef RANSAC_B200_H
+#define RANSAC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2R_OK 0
+#define B2R_NO_MODEL 1
+#define B2R_ERR_ARG (-1)
+#define B2R_ERR_CUDA (-2)
+#define B2R_ERR_INTERNAL (-3)
+
+/* sampler */
+#define B2R_SAMPLER_CV_REPLAY 0 /* replay OpenCV's cv::RNG sample stream + adaptive termination (parity mode) */
+#define B2R_SAMPLER_PHILOX 1    /* Philox4x32-10 counter-based sampler, fixed number of hypotheses           */
+/* arithmetic of the hypotheses x points scoring kernel */
+#define B2R_ARITH_EXACT 0 /* the reference's un-fused fp32 sequence: inlier sets bit-exact with cv2 */
+#define B2R_ARITH_FAST 1  /* FMA-contracted, MUFU reciprocal                                        */
+/* which mask cv2.findHomography returns */
+#define B2R_MASK_CV413 0  /* OpenCV 4.13: mask re-derived from the refined H   */
+#define B2R_MASK_LEGACY 1 /* older OpenCV (the reference's debug.log): RANSAC-stage mask */
+
+typedef struct b2r_ctx b2r_ctx;
+
+typedef struct {
+    double thr;          /* ransacReprojThreshold, pixels (main_v1.py:862 passes 75.0, process.py:374 120.0) */
+    int32_t max_iters;   /* cv2 default 2000; with B2R_SAMPLER_PHILOX: number of hypotheses scored           */
+    double confidence;   /* cv2 default 0.995                                                                */
+    int32_t sampler;     /* B2R_SAMPLER_*                                                                    */
+    uint64_t seed;       /* Philox key (ignored for CV_REPLAY, whose seed OpenCV fixes at 2^64-1)            */
+    int32_t arith;       /* B2R_ARITH_*                                                                      */
+    int32_t mask_semantics; /* B2R_MASK_*                                                                    */
+    int32_t refine;      /* 1: refit on inliers + 10 Levenberg-Marquardt iterations, as cv2 does; 0: skip    */
+    /* hypothesis-id shard of this rank (PHILOX only): ids [hyp_begin, hyp_begin + max_iters) are scored.   */
+    int64_t hyp_begin;
+} b2r_h_params;
+
+typedef struct {
+    int32_t status;       /* B2R_OK / B2R_NO_MODEL                                          */
+    int32_t iters_run;    /* RANSAC iterations executed (CV_REPLAY) / hypotheses scored      */
+    int32_t best_iter;    /* 0-based iteration (CV_REPLAY) or hypothesis id - hyp_begin      */
+    int32_t best_count;   /* RANSAC-stage inlier count of the winning hypothesis             */
+    int32_t sample[4];    /* its minimal sample (point indices)                              */
+    int32_t n_inliers;    /* number of ones in the returned mask                             */
+    int32_t lm_iters;     /* LM iterations executed by the refinement                        */
+    int32_t reserved[2];
+} b2r_h_info;
+
+/* ---- life cycle -------------------------------------------------------------------------------------- */
+int b2r_version(void);
+const char* b2r_last_error(void);
+int b2r_device_count(void);
+/* Creates a context on CUDA device `device` (own stream, growable workspaces).  NULL + last_error on failure. */
+b2r_ctx* b2r_ctx_create(int device);
+void b2r_ctx_destroy(b2r_ctx* ctx);
+/* The context's cudaStream_t, as an opaque pointer (for callers that time with their own CUDA events). */
+void* b2r_ctx_stream(b2r_ctx* ctx);
+int b2r_ctx_synchronize(b2r_ctx* ctx);
+void b2r_default_h_params(b2r_h_params* p);
+
+/* ---- cv2.findHomography(src, dst, cv2.RANSAC, thr)  —  main_v1.py:312 ------------------------------- */
+/* src_host, dst_host: (n,2) float64.  H_out: 9 doubles (row-major; all zero when there is no model).
+ * mask_out: n bytes.  info_out may be NULL.  n < 4 -> B2R_ERR_ARG (cv2 raises).  End to end: uploads the
+ * points, runs sampler -> solver -> scoring -> selection -> refinement on the GPU, downloads H and the mask. */
+int b2r_find_homography(b2r_ctx* ctx, const double* src_host, const double* dst_host, int32_t n,
+                        const b2r_h_params* params, double* H_out, uint8_t* mask_out, b2r_h_info* info_out);
+
+/* ---- the loop of find_homographies (main_v1.py:254-297): Q independent problems of n points each ---- */
+/* src_host: (Q,n,2) float64.  dst_host: (n,2) if dst_shared != 0 (the sweep: same pixels for every candidate
+ * camera), else (Q,n,2).  H_out: (Q,9).  mask_out: (Q,n).  info_out: Q entries or NULL.  Returns B2R_OK even
+ * when some problems have no model (see info_out[q].status; their H is zero and mask zero). */
+int b2r_find_homography_batch(b2r_ctx* ctx, const double* src_host, const double* dst_host, int32_t dst_shared,
+                              int32_t Q, int32_t n, const b2r_h_params* params, double* H_out, uint8_t* mask_out,
+                              b2r_h_info* info_out);
+
+/* ---- device-resident form: the points already live in HBM -------------------------------------------- */
+/* Uploads and packs Q problems once (fp32 quantisation as cv2 does); returns a handle. */
+typedef struct b2r_h_problem b2r_h_problem;
+b2r_h_problem* b2r_h_problem_upload(b2r_ctx* ctx, const double* src_host, const double* dst_host, int32_t dst_shared,
+                                    int32_t Q, int32_t n);
+void b2r_h_problem_free(b2r_ctx* ctx, b2r_h_problem* prob);
+/* Runs the whole RANSAC on a resident problem set; results stay on the device until fetched. */
+int b2r_h_problem_run(b2r_ctx* ctx, b2r_h_problem* prob, const b2r_h_params* params);
+int b2r_h_problem_fetch(b2r_ctx* ctx, b2r_h_problem* prob, double* H_out, uint8_t* mask_out, b2r_h_info* info_out);
+/* Multi-GPU (PHILOX): stage 1 scores this rank's hypothesis shard and returns, per problem, the packed key
+ * (count << 32) | (0xFFFFFFFF - global hypothesis id) — the value ranks reduce with MAX (one 8-byte NCCL
+ * all-reduce per problem).  Stage 2 re-derives the winning hypothesis from its global id and finishes
+ * (mask, refit, LM) identically on every rank. */
+int b2r_h_problem_score_shard(b2r_ctx* ctx, b2r_h_problem* prob, const b2r_h_params* params, uint64_t* keys_out);
+int b2r_h_problem_finish(b2r_ctx* ctx, b2r_h_problem* prob, const b2r_h_params* params, const uint64_t* keys);
+/* Device time (ms, CUDA events on the context stream) of the stages of the last run:
+ * [0] sample+solve, [1] scoring kernel, [2] select, [3] finalize (mask/refit/LM), [4] total. */
+int b2r_h_problem_stage_ms(b2r_ctx* ctx, b2r_h_problem* prob, float ms_out[5]);
+/* Number of kernels the last run launched (for bench.py's gpu_launches). */
+int b2r_ctx_launch_count(b2r_ctx* ctx);
+
+/* ---- building blocks (used by the parity tests; each is one kernel of the pipeline) ------------------ */
+/* K3: inlier counts of n_models fp32 models (n_models,8) over n points.  src/dst (n,2) float32 (already
+ * quantised).  counts_out: n_models int32. */
+int b2r_score_h(b2r_ctx* ctx, const float* models_host, int32_t n_models, const float* src_host,
+                const float* dst_host, int32_t n, float thr_sq, int32_t arith, int32_t* counts_out);
+/* K2: 4-point solves.  idx_host (n_samples,4) int32 into the n points.  H_out (n_samples,9) fp64,
+ * ok_out (n_samples) 1/0 (0: degenerate normalisation, or checkSubset rejected the sample). */
+int b2r_solve_h4(b2r_ctx* ctx, const float* src_host, const float* dst_host, int32_t n, const int32_t* idx_host,
+                 int32_t n_samples, double* H_out, uint8_t* ok_out, uint8_t* subset_ok_out);
+/* K1: the first n_iters minimal samples OpenCV's RANSAC would draw on these points (replay sampler).
+ * idx_out (n_iters,4).  *n_generated_out < n_iters when getSubset gave up. */
+int b2r_sample_cv(b2r_ctx* ctx, const float* src_host, const float* dst_host, int32_t n, int32_t n_iters,
+                  int32_t* idx_out, int32_t* n_generated_out);
+/* K1: Philox samples for hypothesis ids [hyp_begin, hyp_begin + n_hyp) of problem q.  idx_out (n_hyp,4);
+ * an all -1 row marks a hypothesis whose 16 attempts were all rejected by checkSubset. */
+int b2r_sample_philox(b2r_ctx* ctx, const float* src_host, const float* dst_host, int32_t n, uint64_t seed,
+                      int32_t q, int64_t hyp_begin, int32_t n_hyp, int32_t* idx_out);
+/* K4 refinement only: refit on the masked points + LM(10).  H_io: in = RANSAC model, out = refined. */
+int b2r_refine_h(b2r_ctx* ctx, const float* src_host, const float* dst_host, int32_t n, const uint8_t* mask_host,
+                 double* H_io, int32_t* lm_iters_out);
+/* Sweeps all 2^32 bit patterns of x and compares the scoring kernel's reciprocal with IEEE 1.0f/x inside the
+ * kernel's fast range; *mismatches_out must be 0. */
+int b2r_selftest_rcp(b2r_ctx* ctx, uint64_t* mismatches_out, uint64_t* tested_out);
+/* Register-resident FFMA peak of this GPU, in fp32 FMA lane-operations per second (x2 = FLOP/s). */
+int b2r_probe_fp32_peak(b2r_ctx* ctx, double* fma_per_s_out, double* ffma2_per_s_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RANSAC_B200_H */

@@ -485,7 +485,7 @@ ORC_API int orc_h_lm_refine(const float* M, const float* m, int count, double* H
 /* cv2.findHomography(src, dst, cv2.RANSAC, thr, maxIters, confidence) — the whole call          */
 /*   src, dst: n fp64 (x,y) pairs, as the reference passes them (main_v1.py:312)                */
 /*   mask_semantics 0: OpenCV 4.13 (mask re-derived from the refined H); 1: legacy (RANSAC mask)*/
-/*   returns 1 and fills H (row-major 3x3, H[8]==1) / mask, or 0 (cv2 returns None, zero mask)  */
+/*   returns 1 and fills H (row-major 3x3, H[8] = 1 up to one ulp, as cv2) / mask, or 0 (cv2 returns None, zero mask)  */
 /* ------------------------------------------------------------------------------------------- */
 ORC_API int orc_find_homography(const double* src, const double* dst, int n, double thresh, int maxIters, double confidence,
                                 int mask_semantics, double* H, uint8_t* mask, int* iters_run, uint8_t* ransac_mask_out,
@@ -504,8 +504,7 @@ ORC_API int orc_find_homography(const double* src, const double* dst, int n, dou
         for (i = 0; i < n; i++)
             if (rmask[i]) { M1[2 * k] = M[2 * i]; M1[2 * k + 1] = M[2 * i + 1]; m1[2 * k] = m[2 * i]; m1[2 * k + 1] = m[2 * i + 1]; k++; }
         orc_h_run_kernel(M1, m1, k, H);
-        orc_h_lm_refine(M1, m1, k, H, 10);
-        H[8] = 1.;
+        orc_h_lm_refine(M1, m1, k, H, 10); /* refines H[0..7]; H[8] stays as runKernel left it (1 or 1-ulp) */
         free(M1);
         free(m1);
     }
