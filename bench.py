@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — hypothesis·points scored per second on the RANSAC camera-location hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (B200, CUDA)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path (cv2), host cores
+
+Workload (config.workload): BASELINE.json configs[2] — synthetic 2D-3D correspondences, 100k points, 50 % outliers,
+100k hypotheses per GPU, homography model (the reference's cv2.findHomography path, main_v1.py:312); Philox sampler
+and a fixed hypothesis count, so one step is exactly hypotheses x points evaluations.  A step is one
+full pass of the hot path: sample -> minimal solve -> score every hypothesis against every point -> select -> refit
++ LM -> final mask.  With N GPUs each rank scores its own 100k hypothesis ids (weak scaling) and one 8-byte NCCL MAX
+all-reduce picks the global winner.
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM.  `e2e`: same metric through the public host API
+with pinned HOST buffers, H2D and D2H inside the timed region.  `roofline`: the scoring kernel against the FP32
+FMA-pipe peak measured in the same run.  `cpu_baseline`: cv2.findHomography on the same points on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_ALG = 20.0            # algorithmic FLOP per hypothesis·point, homography model
+THR_PX = 3.0            # inlier threshold for the synthetic sets (1 px noise)
+NOMINAL_FP32_TFLOPS = 2 * 128 * 148 * 1.965e9 / 1e12  # 74.45, BASELINE.md accounting
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=100_000)
+    ap.add_argument("--hyps-per-gpu", type=int, default=100_000)
+    ap.add_argument("--outliers", type=float, default=0.5)
+    ap.add_argument("--arith", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    from ransac_b200 import synth
+    rng = np.random.default_rng(1898 + 2)
+    src, dst, _ = synth.homography_set(args.points, args.outliers, rng)
+    return np.ascontiguousarray(src), np.ascontiguousarray(dst)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi SM clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1 + 0.1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except (ValueError, IndexError):
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in the timed region"], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_throughput(src, dst, thr, seconds, threads):
+    """The reference's own implementation of the path — cv2.findHomography(..., cv2.RANSAC, thr), main_v1.py:312 —
+    on the host cores: `threads` concurrent callers (the RANSAC loop inside OpenCV is serial; the GIL is released
+    inside the call), repeated for about `seconds`.  hypothesis·points = iterations executed x points; OpenCV does
+    not report the iteration count, so it is taken from the validated CPU restatement (oracle/) run once."""
+    import oracle as O
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        kind = "reference"
+
+        def call():
+            cv2.findHomography(src, dst, cv2.RANSAC, thr)
+    except ImportError:
+        kind = "port"
+
+        def call():
+            O.find_homography(src, dst, thr)
+    det = O.find_homography(src, dst, thr, details=True)[2]
+    iters = det["iters"]
+    call()  # warm
+    t_one = time.perf_counter()
+    call()
+    t_one = time.perf_counter() - t_one
+    reps = max(1, int(seconds / max(t_one, 1e-4)))
+    reps = min(reps, 2000)
+
+    def worker():
+        for _ in range(reps):
+            call()
+
+    ths = [threading.Thread(target=worker) for _ in range(threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    wall = time.perf_counter() - t0
+    evals = float(iters) * len(src) * reps * threads
+    sample = (f"{'cv2 4.x findHomography' if kind == 'reference' else 'oracle port'} RANSAC thr={thr}, default "
+              f"maxIters=2000/conf=0.995 (adaptive: {iters} iterations executed) on the same {len(src)} points; "
+              f"{threads} concurrent callers x {reps} calls, {wall:.1f} s")
+    return dict(value=evals / wall, unit="hypothesis·points/s", cores=threads, kind=kind, sample=sample), wall, reps
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    src, dst = workload(args)
+    cores = os.cpu_count() or 1
+    per_step = max(0.5, min(6.0, 60.0 / max(1, args.steps + args.warmup)))
+    times, evals = [], []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base, wall, reps = reference_throughput(src, dst, THR_PX, per_step, cores)
+        if i >= args.warmup:
+            times.append(wall)
+            evals.append(base["value"] * wall)
+    value = float(sum(evals) / sum(times))
+    base["value"] = value
+    out = {
+        "impl": "reference", "metric": "hypothesis·points scored/sec", "value": value, "unit": "hypothesis·points/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args), "cpu_baseline": base,
+        "e2e": {"value": value, "unit": "hypothesis·points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def config_dict(args):
+    return {"workload": f"BASELINE configs[2]: synthetic 2D-3D correspondences, {args.points} points, "
+                        f"{int(args.outliers * 100)}% outliers, {args.hyps_per_gpu} hypotheses per GPU, homography model "
+                        f"(cv2.findHomography path), thr {THR_PX} px, Philox sampler, fixed hypothesis count",
+            "points": args.points, "hypotheses_per_gpu": args.hyps_per_gpu, "arith": args.arith,
+            "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"hypothesis-sharded x{args.gpus}"}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import ransac_b200
+    from ransac_b200 import dist as rdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = ransac_b200.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=device)
+    arith = ransac_b200.ARITH_FAST if args.arith == "fast" else ransac_b200.ARITH_EXACT
+    solver = ransac_b200.SOLVER_FAST if args.arith == "fast" else ransac_b200.SOLVER_EXACT
+    src, dst = workload(args)
+    N, Hper = args.points, args.hyps_per_gpu
+    hyp_begin = rank * Hper
+    seed = 1898
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    # ---- FP32 pipe peak of this GPU, measured now ----------------------------------------------------------------
+    fma_scalar, fma_packed = ctx.probe_fp32_peak()
+    peak_tflops = 2.0 * fma_scalar / 1e12
+
+    # ---- value: points resident in HBM ---------------------------------------------------------------------------------
+    prob = ctx.upload(src, dst)
+
+    def step_resident():
+        rdist.run_sharded(prob, THR_PX, hyp_begin, Hper, seed=seed, arith=arith, solver=solver, device=device)
+
+    def timed(fn, steps, warmup, clocks=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        launches0 = ctx.launch_count()
+        t0 = time.time()
+        if clocks:
+            clocks.start()
+            time.sleep(0.25)
+            t0 = time.time()
+        score_ms = []
+        for a, b in ev:
+            flush.fill_(1)              # evict L2 between timed steps (outside the step's events)
+            torch.cuda.synchronize()
+            a.record(stream)
+            fn()
+            b.record(stream)
+            b.synchronize()
+            score_ms.append(prob_stage() if fn is step_resident else None)
+        barrier()
+        t1 = time.time()
+        total_ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), ctx.launch_count() - launches0, (t0, t1), score_ms
+
+    def prob_stage():
+        prob.fetch(want_mask=False)  # also refreshes the per-stage event timings (tiny D2H, outside the events)
+        return prob.stage_ms()
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    total_ms, launches, (t0, t1), stages = timed(step_resident, args.steps, max(args.warmup, 3), clocks)
+    clock_info = clocks.stop(t0, t1) if clocks else None
+    evals_per_step = float(Hper) * N * world
+    value = evals_per_step * args.steps / (total_ms * 1e-3)
+    H_res, _, info_res = prob.fetch(want_mask=False)
+
+    # ---- roofline of the dominant kernel (K3 scoring), this rank -------------------------------------------------------
+    k3_ms = float(np.mean([s["score"] for s in stages]))
+    stage_mean = {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}
+    k3_evals_per_s = float(Hper) * N / (k3_ms * 1e-3)
+    achieved_tflops = k3_evals_per_s * F_ALG / 1e12
+    roofline = {
+        "bound": "fp32", "kernel": "k3_score_h", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+        "frac": achieved_tflops / peak_tflops,
+        "peak_source": "register-resident FFMA probe run in this process (b2r_probe_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
+        "frac_of_nominal_74.45": achieved_tflops / NOMINAL_FP32_TFLOPS,
+        "flop_per_eval": F_ALG, "k3_evals_per_s": k3_evals_per_s, "k3_ms": k3_ms, "k3_share_of_step": k3_ms / stage_mean["total"],
+        "ffma2_peak_tflops": 2.0 * fma_packed / 1e12,
+        "traffic": None,
+        "hbm": {"algorithmic_bytes_per_launch": 16.0 * N + 36.0 * Hper, "achieved_GBps": (16.0 * N + 36.0 * Hper) / (k3_ms * 1e-3) / 1e9,
+                "peak_GBps": measured_peaks().get("hbm_gbs")},
+    }
+
+    # ---- e2e: host buffers in pinned memory, H2D + D2H inside the timed region ---------------------------------------------
+    src_pin = torch.from_numpy(src).pin_memory().numpy()
+    dst_pin = torch.from_numpy(dst).pin_memory().numpy()
+    total_h = Hper * world
+
+    prob_e2e = ctx.upload(src_pin, dst_pin)  # buffers reused by every call, like a long-lived caller would
+
+    def step_e2e():
+        return rdist.find_homography_sharded(ctx, src_pin, dst_pin, THR_PX, total_h, seed=seed, arith=arith, solver=solver,
+                                             device=device, problem=prob_e2e)
+
+    e2e_ms, _, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    H_e2e, mask_e2e, info_e2e = step_e2e()
+    e2e_value = evals_per_step * args.steps / (e2e_ms * 1e-3)
+    if H_e2e is None or not np.array_equal(H_e2e, H_res[0]):
+        raise SystemExit("bench.py: resident and end-to-end paths disagree")
+
+    launches_t = torch.tensor([launches], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(launches_t)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _, _ = reference_throughput(src, dst, THR_PX, args.cpu_seconds, 1)
+
+    if rank == 0:
+        out = {
+            "metric": "hypothesis·points scored/sec", "value": value, "unit": "hypothesis·points/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args),
+            "e2e": {"value": e2e_value, "unit": "hypothesis·points/s", "h2d_bytes_per_step": int(src.nbytes + dst.nbytes),
+                    "d2h_bytes_per_step": int(72 + N + 48), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches_t.item()), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
+            "stage_ms": stage_mean, "result": {"inliers": info_res[0]["n_inliers"], "best_count": info_res[0]["best_count"]},
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except OSError:
+        return {}
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

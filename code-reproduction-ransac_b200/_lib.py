@@ -18,7 +18,7 @@ class HParams(C.Structure):
     """b2r_h_params"""
     _fields_ = [("thr", C.c_double), ("max_iters", C.c_int32), ("confidence", C.c_double), ("sampler", C.c_int32),
                 ("seed", C.c_uint64), ("arith", C.c_int32), ("mask_semantics", C.c_int32), ("refine", C.c_int32),
-                ("hyp_begin", C.c_int64)]
+                ("hyp_begin", C.c_int64), ("solver", C.c_int32), ("reserved", C.c_int32)]
 
 
 class HInfo(C.Structure):
@@ -42,6 +42,7 @@ SIGNATURES = {
     "b2r_find_homography_batch": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_int32, C.c_int32,
                                             C.POINTER(HParams), c_double_p, c_u8_p, C.POINTER(HInfo)]),
     "b2r_h_problem_upload": (C.c_void_p, [C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_int32, C.c_int32]),
+    "b2r_h_problem_reupload": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_int32, C.c_int32]),
     "b2r_h_problem_free": (None, [C.c_void_p, C.c_void_p]),
     "b2r_h_problem_run": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(HParams)]),
     "b2r_h_problem_fetch": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, c_u8_p, C.POINTER(HInfo)]),
@@ -51,8 +52,8 @@ SIGNATURES = {
     "b2r_ctx_launch_count": (C.c_int, [C.c_void_p]),
     "b2r_score_h": (C.c_int, [C.c_void_p, c_float_p, C.c_int32, c_float_p, c_float_p, C.c_int32, C.c_float, C.c_int32,
                               c_i32_p]),
-    "b2r_solve_h4": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int32, c_i32_p, C.c_int32, c_double_p, c_u8_p,
-                               c_u8_p]),
+    "b2r_solve_h4": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int32, c_i32_p, C.c_int32, C.c_int32, c_double_p,
+                               c_u8_p, c_u8_p]),
     "b2r_sample_cv": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int32, C.c_int32, c_i32_p, c_i32_p]),
     "b2r_sample_philox": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int32, C.c_uint64, C.c_int32, C.c_int64,
                                     C.c_int32, c_i32_p]),

@@ -13,6 +13,7 @@ from ._lib import HInfo, HParams
 SAMPLER_CV_REPLAY, SAMPLER_PHILOX = 0, 1
 ARITH_EXACT, ARITH_FAST = 0, 1
 MASK_CV413, MASK_LEGACY = 0, 1
+SOLVER_EXACT, SOLVER_FAST = 0, 1
 OK, NO_MODEL = 0, 1
 
 
@@ -33,7 +34,7 @@ def _f32(a, cols):
 
 
 def make_params(thr, max_iters=2000, confidence=0.995, sampler=SAMPLER_CV_REPLAY, seed=0, arith=ARITH_EXACT,
-                mask_semantics=MASK_CV413, refine=True, hyp_begin=0):
+                mask_semantics=MASK_CV413, refine=True, hyp_begin=0, solver=SOLVER_EXACT):
     p = HParams()
     p.thr = float(thr)
     p.max_iters = int(max_iters)
@@ -44,6 +45,7 @@ def make_params(thr, max_iters=2000, confidence=0.995, sampler=SAMPLER_CV_REPLAY
     p.mask_semantics = int(mask_semantics)
     p.refine = 1 if refine else 0
     p.hyp_begin = int(hyp_begin)
+    p.solver = int(solver)
     return p
 
 
@@ -75,6 +77,18 @@ class HomographyProblem:
                                               self.Q, self.n)
         if not self._h:
             raise RansacB200Error(_lib.last_error())
+
+    def reupload(self, src, dst):
+        """Replace the points (host arrays, same layout rules as the constructor), reusing the device buffers."""
+        src = np.ascontiguousarray(np.asarray(src, dtype=np.float64))
+        dst = np.ascontiguousarray(np.asarray(dst, dtype=np.float64))
+        if src.ndim == 2:
+            src = src[None]
+        shared = dst.ndim == 2
+        self.Q, self.n = int(src.shape[0]), int(src.shape[1])
+        self.h2d_bytes = src.nbytes + dst.nbytes
+        self.ctx._check(self.ctx._L.b2r_h_problem_reupload(self.ctx._c, self._h, _ptr(src, C.c_double), _ptr(dst, C.c_double),
+                                                           1 if shared else 0, self.Q, self.n))
 
     def run(self, params):
         self.ctx._check(self.ctx._L.b2r_h_problem_run(self.ctx._c, self._h, C.byref(params)))
@@ -198,7 +212,7 @@ class Context:
                                         C.c_float(np.float32(thr_sq)), int(arith), _ptr(counts, C.c_int32)))
         return counts
 
-    def solve_h4(self, src_f32, dst_f32, idx):
+    def solve_h4(self, src_f32, dst_f32, idx, solver=SOLVER_EXACT):
         s, d = _f32(src_f32, 2), _f32(dst_f32, 2)
         idx = np.ascontiguousarray(np.asarray(idx, dtype=np.int32).reshape(-1, 4))
         k = len(idx)
@@ -206,7 +220,7 @@ class Context:
         ok = np.zeros(k, dtype=np.uint8)
         sub = np.zeros(k, dtype=np.uint8)
         self._check(self._L.b2r_solve_h4(self._c, _ptr(s, C.c_float), _ptr(d, C.c_float), len(s), _ptr(idx, C.c_int32), k,
-                                         _ptr(H, C.c_double), _ptr(ok, C.c_uint8), _ptr(sub, C.c_uint8)))
+                                         int(solver), _ptr(H, C.c_double), _ptr(ok, C.c_uint8), _ptr(sub, C.c_uint8)))
         return H, ok.astype(bool), sub.astype(bool)
 
     def sample_cv(self, src_f32, dst_f32, n_iters):

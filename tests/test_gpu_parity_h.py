@@ -55,6 +55,20 @@ def test_solver_bit_exact_and_check_subset(ctx, oracle, n, seed):
         assert sub[k] == oracle.h_check_subset(sq[idx[k]], dq[idx[k]])
 
 
+def test_fast_solver_agrees_with_exact(ctx):
+    s, d = _problem(2000, 0.3, 12)
+    sq, dq = _quant(s), _quant(d)
+    rng = np.random.default_rng(12)
+    idx = np.stack([rng.choice(2000, 4, replace=False) for _ in range(2000)]).astype(np.int32)
+    He, oke, sub = ctx.solve_h4(sq, dq, idx)
+    Hf, okf, _ = ctx.solve_h4(sq, dq, idx, solver=ransac_b200.SOLVER_FAST)
+    good = oke & okf & sub
+    assert good.sum() > 500
+    rel = np.abs(He[good] - Hf[good]).max(axis=(1, 2)) / np.abs(He[good]).max(axis=(1, 2))
+    # both are fp64 solves of the same 4-point problem; they differ by conditioning only
+    assert np.median(rel) < 1e-11 and np.percentile(rel, 99) < 1e-6
+
+
 @pytest.mark.parametrize("n,n_models,seed", [(12, 100, 8), (1000, 3000, 9), (4097, 5000, 10), (30000, 2048, 11)])
 def test_score_exact_counts_bit_exact(ctx, oracle, n, n_models, seed):
     s, d = _problem(n, 0.5, seed)
