@@ -257,7 +257,7 @@ __device__ __forceinline__ float h_err_exact(const float* Hf, float X, float Y, 
 // barrier per reduction is enough.
 namespace cg = cooperative_groups;
 
-constexpr int RED_MAX = 48;
+constexpr int RED_MAX = 32;
 
 struct ClusterRed {
     double part[2][RED_MAX];  // this CTA's partial sums (double-buffered), read remotely
@@ -329,35 +329,89 @@ __device__ void solve_sym_eig(const double* A, const double* b, double* x, doubl
     }
 }
 
-// Cholesky solve of a symmetric positive definite 8x8 system; false when a pivot is not safely positive
-// (the caller then falls back to the eigen-decomposition solve above, which is what OpenCV always uses).
-__device__ __forceinline__ bool solve_spd8(const double* A, const double* b, double* x) {
-    double L[64];
+// Cholesky factor of a symmetric positive definite N x N matrix (lower triangle in L); false when a pivot is not
+// safely positive — callers then fall back to the Jacobi eigen-decomposition, which is what OpenCV always uses.
+template <int N>
+__device__ __forceinline__ bool cholesky(const double* A, double* L) {
     double dmax = 0;
-    for (int i = 0; i < 8; ++i) dmax = fmax(dmax, fabs(A[i * 8 + i]));
-    for (int j = 0; j < 8; ++j) {
-        double d = A[j * 8 + j];
-        for (int k = 0; k < j; ++k) d -= L[j * 8 + k] * L[j * 8 + k];
-        if (!(d > dmax * 1e-13)) return false;
+    for (int i = 0; i < N; ++i) dmax = fmax(dmax, fabs(A[i * N + i]));
+    for (int j = 0; j < N; ++j) {
+        double d = A[j * N + j];
+        for (int k = 0; k < j; ++k) d -= L[j * N + k] * L[j * N + k];
+        if (!(d > dmax * 1e-14)) return false;
         d = sqrt(d);
-        L[j * 8 + j] = d;
-        for (int i = j + 1; i < 8; ++i) {
-            double t = A[i * 8 + j];
-            for (int k = 0; k < j; ++k) t -= L[i * 8 + k] * L[j * 8 + k];
-            L[i * 8 + j] = t / d;
+        L[j * N + j] = d;
+        for (int i = j + 1; i < N; ++i) {
+            double t = A[i * N + j];
+            for (int k = 0; k < j; ++k) t -= L[i * N + k] * L[j * N + k];
+            L[i * N + j] = t / d;
         }
     }
-    double y[8];
-    for (int i = 0; i < 8; ++i) {
+    return true;
+}
+
+template <int N>
+__device__ __forceinline__ void cholesky_solve(const double* L, const double* b, double* x) {
+    double y[N];
+    for (int i = 0; i < N; ++i) {
         double t = b[i];
-        for (int k = 0; k < i; ++k) t -= L[i * 8 + k] * y[k];
-        y[i] = t / L[i * 8 + i];
+        for (int k = 0; k < i; ++k) t -= L[i * N + k] * y[k];
+        y[i] = t / L[i * N + i];
     }
-    for (int i = 7; i >= 0; --i) {
+    for (int i = N - 1; i >= 0; --i) {
         double t = y[i];
-        for (int k = i + 1; k < 8; ++k) t -= L[k * 8 + i] * x[k];
-        x[i] = t / L[i * 8 + i];
+        for (int k = i + 1; k < N; ++k) t -= L[k * N + i] * x[k];
+        x[i] = t / L[i * N + i];
     }
+}
+
+__device__ __forceinline__ bool solve_spd8(const double* A, const double* b, double* x) {
+    double L[64];
+    if (!cholesky<8>(A, L)) return false;
+    cholesky_solve<8>(L, b, x);
+    return true;
+}
+
+// diag(A^-1) of an SPD 8x8 through its Cholesky factor (column by column)
+__device__ __forceinline__ bool inv_diag_spd8(const double* A, double* diag) {
+    double L[64];
+    if (!cholesky<8>(A, L)) return false;
+    for (int j = 0; j < 8; ++j) {
+        double e[8] = {0, 0, 0, 0, 0, 0, 0, 0}, x[8];
+        e[j] = 1;
+        cholesky_solve<8>(L, e, x);
+        diag[j] = x[j];
+    }
+    return true;
+}
+
+// Eigenvector of the smallest eigenvalue of the symmetric PSD 9x9 L^T L by shifted inverse iteration
+// (fast-solver mode; the exact mode runs OpenCV's Jacobi).  false -> caller falls back to Jacobi.
+__device__ __forceinline__ bool smallest_eigvec9(const double* LtL_upper_full, double* vec) {
+    double A[81], L[81];
+    double tr = 0;
+    for (int j = 0; j < 9; ++j)
+        for (int k = 0; k < 9; ++k) A[j * 9 + k] = j <= k ? LtL_upper_full[j * 9 + k] : LtL_upper_full[k * 9 + j];
+    for (int j = 0; j < 9; ++j) tr += A[j * 9 + j];
+    const double mu = tr * 1e-13;
+    for (int j = 0; j < 9; ++j) A[j * 9 + j] += mu;
+    if (!cholesky<9>(A, L)) return false;
+    double b[9], x[9];
+    for (int j = 0; j < 9; ++j) b[j] = 1. / 3.;
+    for (int it = 0; it < 16; ++it) {
+        cholesky_solve<9>(L, b, x);
+        double nrm = 0;
+        for (int j = 0; j < 9; ++j) nrm += x[j] * x[j];
+        nrm = 1. / sqrt(nrm);
+        double diff = 0;
+        for (int j = 0; j < 9; ++j) {
+            const double v = x[j] * nrm;
+            diff = fmax(diff, fabs(v - b[j]));
+            b[j] = v;
+        }
+        if (it > 1 && diff < 1e-15) break;
+    }
+    for (int j = 0; j < 9; ++j) vec[j] = b[j];
     return true;
 }
 
@@ -369,21 +423,6 @@ struct HFinalizeShared {
     float Hf[8];
     int flag, k, lm_iters, proceed;
 };
-
-// residual/Jacobian of one inlier for the LM refinement
-__device__ __forceinline__ void lm_point(const double* h, double Mx, double My, double mx, double my, double& rx,
-                                         double& ry, double* Jx, double* Jy) {
-    double ww = h[6] * Mx + h[7] * My + 1.;
-    ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
-    const double xi = (h[0] * Mx + h[1] * My + h[2]) * ww;
-    const double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
-    rx = xi - mx;
-    ry = yi - my;
-    if (Jx) {
-        Jx[0] = Mx * ww; Jx[1] = My * ww; Jx[2] = ww; Jx[3] = -Mx * ww * xi; Jx[4] = -My * ww * xi;
-        Jy[0] = Mx * ww; Jy[1] = My * ww; Jy[2] = ww; Jy[3] = -Mx * ww * yi; Jy[4] = -My * ww * yi;
-    }
-}
 
 // K4.  One cluster per problem (blockIdx.x / cluster size = problem).
 //   sel        : selection result; best < 0 -> no model
@@ -482,78 +521,117 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                                 fabs(nm.sMx) < DBL_EPSILON || fabs(nm.sMy) < DBL_EPSILON;
         if (!degenerate) {
             nm.smx = k / nm.smx; nm.smy = k / nm.smy; nm.sMx = k / nm.sMx; nm.sMy = k / nm.sMy;
-            double L[45];  // the 45 unique entries of the symmetric 9x9
+            // L^T L = [[P, 0, -Px], [0, P, -Py], [-Px, -Py, Pxy]] with the 3x3 symmetric blocks
+            // P = sum p p^T, Px = sum x p p^T, Py = sum y p p^T, Pxy = sum (x^2+y^2) p p^T, p = (X, Y, 1):
+            // 4 x 6 = 24 sums instead of the 45 entries of the upper triangle.
+            double L[24];
 #pragma unroll
-            for (int j = 0; j < 45; ++j) L[j] = 0;
+            for (int j = 0; j < 24; ++j) L[j] = 0;
             for (int i = gtid; i < n; i += gstride)
                 if (rmask[i]) {
                     const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
                     const double x = ((double)(-p.z) - nm.cmx) * nm.smx, y = ((double)(-p.w) - nm.cmy) * nm.smy;
                     const double X = ((double)p.x - nm.cMx) * nm.sMx, Y = ((double)p.y - nm.cMy) * nm.sMy;
-                    const double Lx[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x};
-                    const double Ly[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
-                    int e = 0;
+                    const double pp[6] = {X * X, X * Y, X, Y * Y, Y, 1.0};
+                    const double r2 = x * x + y * y;
 #pragma unroll
-                    for (int j = 0; j < 9; ++j)
-#pragma unroll
-                        for (int kk = j; kk < 9; ++kk) L[e++] += Lx[j] * Lx[kk] + Ly[j] * Ly[kk];
+                    for (int j = 0; j < 6; ++j) {
+                        L[j] += pp[j];
+                        L[6 + j] += x * pp[j];
+                        L[12 + j] += y * pp[j];
+                        L[18 + j] += r2 * pp[j];
+                    }
                 }
-            cluster_reduce<THREADS, 45, false>(R, L);
+            cluster_reduce<THREADS, 24, false>(R, L);
             if (tid == 0) {
                 double LtL[81];
-                int e = 0;
-                for (int j = 0; j < 9; ++j)
-                    for (int kk = j; kk < 9; ++kk) LtL[j * 9 + kk] = R.out[e++];
-                double Hm[9];
-                h_from_LtL(LtL, nm, Hm);
+                for (int j = 0; j < 81; ++j) LtL[j] = 0;
+                // index of (a,b), a<=b, in the packed symmetric 3x3: (0,0)=0 (0,1)=1 (0,2)=2 (1,1)=3 (1,2)=4 (2,2)=5
+                const int sym[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b) {
+                        const int e = sym[a][b];
+                        if (b >= a) {
+                            LtL[a * 9 + b] = R.out[e];
+                            LtL[(3 + a) * 9 + 3 + b] = R.out[e];
+                            LtL[(6 + a) * 9 + 6 + b] = R.out[18 + e];
+                        }
+                        LtL[a * 9 + 6 + b] = -R.out[6 + e];
+                        LtL[(3 + a) * 9 + 6 + b] = -R.out[12 + e];
+                    }
+                double Hm[9], vec[9];
+                if (fast_solver && smallest_eigvec9(LtL, vec))
+                    h_from_eigvec(vec, nm, Hm);
+                else
+                    h_from_LtL(LtL, nm, Hm);
                 for (int i = 0; i < 9; ++i) sh.H[i] = Hm[i];
             }
             __syncthreads();
         }
 
         // ---- Levenberg-Marquardt, max 10 iterations, eps = FLT_EPSILON (cv::LMSolver) ---------------------
-        // per-thread accumulators: S, the 36 unique entries of J^T J, the 8 of J^T r; and max |r|
+        // Rows of J: Jx = [a, 0, cx], Jy = [0, a, cy] with a = (X, Y, 1) ww, cx = -(X, Y) ww xi, cy = -(X, Y) ww yi,
+        // so J^T J = [[aa, 0, a cx^T], [0, aa, a cy^T], [., ., cx cx^T + cy cy^T]] and J^T r = [a rx, a ry, cx rx + cy ry]:
+        // per-thread accumulators  S | aa (6) | a cx^T (6) | a cy^T (6) | cc (3) | a rx (3) | a ry (3) | c.r (2)  = 30
         auto eval = [&](const double* h, bool want_J) -> double2 {
-            double acc[45];
+            double acc[30];
 #pragma unroll
-            for (int j = 0; j < 45; ++j) acc[j] = 0;
+            for (int j = 0; j < 30; ++j) acc[j] = 0;
             double rmax[1] = {0};
             for (int i = gtid; i < n; i += gstride)
                 if (rmask[i]) {
                     const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
-                    double rx, ry, Jx[5], Jy[5];
-                    lm_point(h, (double)p.x, (double)p.y, (double)(-p.z), (double)(-p.w), rx, ry, want_J ? Jx : nullptr,
-                             want_J ? Jy : nullptr);
+                    const double Mx = (double)p.x, My = (double)p.y;
+                    double ww = h[6] * Mx + h[7] * My + 1.;
+                    ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
+                    const double xi = (h[0] * Mx + h[1] * My + h[2]) * ww;
+                    const double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
+                    const double rx = xi - (double)(-p.z), ry = yi - (double)(-p.w);
                     acc[0] += rx * rx + ry * ry;
                     rmax[0] = fmax(rmax[0], fmax(fabs(rx), fabs(ry)));
                     if (want_J) {
-                        const double jx[8] = {Jx[0], Jx[1], Jx[2], 0, 0, 0, Jx[3], Jx[4]};
-                        const double jy[8] = {0, 0, 0, Jy[0], Jy[1], Jy[2], Jy[3], Jy[4]};
-                        int e = 1;
+                        const double a[3] = {Mx * ww, My * ww, ww};
+                        const double cx[2] = {-a[0] * xi, -a[1] * xi}, cy[2] = {-a[0] * yi, -a[1] * yi};
+                        acc[1] += a[0] * a[0]; acc[2] += a[0] * a[1]; acc[3] += a[0] * a[2];
+                        acc[4] += a[1] * a[1]; acc[5] += a[1] * a[2]; acc[6] += a[2] * a[2];
 #pragma unroll
-                        for (int a = 0; a < 8; ++a)
-#pragma unroll
-                            for (int b = a; b < 8; ++b) acc[e++] += jx[a] * jx[b] + jy[a] * jy[b];
-#pragma unroll
-                        for (int a = 0; a < 8; ++a) acc[37 + a] += jx[a] * rx + jy[a] * ry;
+                        for (int u = 0; u < 3; ++u) {
+                            acc[7 + 2 * u] += a[u] * cx[0];  acc[8 + 2 * u] += a[u] * cx[1];
+                            acc[13 + 2 * u] += a[u] * cy[0]; acc[14 + 2 * u] += a[u] * cy[1];
+                            acc[22 + u] += a[u] * rx;        acc[25 + u] += a[u] * ry;
+                        }
+                        acc[19] += cx[0] * cx[0] + cy[0] * cy[0];
+                        acc[20] += cx[0] * cx[1] + cy[0] * cy[1];
+                        acc[21] += cx[1] * cx[1] + cy[1] * cy[1];
+                        acc[28] += cx[0] * rx + cy[0] * ry;
+                        acc[29] += cx[1] * rx + cy[1] * ry;
                     }
                 }
             if (want_J) {
-                cluster_reduce<THREADS, 45, false>(R, acc);
+                cluster_reduce<THREADS, 30, false>(R, acc);
             } else {
                 double a1[1] = {acc[0]};
                 cluster_reduce<THREADS, 1, false>(R, a1);
             }
             const double S = R.out[0];
             if (want_J && tid == 0) {
-                int e = 1;
-                for (int a = 0; a < 8; ++a)
-                    for (int b = a; b < 8; ++b) {
-                        sh.A[a * 8 + b] = R.out[e];
-                        sh.A[b * 8 + a] = R.out[e];
-                        ++e;
+                const double* o = R.out;
+                for (int j = 0; j < 64; ++j) sh.A[j] = 0;
+                const int sym[3][3] = {{1, 2, 3}, {2, 4, 5}, {3, 5, 6}};
+                for (int u = 0; u < 3; ++u) {
+                    for (int w = 0; w < 3; ++w) {
+                        sh.A[u * 8 + w] = o[sym[u][w]];
+                        sh.A[(3 + u) * 8 + 3 + w] = o[sym[u][w]];
                     }
-                for (int a = 0; a < 8; ++a) sh.v[a] = R.out[37 + a];
+                    for (int w = 0; w < 2; ++w) {
+                        sh.A[u * 8 + 6 + w] = sh.A[(6 + w) * 8 + u] = o[7 + 2 * u + w];
+                        sh.A[(3 + u) * 8 + 6 + w] = sh.A[(6 + w) * 8 + 3 + u] = o[13 + 2 * u + w];
+                    }
+                    sh.v[u] = o[22 + u];
+                    sh.v[3 + u] = o[25 + u];
+                }
+                sh.A[6 * 8 + 6] = o[19]; sh.A[6 * 8 + 7] = sh.A[7 * 8 + 6] = o[20]; sh.A[7 * 8 + 7] = o[21];
+                sh.v[6] = o[28]; sh.v[7] = o[29];
             }
             __syncthreads();
             cluster_reduce<THREADS, 1, true>(R, rmax);
@@ -602,7 +680,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     nu = fmin(fmax(nu, 2.), 10.);
                     if (sh.lambda == 0) {
                         double diag[8], maxval = DBL_EPSILON;
-                        solve_sym_eig<8>(sh.A, nullptr, nullptr, diag);
+                        if (!inv_diag_spd8(sh.A, diag)) solve_sym_eig<8>(sh.A, nullptr, nullptr, diag);
                         for (int i = 0; i < 8; ++i) maxval = fmax(maxval, fabs(diag[i]));
                         sh.lambda = sh.lc = 1. / maxval;
                         nu *= 0.5;

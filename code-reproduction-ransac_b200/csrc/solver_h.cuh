@@ -146,6 +146,17 @@ struct HNorm {
     double sMx, sMy, smx, smy;  // count / sum |coord - centroid|
 };
 
+// de-normalise the 9-vector of the smallest eigenvalue and scale by 1/H[2][2]
+__device__ __forceinline__ void h_from_eigvec(const double* vec, const HNorm& nm, double* H) {
+    const double invHnorm[9] = {1. / nm.smx, 0, nm.cmx, 0, 1. / nm.smy, nm.cmy, 0, 0, 1};
+    const double Hnorm2[9] = {nm.sMx, 0, -nm.cMx * nm.sMx, 0, nm.sMy, -nm.cMy * nm.sMy, 0, 0, 1};
+    double Ht[9], H0[9];
+    mat3_mul(invHnorm, vec, Ht);
+    mat3_mul(Ht, Hnorm2, H0);
+    const double sc = 1. / H0[8];
+    for (int i = 0; i < 9; i++) H[i] = H0[i] * sc;
+}
+
 // L^T L (full 9x9, upper triangle accumulated then mirrored by the caller) -> H.  Returns false when
 // the normalisation is degenerate.  LtL is destroyed.
 __device__ __forceinline__ void h_from_LtL(double* LtL, const HNorm& nm, double* H) {
@@ -153,13 +164,7 @@ __device__ __forceinline__ void h_from_LtL(double* LtL, const HNorm& nm, double*
     for (int j = 0; j < 9; j++)
         for (int k = 0; k < j; k++) LtL[j * 9 + k] = LtL[k * 9 + j];
     jacobi_eig<9>(LtL, W, V);
-    const double invHnorm[9] = {1. / nm.smx, 0, nm.cmx, 0, 1. / nm.smy, nm.cmy, 0, 0, 1};
-    const double Hnorm2[9] = {nm.sMx, 0, -nm.cMx * nm.sMx, 0, nm.sMy, -nm.cMy * nm.sMy, 0, 0, 1};
-    double Ht[9], H0[9];
-    mat3_mul(invHnorm, V + 72, Ht);
-    mat3_mul(Ht, Hnorm2, H0);
-    const double sc = 1. / H0[8];
-    for (int i = 0; i < 9; i++) H[i] = H0[i] * sc;
+    h_from_eigvec(V + 72, nm, H);
 }
 
 __device__ __forceinline__ void h_accumulate_LtL(double* LtL, const HNorm& nm, double Mx, double My, double mx,
