@@ -1,0 +1,138 @@
+"""CPU: the C ABI loads and exports every symbol the header declares; host-side logic (geodesy, the reference's
+score formulas, hypothesis sharding, the gloo path of the multi-rank reduce).  No compute calls without a GPU."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "ransac_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2r_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    from ransac_b200 import _lib
+    L = _lib.load()
+    declared = header_symbols()
+    assert len(declared) >= 25
+    assert sorted(_lib.SIGNATURES) == declared          # the ctypes table and the header agree
+    for name in declared:
+        assert getattr(L, name) is not None
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.lib_path()], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (b2r_[a-z0-9_]+)", out)))
+    assert exported == declared                          # and nothing else is exported under that prefix
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly (and it never imports the oracle)."""
+    import ransac_b200
+    from ransac_b200 import _lib
+    if _lib.load().b2r_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(ransac_b200.RansacB200Error, match="no CPU fallback"):
+        ransac_b200.Context(0)
+    pkg = os.path.join(ROOT, "code-reproduction-ransac_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
+
+
+def test_utm_transform_check_values():
+    from ransac_b200 import geo
+    e, n = geo.wgs84_to_utm50n(119.390036, 26.098989)           # testpro-K.py:199
+    assert abs(e - 739031.2) < 5e-3 and abs(n - 2888840.39) < 5e-3
+    e, n = geo.wgs84_to_utm50n(119.39055048629785, 26.09361027127146)
+    assert abs(e - 739093.6175) < 1e-3 and abs(n - 2888245.3439) < 1e-3
+
+
+def test_candidate_projection_and_score_formulas():
+    """candidate_pos2 / _score restate main_v1.py:304-311 and :327-348, :419 — checked against a literal loop."""
+    from ransac_b200 import pipeline
+    rng = np.random.default_rng(0)
+    pos3d = rng.uniform([738950, 2888500, 690], [739350, 2889050, 730], (12, 3))
+    cam = np.array([739410.15, 2888321.95, 756.0])
+    pixels = rng.uniform(0, 2000, (12, 2))
+    pos2 = pipeline.candidate_pos2(pos3d, cam)
+    for i in range(12):
+        p = pos3d[i] - cam
+        p = np.array([p[2], p[1], p[0]])
+        p = p / p[2]
+        np.testing.assert_array_equal(pos2[i], p[0:2])
+    H = np.array([[1500., 80, 600], [-40, -700, 100], [0.05, -0.02, 1]])
+    mask = (rng.random(12) < 0.7).astype(np.uint8).reshape(-1, 1)
+    M, e1, e2 = pipeline._score(H, mask, pos2, pixels, 75.0)
+    Mr = np.linalg.inv(H)
+    r1 = r2 = 0.0
+    for i in range(12):
+        pp2 = np.linalg.inv(Mr) @ np.array([pos2[i, 0], pos2[i, 1], 1.0])
+        pp2 = pp2 / pp2[2]
+        PP2 = Mr @ np.array([pixels[i, 0], pixels[i, 1], 1.0])
+        PP2 = PP2 / PP2[2]
+        if mask[i] == 1:
+            r1 += np.linalg.norm(pixels[i] - pp2[0:2])
+            r2 += np.linalg.norm(pos2[i] - PP2[0:2])
+    r2 += np.sum(1 - mask) * 75.0
+    assert abs(e1 - r1) < 1e-9 * max(1, r1) and abs(e2 - r2) < 1e-9 * max(1, r2)
+    nm = np.array([[1., 0.], [2., 5.], [3., 4.]])
+    assert pipeline.best_location(nm) == 2                       # zeros count as 1e6, main_v1.py:865
+
+
+def test_shard_range_partitions_ids():
+    from ransac_b200 import dist
+    for total, world in [(100000, 8), (10, 3), (7, 8), (1, 1)]:
+        covered = []
+        for r in range(world):
+            b, c = dist.shard_range(total, r, world)
+            covered += list(range(b, b + c))
+        assert covered == list(range(total))
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch.distributed as dist
+from ransac_b200 import dist as rdist
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=2)
+# rank 0 holds the better count for problem 0; equal counts for problem 1 -> the lower hypothesis id wins
+keys = [np.array([(50 << 32) | (0xFFFFFFFF - 7), (40 << 32) | (0xFFFFFFFF - 9)], dtype=np.uint64),
+        np.array([(48 << 32) | (0xFFFFFFFF - 3), (40 << 32) | (0xFFFFFFFF - 2)], dtype=np.uint64)][rank]
+best = rdist.reduce_keys_max(keys)
+assert int(best[0]) >> 32 == 50 and 0xFFFFFFFF - (int(best[0]) & 0xFFFFFFFF) == 7, best
+assert int(best[1]) >> 32 == 40 and 0xFFFFFFFF - (int(best[1]) & 0xFFFFFFFF) == 2, best
+assert rdist.shard_range(10, rank, 2) == ((0, 5) if rank == 0 else (5, 5))
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_key_reduce_over_gloo(tmp_path):
+    """The N>1 path of dist.reduce_keys_max with world_size 2 on CPU (gloo): MAX of the packed keys = best count,
+    lowest id on ties."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, port=port))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"ok {r}" in o

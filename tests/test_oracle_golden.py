@@ -1,0 +1,133 @@
+"""CPU: the oracle against the golden vectors recorded from the cv2 4.13.0 binary and from the reference's own
+debug.log (tests/golden/make_golden.py).  No cv2, no /root/reference, no GPU needed."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cv2_golden.json")
+REL_H_TOL = 1e-5   # north star tolerance; observed agreement is ~1e-9
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(GOLD) as f:
+        return json.load(f)
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def test_rng_known_answers(oracle, gold):
+    assert oracle.rng_stream(8) == gold["rng_first8"]
+    assert [x % 12 for x in oracle.rng_stream(10)] == [9, 4, 8, 9, 3, 8, 9, 8, 5, 6]
+
+
+def test_jacobi_bit_exact_with_cv2_eigen(oracle, gold):
+    for c in gold["eigen9"]:
+        W, V = oracle.jacobi(np.array(c["A"]))
+        np.testing.assert_array_equal(W, np.array(c["w"]))
+        np.testing.assert_array_equal(V, np.array(c["v"]))
+
+
+def test_four_point_solver_bit_exact(oracle, gold):
+    assert len(gold["kernel4"]) >= 50
+    for c in gold["kernel4"]:
+        H = oracle.h_run_kernel(np.array(c["src"]), np.array(c["dst"]))
+        np.testing.assert_array_equal(H, np.array(c["H"]))
+
+
+def test_find_homography_random_problems(oracle, gold):
+    worst = 0.0
+    for c in gold["ransac_random"]:
+        H, mask = oracle.find_homography(np.array(c["src"]), np.array(c["dst"]), c["thr"])
+        assert (H is None) == (c["H"] is None)
+        np.testing.assert_array_equal(mask.ravel(), np.array(c["mask"], dtype=np.uint8))
+        if H is not None:
+            worst = max(worst, relerr(H, c["H"]))
+    assert worst < REL_H_TOL
+
+
+def test_fixture_a_sweep(oracle, gold):
+    """The repo's own data: testpro-K.py:198-225 points x 458 candidate cameras, thr 75 (main_v1.py:862).
+
+    With 12 points and a 75 px threshold most candidates keep only 6-8 inliers, and OpenCV 4.13's final
+    Levenberg-Marquardt refinement is a black box there (DESIGN.md "Parity status"): the restated LM agrees with
+    the binary to 1e-5 on the well-conditioned candidates (75 % of the sweep) and lands in a different local
+    minimum on the others.  What the reference consumes downstream — the arg-min of err2 — is identical."""
+    from ransac_b200 import pipeline
+    s = gold["fixture_a_sweep"]
+    pos3d, pixels, loc3ds = np.array(s["pos3d"]), np.array(s["pixels"]), np.array(s["loc3ds"])
+    nm = np.zeros((len(loc3ds), 2))
+    close = np.zeros(len(loc3ds), dtype=bool)
+    for i in range(len(loc3ds)):
+        pos2 = pipeline.candidate_pos2(pos3d, loc3ds[i])
+        H, mask = oracle.find_homography(pos2, pixels, s["thr"])
+        assert H is not None
+        close[i] = relerr(H, s["H"][i]) < REL_H_TOL
+        if close[i]:
+            np.testing.assert_array_equal(mask.ravel(), np.array(s["mask"][i], dtype=np.uint8))
+        _, nm[i, 0], nm[i, 1] = pipeline._score(H, mask, pos2, pixels, s["thr"])
+    assert close.mean() >= 0.70
+    np.testing.assert_allclose(nm[close, 0], np.array(s["err1"])[close], rtol=1e-4)
+    np.testing.assert_allclose(nm[close, 1], np.array(s["err2"])[close], rtol=1e-4)
+    assert close[180]
+    assert pipeline.best_location(nm) == s["best_index"] == 180      # Pointid 181, SURVEY.md Appendix C
+    assert abs(nm[180, 1] - 75.212638) < 1e-5
+
+
+def test_debug_log_known_answers(oracle, gold):
+    """The reference's recorded run (thr 120, process.py:374; older OpenCV -> RANSAC-stage "legacy" mask).
+
+    The RANSAC stage (sampler replay, degeneracy tests, 4-point solver, fp32 scoring, termination) reproduces the
+    logged mask in all 24 complete blocks.  The logged matrix M = inv(refined H) depends on OpenCV's final
+    Levenberg-Marquardt pass, which is not reproducible from outside the binary on this ill-conditioned 12-point
+    data (DESIGN.md "Parity status"): the restated LM lands within ~10 % of it, not within tolerance, so M is only
+    held to a loose bound here and the failure to pin it is reported, not hidden."""
+    blocks = gold["debug_log"]
+    assert len(blocks) == 24
+    rel_M, masks413 = [], 0
+    for b in blocks:
+        pos2, p1 = np.array(b["pos2"]), np.array(b["p1"])
+        H, mask_legacy = oracle.find_homography(pos2, p1, 120.0, mask_semantics=1)
+        assert mask_legacy.ravel().tolist() == b["logged_mask"]
+        M = np.linalg.inv(H)
+        M = M * (np.array(b["logged_M"])[2, 2] / M[2, 2])
+        rel_M.append(relerr(M, b["logged_M"]))
+        H413, mask413 = oracle.find_homography(pos2, p1, 120.0, mask_semantics=0)
+        masks413 += mask413.ravel().tolist() == b["cv413_mask"]
+    assert np.median(rel_M) < 0.2
+    assert masks413 >= 20
+
+
+def test_project_points_bit_exact(oracle, gold):
+    K = np.array(gold["pnp_fixture_a"]["K"])
+    for c in gold["project_points"]:
+        R = oracle.rodrigues(np.array(c["rvec"]))
+        assert np.abs(R - np.array(c["R"])).max() < 1e-15
+        proj = oracle.pnp_project_f32(np.array(c["R"]), np.array(c["tvec"]), K, np.array(c["obj"], dtype=np.float32))
+        np.testing.assert_array_equal(proj, np.array(c["proj_f32"], dtype=np.float32))
+
+
+def test_pnp_fixture_a_scoring(oracle, gold):
+    """cv2.solvePnPRansac on the repo data returns inliers [0 1 2 3 7 9]; the oracle's PnP
+    scoring reproduces cv2.projectPoints for the returned pose, and the replayed 5-point sample stream starts with
+    the tuples the survey recorded."""
+    p = gold["pnp_fixture_a"]
+    assert p["inliers"] == [0, 1, 2, 3, 7, 9]
+    s = gold["fixture_a_sweep"]
+    obj32 = np.array(s["pos3d"], dtype=np.float32)
+    proj = oracle.pnp_project_f32(np.array(p["R"]), np.array(p["tvec"]), np.array(p["K"]), obj32)
+    np.testing.assert_array_equal(proj, np.array(p["proj_f32"], dtype=np.float32))
+    first = oracle.pnp_sample_stream(12, 6).tolist()
+    assert first == [[9, 4, 8, 3, 5], [6, 1, 10, 2, 3], [2, 8, 0, 4, 3], [7, 0, 9, 1, 8], [4, 9, 6, 8, 2], [1, 7, 9, 2, 0]]
+
+
+def test_update_num_iters(oracle):
+    assert oracle.update_num_iters(0.995, 0.5, 4, 2000) == 82
+    assert oracle.update_num_iters(0.995, 0.0, 4, 2000) == 0
+    assert oracle.update_num_iters(0.995, 1.0, 4, 2000) == 2000
+    assert oracle.update_num_iters(0.99, 0.5, 5, 5000) == 145   # the PnP run on the repo data executes 145 iterations
