@@ -1,0 +1,113 @@
+// Probe: K3 with the point tile in the constant bank (uniform-register operands) vs the shared-memory tile kernel.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -I code-reproduction-ransac_b200/csrc tools/microbench_const.cu -o tools/microbench_const
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "score_h.cuh"
+using namespace b2r;
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
+
+constexpr int CPTS = 4096;
+__constant__ float4 c_pts[CPTS];
+
+template <int NPAIR>
+__global__ void __launch_bounds__(K3_THREADS, 2)
+k3c_score_h(const float4* __restrict__ models, int H, int chunk, int npts, float thr, int* __restrict__ counts) {
+    const int h_base = blockIdx.x * (K3_THREADS * 2 * NPAIR) + threadIdx.x;
+    f2_t h[NPAIR][8];
+#pragma unroll
+    for (int j = 0; j < NPAIR; ++j) {
+        const int ha = h_base + (2 * j) * K3_THREADS, hb = ha + K3_THREADS;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+        if (ha < H) { a0 = __ldg(models + 2 * ha); a1 = __ldg(models + 2 * ha + 1); }
+        if (hb < H) { b0 = __ldg(models + 2 * hb); b1 = __ldg(models + 2 * hb + 1); }
+        h[j][0] = f2_pack(a0.x, b0.x); h[j][1] = f2_pack(a0.y, b0.y); h[j][2] = f2_pack(a0.z, b0.z); h[j][3] = f2_pack(a0.w, b0.w);
+        h[j][4] = f2_pack(a1.x, b1.x); h[j][5] = f2_pack(a1.y, b1.y); h[j][6] = f2_pack(a1.z, b1.z); h[j][7] = f2_pack(a1.w, b1.w);
+    }
+    int cnt[2 * NPAIR];
+#pragma unroll
+    for (int j = 0; j < 2 * NPAIR; ++j) cnt[j] = 0;
+    const f2_t one = f2_dup(1.0f);
+    const int p0 = blockIdx.y * chunk, p1 = min(p0 + chunk, npts);
+#pragma unroll 2
+    for (int p = p0; p < p1; ++p) {
+        const float4 pt = c_pts[p];
+        const f2_t X = f2_dup(pt.x), Y = f2_dup(pt.y), nu = f2_dup(pt.z), nv = f2_dup(pt.w);
+#pragma unroll
+        for (int j = 0; j < NPAIR; ++j) {
+            float e0, e1;
+            f2_unpack(HEval<false>::err(h[j], X, Y, nu, nv, one), e0, e1);
+            cnt[2 * j] += (e0 <= thr) ? 1 : 0;
+            cnt[2 * j + 1] += (e1 <= thr) ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 2 * NPAIR; ++j) {
+        const int hh = h_base + j * K3_THREADS;
+        if (hh < H) atomicAdd(counts + hh, cnt[j]);
+    }
+}
+
+template <int NPAIR>
+static void run(const float4* d_models, int H, const PointH* d_pts, int N, float thr, int* d_counts, int chunk, std::vector<int>& ref) {
+    dim3 gc((H + K3_THREADS * 2 * NPAIR - 1) / (K3_THREADS * 2 * NPAIR), (CPTS + chunk - 1) / chunk);
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int r = 0; r < 6; ++r) {
+        CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * H));
+        CK(cudaEventRecord(e0));
+        for (int t = 0; t * CPTS < N; ++t) {
+            int np = std::min(CPTS, N - t * CPTS);
+            CK(cudaMemcpyToSymbolAsync(c_pts, d_pts + (size_t)t * CPTS, sizeof(float4) * np, 0, cudaMemcpyDeviceToDevice));
+            k3c_score_h<NPAIR><<<gc, K3_THREADS>>>(d_models, H, chunk, np, thr, d_counts);
+        }
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (r >= 2) best = fminf(best, ms);
+    }
+    std::vector<int> got(H); CK(cudaMemcpy(got.data(), d_counts, sizeof(int) * H, cudaMemcpyDeviceToHost));
+    int bad = 0; for (int k = 0; k < H; ++k) bad += got[k] != ref[k];
+    printf("{\"k3c\": \"const-bank\", \"npair\": %d, \"chunk\": %d, \"grid\": [%d,%d], \"launches\": %d, \"ms\": %.4f, \"evals_per_s\": %.4e, \"count_mismatch_vs_smem_kernel\": %d}\n",
+           NPAIR, chunk, gc.x, gc.y, (N + CPTS - 1) / CPTS, best, (double)H * N / (best * 1e-3), bad);
+    fflush(stdout);
+}
+
+int main(int argc, char** argv) {
+    int H = argc > 1 ? atoi(argv[1]) : 100000, N = argc > 2 ? atoi(argv[2]) : 100000;
+    srand(1898);
+    auto frand = []() { return (float)rand() / (float)RAND_MAX; };
+    const float Ht[8] = {1500.f, 80.f, 600.f, -40.f, -700.f, 100.f, 0.05f, -0.02f};
+    std::vector<PointH> pts(N);
+    for (int i = 0; i < N; ++i) {
+        float X = 0.05f + 0.35f * frand(), Y = -2.6f + 1.7f * frand(), w = Ht[6] * X + Ht[7] * Y + 1.f;
+        float u = (Ht[0] * X + Ht[1] * Y + Ht[2]) / w + (frand() - 0.5f) * 4.f, v = (Ht[3] * X + Ht[4] * Y + Ht[5]) / w + (frand() - 0.5f) * 4.f;
+        if (i & 1) { u = 2142.f * frand(); v = 1620.f * frand(); }
+        pts[i] = PointH{X, Y, -u, -v};
+    }
+    std::vector<float> models((size_t)H * 8);
+    for (int k = 0; k < H; ++k) for (int j = 0; j < 8; ++j) models[(size_t)k * 8 + j] = Ht[j] * (1.f + 0.02f * (frand() - 0.5f) * (float)(k % 7));
+    const float thr = 9.f;
+    float4* d_models; PointH* d_pts; int* d_counts;
+    CK(cudaMalloc(&d_models, sizeof(float) * 8 * H)); CK(cudaMalloc(&d_pts, sizeof(PointH) * N)); CK(cudaMalloc(&d_counts, sizeof(int) * H));
+    CK(cudaMemcpy(d_models, models.data(), sizeof(float) * 8 * H, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_pts, pts.data(), sizeof(PointH) * N, cudaMemcpyHostToDevice));
+    // reference: the shared-memory tile kernel
+    std::vector<int> ref(H);
+    {
+        const int tile = 512; size_t smem = 128 + tile * 16;
+        dim3 grid((H + K3_THREADS * 4 - 1) / (K3_THREADS * 4), (N + tile - 1) / tile);
+        cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); float best = 1e30f;
+        for (int r = 0; r < 6; ++r) {
+            CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * H)); CK(cudaEventRecord(e0));
+            k3_score_h<2, false><<<grid, K3_THREADS, smem>>>(d_models, H, d_pts, N, thr, d_counts, tile);
+            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (r >= 2) best = fminf(best, ms);
+        }
+        CK(cudaMemcpy(ref.data(), d_counts, sizeof(int) * H, cudaMemcpyDeviceToHost));
+        printf("{\"k3\": \"smem-tile npair2 tile512\", \"ms\": %.4f, \"evals_per_s\": %.4e}\n", best, (double)H * N / (best * 1e-3));
+    }
+    run<2>(d_models, H, d_pts, N, thr, d_counts, 512, ref);
+    run<2>(d_models, H, d_pts, N, thr, d_counts, 1024, ref);
+    run<2>(d_models, H, d_pts, N, thr, d_counts, 2048, ref);
+    run<4>(d_models, H, d_pts, N, thr, d_counts, 512, ref);
+    run<4>(d_models, H, d_pts, N, thr, d_counts, 1024, ref);
+    run<3>(d_models, H, d_pts, N, thr, d_counts, 1024, ref);
+    return 0;
+}
