@@ -229,14 +229,13 @@ def run_b200(args):
     def timed(fn, steps, warmup, clocks=None):
         for _ in range(warmup):
             fn()
+        if clocks:
+            clocks.start()
+            time.sleep(0.25)       # let nvidia-smi deliver its first samples; the barrier below re-aligns the ranks
         barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         launches0 = ctx.launch_count()
         t0 = time.time()
-        if clocks:
-            clocks.start()
-            time.sleep(0.25)
-            t0 = time.time()
         score_ms = []
         for a, b in ev:
             flush.fill_(1)              # evict L2 between timed steps (outside the step's events)
