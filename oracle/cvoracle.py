@@ -15,8 +15,8 @@ _SO = os.path.join(_HERE, "_build", "liboracle.so")
 
 def build(force=False):
     """Compile the C restatement (gcc, seconds).  Building the checker is not using it."""
-    src = os.path.join(_HERE, "cv_ransac_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("cv_ransac_oracle.c", "cv_pnp_oracle.c", "Makefile")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE])
     return _SO
 
@@ -52,6 +52,20 @@ def lib():
         L.orc_pnp_count_inliers.argtypes = [dp, dp, dp, fp, fp, C.c_int, C.c_double, u8p]
         L.orc_pnp_count_inliers.restype = C.c_int
         L.orc_pnp_sample_stream.argtypes = [C.c_int, C.c_int, C.c_int, i32p]
+        L.orc_epnp.argtypes = [dp, dp, C.c_int, dp, dp, dp]
+        L.orc_epnp.restype = C.c_int
+        L.orc_rodrigues_inv.argtypes = [dp, dp]
+        L.orc_svd.argtypes = [dp, C.c_int, C.c_int, dp, dp, dp]
+        L.orc_pnp_minimal_model.argtypes = [fp, fp, C.c_int, dp, dp, dp]
+        L.orc_pnp_minimal_model.restype = C.c_int
+        L.orc_pnp_ransac_stage.argtypes = [fp, fp, C.c_int, dp, C.c_int, C.c_double, C.c_double, dp, u8p, ip, ip, i32p]
+        L.orc_pnp_ransac_stage.restype = C.c_int
+        L.orc_pnp_refine_lm.argtypes = [dp, dp, C.c_int, dp, dp, dp, C.c_int]
+        L.orc_pnp_refine_lm.restype = C.c_int
+        L.orc_pnp_refine_cvlevmarq.argtypes = [dp, dp, C.c_int, dp, dp, dp]
+        L.orc_pnp_refine_cvlevmarq.restype = C.c_int
+        L.orc_solve_pnp_ransac.argtypes = [dp, dp, C.c_int, dp, C.c_int, C.c_double, C.c_double, dp, dp, i32p, ip, ip, dp]
+        L.orc_solve_pnp_ransac.restype = C.c_int
         L.orc_rng_next.argtypes = [C.POINTER(C.c_uint64)]
         L.orc_rng_next.restype = C.c_uint32
         _lib = L
@@ -204,3 +218,83 @@ def pnp_sample_stream(n_points, iters, model_points=5):
     idx = np.zeros((iters, model_points), dtype=np.int32)
     lib().orc_pnp_sample_stream(n_points, iters, model_points, _p(idx, C.c_int32))
     return idx
+
+
+def epnp(obj, img, K):
+    """EPnP on n (4..16) correspondences as OpenCV runs it for a RANSAC minimal sample: (R, t) or None."""
+    o = np.ascontiguousarray(np.asarray(obj, dtype=np.float64).reshape(-1, 3))
+    im = np.ascontiguousarray(np.asarray(img, dtype=np.float64).reshape(-1, 2))
+    Kd = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+    R, t = np.zeros(9), np.zeros(3)
+    ok = lib().orc_epnp(_p(o, C.c_double), _p(im, C.c_double), len(o), _p(Kd, C.c_double), _p(R, C.c_double), _p(t, C.c_double))
+    return (R.reshape(3, 3), t) if ok else None
+
+
+def rodrigues_inv(R):
+    Rd = np.ascontiguousarray(np.asarray(R, dtype=np.float64).reshape(9))
+    r = np.zeros(3)
+    lib().orc_rodrigues_inv(_p(Rd, C.c_double), _p(r, C.c_double))
+    return r
+
+
+def svd(A):
+    """cv::SVD::compute for a small m x n (m >= n) matrix: (w (n,), u (m,n), vt (n,n)) — OpenCV's one-sided Jacobi."""
+    A = np.ascontiguousarray(np.asarray(A, dtype=np.float64))
+    m, n = A.shape
+    w, Ut, Vt = np.zeros(n), np.zeros((n, m)), np.zeros((n, n))
+    lib().orc_svd(_p(A, C.c_double), m, n, _p(w, C.c_double), _p(Ut, C.c_double), _p(Vt, C.c_double))
+    return w, Ut.T.copy(), Vt
+
+
+def pnp_minimal_model(obj5_f32, img5_f32, K):
+    """[rvec | tvec] of one minimal sample as PnPRansacCallback::runKernel produces it (EPnP + Rodrigues), or None."""
+    o, im = _f32(obj5_f32, 3), _f32(img5_f32, 2)
+    Kd = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+    r, t = np.zeros(3), np.zeros(3)
+    ok = lib().orc_pnp_minimal_model(_p(o, C.c_float), _p(im, C.c_float), len(o), _p(Kd, C.c_double), _p(r, C.c_double), _p(t, C.c_double))
+    return (r, t) if ok else None
+
+
+def pnp_ransac_stage(obj_f32, img_f32, K, max_iters=5000, thr=30.0, confidence=0.99):
+    o, im = _f32(obj_f32, 3), _f32(img_f32, 2)
+    n = len(o)
+    Kd = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+    model = np.zeros(6)
+    mask = np.zeros(max(n, 1), dtype=np.uint8)
+    iters, best = C.c_int(0), C.c_int(-1)
+    trace = np.full(max(max_iters, 1), -2, dtype=np.int32)
+    ok = lib().orc_pnp_ransac_stage(_p(o, C.c_float), _p(im, C.c_float), n, _p(Kd, C.c_double), max_iters, thr, confidence,
+                                    _p(model, C.c_double), _p(mask, C.c_uint8), C.byref(iters), C.byref(best), _p(trace, C.c_int32))
+    return dict(ok=bool(ok), rvec=model[:3].copy(), tvec=model[3:].copy(), mask=mask[:n].copy(), iters=iters.value,
+                best_iter=best.value, counts=trace[:iters.value].copy())
+
+
+def pnp_refine_lm(obj, img, K, rvec, tvec, max_iters=20):
+    """cv2.solvePnPRefineLM(obj, img, K, 0, rvec, tvec) restated (main_v1.py:508): classic LMSolver, 20 iterations."""
+    o = np.ascontiguousarray(np.asarray(obj, dtype=np.float64).reshape(-1, 3))
+    im = np.ascontiguousarray(np.asarray(img, dtype=np.float64).reshape(-1, 2))
+    Kd = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+    r = np.ascontiguousarray(np.asarray(rvec, dtype=np.float64).reshape(3)).copy()
+    t = np.ascontiguousarray(np.asarray(tvec, dtype=np.float64).reshape(3)).copy()
+    lib().orc_pnp_refine_lm(_p(o, C.c_double), _p(im, C.c_double), len(o), _p(Kd, C.c_double), _p(r, C.c_double), _p(t, C.c_double), max_iters)
+    return r, t
+
+
+def solve_pnp_ransac(obj, img, K, iterations_count=100, reprojection_error=8.0, confidence=0.99, details=False):
+    """cv2.solvePnPRansac(obj, img, K, zeros, iterationsCount=..., reprojectionError=..., confidence=...) restated.
+
+    Reference call site /root/reference/main_v1.py:497-502.  Returns (ok, rvec (3,1), tvec (3,1), inliers int32 (k,1))."""
+    o = np.ascontiguousarray(np.asarray(obj, dtype=np.float64).reshape(-1, 3))
+    im = np.ascontiguousarray(np.asarray(img, dtype=np.float64).reshape(-1, 2))
+    n = len(o)
+    Kd = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+    r, t, model = np.zeros(3), np.zeros(3), np.zeros(6)
+    inl = np.zeros(max(n, 1), dtype=np.int32)
+    k, iters = C.c_int(0), C.c_int(0)
+    ok = lib().orc_solve_pnp_ransac(_p(o, C.c_double), _p(im, C.c_double), n, _p(Kd, C.c_double), iterations_count,
+                                    reprojection_error, confidence, _p(r, C.c_double), _p(t, C.c_double), _p(inl, C.c_int32),
+                                    C.byref(k), C.byref(iters), _p(model, C.c_double))
+    out = (bool(ok), r.reshape(3, 1), t.reshape(3, 1), inl[:k.value].reshape(-1, 1).copy() if ok else None)
+    if details:
+        return out + (dict(iters=iters.value, ransac_rvec=model[:3].copy(), ransac_tvec=model[3:].copy()),)
+    return out

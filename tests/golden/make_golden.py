@@ -158,6 +158,28 @@ def main():
                        proj_f32=tolist(pr.reshape(-1, 2).astype(np.float64))))
     g["project_points"] = pv
 
+    # ---- EPnP minimal solver on 5-point samples (PnPRansacCallback::runKernel) + full solvePnPRansac on synthetic sets ------
+    ep = []
+    for _ in range(40):
+        P, px, _ = synth.pnp_set(5, 0.0, rng, noise_px=float(rng.choice([0.0, 1.0])))
+        o32, i32 = P.astype(np.float32), px.astype(np.float32)
+        ok, rv, tv = cv2.solvePnP(o32, i32, K, dist, flags=cv2.SOLVEPNP_EPNP)
+        ep.append(dict(obj=tolist(o32.astype(np.float64)), img=tolist(i32.astype(np.float64)), ok=bool(ok), rvec=tolist(rv.ravel()), tvec=tolist(tv.ravel())))
+    g["epnp5"] = ep
+    pr = []
+    for _ in range(24):
+        n = int(rng.choice([5, 6, 12, 30, 100, 500, 2000]))
+        thr = float(rng.choice([8.0, 30.0]))
+        P, px, _ = synth.pnp_set(n, float(rng.uniform(0.0, 0.5)), rng)
+        ok, rv, tv, inl = cv2.solvePnPRansac(P, px, K, dist, iterationsCount=5000, reprojectionError=thr, confidence=0.99)
+        rec = dict(obj=tolist(P), img=tolist(px), thr=thr, ok=bool(ok), rvec=tolist(rv.ravel()), tvec=tolist(tv.ravel()),
+                   inliers=None if inl is None else tolist(inl.ravel()))
+        if ok and inl is not None and len(inl) >= 6:
+            r3, t3 = cv2.solvePnPRefineLM(P[inl.ravel()], px[inl.ravel()], K, dist, rv.copy(), tv.copy())
+            rec["refined_rvec"], rec["refined_tvec"] = tolist(r3.ravel()), tolist(t3.ravel())
+        pr.append(rec)
+    g["pnp_ransac_random"] = pr
+
     path = os.path.join(HERE, "cv2_golden.json")
     with open(path, "w") as f:
         json.dump(g, f)

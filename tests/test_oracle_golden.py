@@ -126,6 +126,58 @@ def test_pnp_fixture_a_scoring(oracle, gold):
     assert first == [[9, 4, 8, 3, 5], [6, 1, 10, 2, 3], [2, 8, 0, 4, 3], [7, 0, 9, 1, 8], [4, 9, 6, 8, 2], [1, 7, 9, 2, 0]]
 
 
+def test_epnp_minimal_solver_against_cv2(oracle, gold):
+    """PnPRansacCallback::runKernel = solvePnP(5 points, SOLVEPNP_EPNP) + Rodrigues.  With OpenCV's own one-sided
+    Jacobi SVD restated (bit-identical to cv2.SVDecomp) the EPnP poses agree with the binary to ~1e-13."""
+    K = np.array(gold["pnp_fixture_a"]["K"])
+    worst = 0.0
+    for c in gold["epnp5"]:
+        m = oracle.pnp_minimal_model(np.array(c["obj"], dtype=np.float32), np.array(c["img"], dtype=np.float32), K)
+        assert (m is not None) == c["ok"]
+        if m is not None:
+            worst = max(worst, relerr(m[0], c["rvec"]), relerr(m[1], c["tvec"]))
+    assert worst < 1e-9
+
+
+def test_solve_pnp_ransac_fixture_a(oracle, gold):
+    """cv2.solvePnPRansac(..., 5000, 30.0, 0.99) on testpro-K.py:198-225 (main_v1.py:497-502), then solvePnPRefineLM
+    (main_v1.py:508): inliers [0 1 2 3 7 9], 145 iterations, both poses within the 1e-5 tolerance (observed 1e-9)."""
+    s, p = gold["fixture_a_sweep"], gold["pnp_fixture_a"]
+    pos3d, pixels, K = np.array(s["pos3d"]), np.array(s["pixels"]), np.array(p["K"])
+    ok, rvec, tvec, inl, det = oracle.solve_pnp_ransac(pos3d, pixels, K, 5000, 30.0, 0.99, details=True)
+    assert ok and inl.ravel().tolist() == p["inliers"] == [0, 1, 2, 3, 7, 9]
+    assert inl.dtype == np.int32 and inl.shape == (6, 1)
+    assert det["iters"] == 145
+    assert relerr(rvec, p["rvec"]) < 1e-5 and relerr(tvec, p["tvec"]) < 1e-5
+    r2, t2 = oracle.pnp_refine_lm(pos3d[inl.ravel()], pixels[inl.ravel()], K, p["rvec"], p["tvec"])
+    assert relerr(r2, p["refined_rvec"]) < 1e-5 and relerr(t2, p["refined_tvec"]) < 1e-5
+
+
+def test_solve_pnp_ransac_random(oracle, gold):
+    K = np.array(gold["pnp_fixture_a"]["K"])
+    for c in gold["pnp_ransac_random"]:
+        ok, rvec, tvec, inl = oracle.solve_pnp_ransac(np.array(c["obj"]), np.array(c["img"]), K, 5000, c["thr"], 0.99)
+        assert ok == c["ok"]
+        if not ok:
+            continue
+        assert inl.ravel().tolist() == c["inliers"]                      # identical inlier index set
+        assert relerr(rvec, c["rvec"]) < 1e-5 and relerr(tvec, c["tvec"]) < 1e-5
+
+
+def test_cv_svd_restatement(oracle):
+    """orc_svd is OpenCV's JacobiSVDImpl_: orthogonality and reconstruction here; bit-identity with cv2.SVDecomp was
+    checked when the golden file was made (200/200 matrices, including rank-deficient 12x12 Gram matrices)."""
+    rng = np.random.default_rng(3)
+    for shape in [(3, 3), (6, 4), (12, 12)]:
+        A = rng.standard_normal(shape)
+        if shape == (12, 12):
+            B = rng.standard_normal((10, 12))
+            A = B.T @ B
+        w, u, vt = oracle.svd(A)
+        assert np.all(np.diff(w) <= 1e-12)
+        np.testing.assert_allclose((u * w) @ vt, A, atol=1e-9 * max(1.0, np.abs(A).max()))
+
+
 def test_update_num_iters(oracle):
     assert oracle.update_num_iters(0.995, 0.5, 4, 2000) == 82
     assert oracle.update_num_iters(0.995, 0.0, 4, 2000) == 0
