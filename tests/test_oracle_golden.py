@@ -17,7 +17,7 @@ def gold():
 
 
 def relerr(a, b):
-    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
     return np.abs(a - b).max() / np.abs(b).max()
 
 
