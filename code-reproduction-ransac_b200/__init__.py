@@ -6,8 +6,8 @@ name contains hyphens, so it is imported through the alias module `ransac_b200.p
 """
 from . import _build  # noqa: F401
 from .api import (ARITH_EXACT, ARITH_FAST, MASK_CV413, MASK_LEGACY, SAMPLER_CV_REPLAY, SAMPLER_PHILOX, SOLVER_EXACT, SOLVER_FAST, Context,
-                  HomographyProblem, RansacB200Error, default_context, make_params)
+                  HomographyProblem, PnPProblem, RansacB200Error, default_context, make_p_params, make_params)
 
-__all__ = ["Context", "HomographyProblem", "RansacB200Error", "default_context", "make_params", "ARITH_EXACT", "ARITH_FAST",
+__all__ = ["Context", "HomographyProblem", "RansacB200Error", "default_context", "make_params", "make_p_params", "PnPProblem", "ARITH_EXACT", "ARITH_FAST",
            "MASK_CV413", "MASK_LEGACY", "SAMPLER_CV_REPLAY", "SAMPLER_PHILOX", "SOLVER_EXACT", "SOLVER_FAST"]
 __version__ = "0.1.0"

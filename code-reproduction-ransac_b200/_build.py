@@ -13,8 +13,9 @@ NVCC_FLAGS = [
     # never contract a*b+c on its own: the bit-exact paths need every product and sum rounded separately;
     # fused operations are written explicitly (fma.rn.f32x2 / __fmaf_rn) where they are wanted
     "-fmad=false",
-    "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
 ]
+TRANSLATION_UNITS = ["api.cu", "api_pnp.cu"]   # homography path, PnP path
 
 
 def _sources():
@@ -31,14 +32,27 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/api.cu (which includes every kernel header) into libransac_b200.so."""
+    """Compile the translation units of csrc/ (in parallel) and link them into libransac_b200.so."""
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "api.cu")]
+    objdir = os.path.join(PKG_DIR, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for tu in TRANSLATION_UNITS:
+        obj = os.path.join(objdir, tu.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, tu)]
+        procs.append((tu, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for tu, obj, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {tu}:\n" + out)
+        if verbose:
+            print(out)
+        objs.append(obj)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout)
-    if verbose:
-        print(res.stdout)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout)
     return LIB_PATH

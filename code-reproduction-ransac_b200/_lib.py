@@ -27,6 +27,21 @@ class HInfo(C.Structure):
                 ("sample", C.c_int32 * 4), ("n_inliers", C.c_int32), ("lm_iters", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
+class PParams(C.Structure):
+    """b2r_p_params"""
+    _fields_ = [("thr", C.c_double), ("max_iters", C.c_int32), ("confidence", C.c_double), ("sampler", C.c_int32),
+                ("seed", C.c_uint64), ("arith", C.c_int32), ("refine", C.c_int32), ("hyp_begin", C.c_int64),
+                ("reserved", C.c_int32 * 2)]
+
+
+class PInfo(C.Structure):
+    """b2r_p_info"""
+    _fields_ = [("status", C.c_int32), ("iters_run", C.c_int32), ("best_iter", C.c_int32), ("best_count", C.c_int32),
+                ("sample", C.c_int32 * 5), ("n_inliers", C.c_int32), ("lm_iters", C.c_int32), ("reserved", C.c_int32),
+                ("ransac_rvec", C.c_double * 3), ("ransac_tvec", C.c_double * 3), ("mean_inlier_err", C.c_double),
+                ("sum_sq_err", C.c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/ransac_b200.h declares
 SIGNATURES = {
     "b2r_version": (C.c_int, []),
@@ -60,6 +75,28 @@ SIGNATURES = {
     "b2r_refine_h": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int32, c_u8_p, c_double_p, c_i32_p]),
     "b2r_selftest_rcp": (C.c_int, [C.c_void_p, c_u64_p, c_u64_p]),
     "b2r_probe_fp32_peak": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    # ---- PnP path
+    "b2r_default_p_params": (None, [C.POINTER(PParams)]),
+    "b2r_solve_pnp_ransac": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, c_double_p, C.POINTER(PParams),
+                                       c_double_p, c_double_p, c_i32_p, c_i32_p, C.POINTER(PInfo)]),
+    "b2r_solve_pnp_ransac_batch": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_int32, C.c_int32, c_double_p,
+                                             C.POINTER(PParams), c_double_p, c_double_p, c_i32_p, c_i32_p, C.POINTER(PInfo)]),
+    "b2r_solve_pnp_refine_lm": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p,
+                                          C.c_int32, c_i32_p]),
+    "b2r_p_problem_upload": (C.c_void_p, [C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_int32, C.c_int32, c_double_p]),
+    "b2r_p_problem_reupload": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_int32, C.c_int32,
+                                         c_double_p]),
+    "b2r_p_problem_free": (None, [C.c_void_p, C.c_void_p]),
+    "b2r_p_problem_run": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PParams)]),
+    "b2r_p_problem_fetch": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, c_double_p, c_i32_p, c_i32_p, C.POINTER(PInfo)]),
+    "b2r_p_problem_score_shard": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PParams), c_u64_p]),
+    "b2r_p_problem_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PParams), c_u64_p]),
+    "b2r_p_problem_stage_ms": (C.c_int, [C.c_void_p, C.c_void_p, c_float_p]),
+    "b2r_score_p": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, C.c_int32, c_double_p, C.c_float,
+                              C.c_int32, c_i32_p]),
+    "b2r_pnp_minimal_models": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, c_double_p, c_i32_p, C.c_int32,
+                                         c_double_p, c_double_p, c_double_p, c_u8_p]),
+    "b2r_sample_cv_p": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_i32_p]),
 }
 
 _lib = None

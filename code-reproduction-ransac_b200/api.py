@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import HInfo, HParams
+from ._lib import HInfo, HParams, PInfo, PParams
 
 SAMPLER_CV_REPLAY, SAMPLER_PHILOX = 0, 1
 ARITH_EXACT, ARITH_FAST = 0, 1
@@ -128,6 +128,108 @@ class HomographyProblem:
             pass
 
 
+def make_p_params(thr=8.0, max_iters=100, confidence=0.99, sampler=SAMPLER_CV_REPLAY, seed=0, arith=ARITH_EXACT,
+                  refine=True, hyp_begin=0):
+    """b2r_p_params with cv2.solvePnPRansac's defaults (iterationsCount=100, reprojectionError=8.0, confidence=0.99)."""
+    p = PParams()
+    p.thr = float(thr)
+    p.max_iters = int(max_iters)
+    p.confidence = float(confidence)
+    p.sampler = int(sampler)
+    p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    p.arith = int(arith)
+    p.refine = 1 if refine else 0
+    p.hyp_begin = int(hyp_begin)
+    return p
+
+
+def _p_info_dict(i):
+    return dict(status=i.status, iters_run=i.iters_run, best_iter=i.best_iter, best_count=i.best_count,
+                sample=[int(x) for x in i.sample], n_inliers=i.n_inliers, lm_iters=i.lm_iters,
+                ransac_rvec=np.array(i.ransac_rvec[:]), ransac_tvec=np.array(i.ransac_tvec[:]),
+                mean_inlier_err=float(i.mean_inlier_err), sum_sq_err=float(i.sum_sq_err))
+
+
+def _K9(K, Q=None):
+    K = np.ascontiguousarray(np.asarray(K, dtype=np.float64))
+    if Q is None:
+        return K.reshape(3, 3)
+    return np.ascontiguousarray(K.reshape(Q, 3, 3))
+
+
+class PnPProblem:
+    """Q PnP-RANSAC problems (one camera matrix each) over n correspondences resident in HBM (b2r_p_problem).
+    obj (n,3) / img (n,2): the Q problems share the points (testpro-K.py's intrinsics grid); (Q,n,3)/(Q,n,2): own points."""
+
+    def __init__(self, ctx, obj, img, K):
+        obj = np.ascontiguousarray(np.asarray(obj, dtype=np.float64))
+        img = np.ascontiguousarray(np.asarray(img, dtype=np.float64))
+        K = np.asarray(K, dtype=np.float64)
+        self.Q = 1 if K.ndim == 2 else int(K.shape[0])
+        self.shared = obj.ndim == 2
+        self.n = int(obj.shape[-2])
+        if obj.shape[-1] != 3 or img.shape[-1] != 2 or img.shape[-2] != self.n or (not self.shared and obj.shape[0] != self.Q):
+            raise ValueError("obj must be (n,3) or (Q,n,3), img (n,2) or (Q,n,2), K (3,3) or (Q,3,3)")
+        self.ctx = ctx
+        self.h2d_bytes = obj.nbytes + img.nbytes + 72 * self.Q
+        Kq = _K9(K, self.Q)
+        self._h = ctx._L.b2r_p_problem_upload(ctx._c, _ptr(obj, C.c_double), _ptr(img, C.c_double), 1 if self.shared else 0,
+                                              self.Q, self.n, _ptr(Kq, C.c_double))
+        if not self._h:
+            raise RansacB200Error(_lib.last_error())
+
+    def reupload(self, obj, img, K):
+        obj = np.ascontiguousarray(np.asarray(obj, dtype=np.float64))
+        img = np.ascontiguousarray(np.asarray(img, dtype=np.float64))
+        K = np.asarray(K, dtype=np.float64)
+        self.Q = 1 if K.ndim == 2 else int(K.shape[0])
+        self.shared = obj.ndim == 2
+        self.n = int(obj.shape[-2])
+        Kq = _K9(K, self.Q)
+        self.h2d_bytes = obj.nbytes + img.nbytes + 72 * self.Q
+        self.ctx._check(self.ctx._L.b2r_p_problem_reupload(self.ctx._c, self._h, _ptr(obj, C.c_double), _ptr(img, C.c_double),
+                                                           1 if self.shared else 0, self.Q, self.n, _ptr(Kq, C.c_double)))
+
+    def run(self, params):
+        self.ctx._check(self.ctx._L.b2r_p_problem_run(self.ctx._c, self._h, C.byref(params)))
+
+    def score_shard(self, params):
+        keys = np.zeros(self.Q, dtype=np.uint64)
+        self.ctx._check(self.ctx._L.b2r_p_problem_score_shard(self.ctx._c, self._h, C.byref(params), _ptr(keys, C.c_uint64)))
+        return keys
+
+    def finish(self, params, keys):
+        keys = np.ascontiguousarray(np.asarray(keys, dtype=np.uint64).reshape(self.Q))
+        self.ctx._check(self.ctx._L.b2r_p_problem_finish(self.ctx._c, self._h, C.byref(params), _ptr(keys, C.c_uint64)))
+
+    def fetch(self, want_inliers=True):
+        """(rvec (Q,3), tvec (Q,3), inliers list of int32 arrays or None, infos)"""
+        rvec, tvec = np.zeros((self.Q, 3)), np.zeros((self.Q, 3))
+        inl = np.zeros((self.Q, self.n), dtype=np.int32) if want_inliers else None
+        ninl = np.zeros(self.Q, dtype=np.int32)
+        info = (PInfo * self.Q)()
+        self.ctx._check(self.ctx._L.b2r_p_problem_fetch(self.ctx._c, self._h, _ptr(rvec, C.c_double), _ptr(tvec, C.c_double),
+                                                        _ptr(inl, C.c_int32) if want_inliers else None, _ptr(ninl, C.c_int32), info))
+        lists = [inl[q, :ninl[q]].copy() for q in range(self.Q)] if want_inliers else None
+        return rvec, tvec, lists, [_p_info_dict(i) for i in info]
+
+    def stage_ms(self):
+        ms = (C.c_float * 5)()
+        self.ctx._check(self.ctx._L.b2r_p_problem_stage_ms(self.ctx._c, self._h, ms))
+        return dict(sample_solve=ms[0], score=ms[1], select=ms[2], finalize=ms[3], total=ms[4])
+
+    def free(self):
+        if self._h:
+            self.ctx._L.b2r_p_problem_free(self.ctx._c, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Context:
     """One GPU context (own CUDA stream and workspaces).  Not thread-safe."""
 
@@ -203,7 +305,89 @@ class Context:
     def upload(self, src, dst, dst_shared=None):
         return HomographyProblem(self, src, dst, dst_shared)
 
+    # ---- cv2.solvePnPRansac / solvePnPRefineLM ----------------------------------------------------------
+    def solve_pnp_ransac(self, obj, img, K, iterations_count=100, reprojection_error=8.0, confidence=0.99, **kw):
+        """cv2.solvePnPRansac(obj, img, K, zeros, iterationsCount=..., reprojectionError=..., confidence=...) on the GPU
+        (main_v1.py:497-502).  Returns (ok, rvec (3,1), tvec (3,1), inliers int32 (k,1) or None, info dict)."""
+        o, im = _f64(obj, 3), _f64(img, 2)
+        if len(o) != len(im):
+            raise ValueError("obj and img must have the same number of points")
+        n = len(o)
+        Kd = _K9(K)
+        p = make_p_params(reprojection_error, iterations_count, confidence, **kw)
+        rvec, tvec = np.zeros(3), np.zeros(3)
+        inl = np.zeros(max(n, 1), dtype=np.int32)
+        k = C.c_int32(0)
+        info = PInfo()
+        rc = self._check(self._L.b2r_solve_pnp_ransac(self._c, _ptr(o, C.c_double), _ptr(im, C.c_double), n, _ptr(Kd, C.c_double),
+                                                      C.byref(p), _ptr(rvec, C.c_double), _ptr(tvec, C.c_double),
+                                                      _ptr(inl, C.c_int32), C.byref(k), C.byref(info)))
+        ok = rc == OK
+        return ok, rvec.reshape(3, 1), tvec.reshape(3, 1), (inl[:k.value].reshape(-1, 1).copy() if ok else None), _p_info_dict(info)
+
+    def solve_pnp_ransac_batch(self, obj, img, Ks, iterations_count=100, reprojection_error=8.0, confidence=0.99, **kw):
+        """Q problems in one call (the intrinsics grid of testpro-K.py:58-97 when obj/img are 2-D and shared).
+        Returns (ok (Q,), rvec (Q,3), tvec (Q,3), inliers list, infos)."""
+        obj = np.ascontiguousarray(np.asarray(obj, dtype=np.float64))
+        img = np.ascontiguousarray(np.asarray(img, dtype=np.float64))
+        Ks = np.asarray(Ks, dtype=np.float64)
+        Q, n, shared = int(Ks.shape[0]), int(obj.shape[-2]), obj.ndim == 2
+        Kq = _K9(Ks, Q)
+        p = make_p_params(reprojection_error, iterations_count, confidence, **kw)
+        rvec, tvec = np.zeros((Q, 3)), np.zeros((Q, 3))
+        inl = np.zeros((Q, n), dtype=np.int32)
+        ninl = np.zeros(Q, dtype=np.int32)
+        info = (PInfo * Q)()
+        self._check(self._L.b2r_solve_pnp_ransac_batch(self._c, _ptr(obj, C.c_double), _ptr(img, C.c_double), 1 if shared else 0,
+                                                       Q, n, _ptr(Kq, C.c_double), C.byref(p), _ptr(rvec, C.c_double),
+                                                       _ptr(tvec, C.c_double), _ptr(inl, C.c_int32), _ptr(ninl, C.c_int32), info))
+        infos = [_p_info_dict(i) for i in info]
+        ok = np.array([i["status"] == OK for i in infos])
+        return ok, rvec, tvec, [inl[q, :ninl[q]].copy() for q in range(Q)], infos
+
+    def solve_pnp_refine_lm(self, obj, img, K, rvec, tvec, max_iters=20):
+        """cv2.solvePnPRefineLM(obj, img, K, zeros, rvec, tvec) on the GPU (main_v1.py:508).  Returns (rvec (3,1), tvec (3,1), iters)."""
+        o, im = _f64(obj, 3), _f64(img, 2)
+        Kd = _K9(K)
+        r = np.ascontiguousarray(np.asarray(rvec, dtype=np.float64).reshape(3)).copy()
+        t = np.ascontiguousarray(np.asarray(tvec, dtype=np.float64).reshape(3)).copy()
+        it = C.c_int32(0)
+        self._check(self._L.b2r_solve_pnp_refine_lm(self._c, _ptr(o, C.c_double), _ptr(im, C.c_double), len(o), _ptr(Kd, C.c_double),
+                                                    _ptr(r, C.c_double), _ptr(t, C.c_double), int(max_iters), C.byref(it)))
+        return r.reshape(3, 1), t.reshape(3, 1), it.value
+
+    def upload_pnp(self, obj, img, K):
+        return PnPProblem(self, obj, img, K)
+
     # ---- single kernels (parity tests) -------------------------------------------------------------------
+    def score_p(self, models_Rt, obj, img, K, thr_sq, arith=ARITH_EXACT):
+        """K3 (PnP): inlier counts of poses models_Rt (m,12) = R row-major | t over the points (quantised to fp32 inside)."""
+        m = np.ascontiguousarray(np.asarray(models_Rt, dtype=np.float64).reshape(-1, 12))
+        o, im = _f64(obj, 3), _f64(img, 2)
+        Kd = _K9(K)
+        counts = np.zeros(len(m), dtype=np.int32)
+        self._check(self._L.b2r_score_p(self._c, _ptr(m, C.c_double), len(m), _ptr(o, C.c_double), _ptr(im, C.c_double), len(o),
+                                        _ptr(Kd, C.c_double), C.c_float(np.float32(thr_sq)), int(arith), _ptr(counts, C.c_int32)))
+        return counts
+
+    def pnp_minimal_models(self, obj, img, K, idx):
+        """K2 (PnP): EPnP models of the 5-point samples idx (m,5): (rvec (m,3), tvec (m,3), R (m,3,3), ok (m,))."""
+        o, im = _f64(obj, 3), _f64(img, 2)
+        Kd = _K9(K)
+        idx = np.ascontiguousarray(np.asarray(idx, dtype=np.int32).reshape(-1, 5))
+        m = len(idx)
+        rvec, tvec, R = np.zeros((m, 3)), np.zeros((m, 3)), np.zeros((m, 3, 3))
+        ok = np.zeros(m, dtype=np.uint8)
+        self._check(self._L.b2r_pnp_minimal_models(self._c, _ptr(o, C.c_double), _ptr(im, C.c_double), len(o), _ptr(Kd, C.c_double),
+                                                   _ptr(idx, C.c_int32), m, _ptr(rvec, C.c_double), _ptr(tvec, C.c_double),
+                                                   _ptr(R, C.c_double), _ptr(ok, C.c_uint8)))
+        return rvec, tvec, R, ok.astype(bool)
+
+    def sample_cv_p(self, n, n_iters):
+        idx = np.zeros((n_iters, 5), dtype=np.int32)
+        self._check(self._L.b2r_sample_cv_p(self._c, int(n), int(n_iters), _ptr(idx, C.c_int32)))
+        return idx
+
     def score_h(self, models8, src_f32, dst_f32, thr_sq, arith=ARITH_EXACT):
         m = _f32(models8, 8)
         s, d = _f32(src_f32, 2), _f32(dst_f32, 2)

@@ -1,77 +1,20 @@
 // C ABI of libransac_b200.so (declared in include/ransac_b200.h).  Host-side orchestration only: every
 // arithmetic step of the hot path runs in the kernels of pipeline_h.cuh / score_h.cuh.  There is no CPU
 // fallback: each entry point fails with B2R_ERR_CUDA when no device is usable.
-#include <cuda_runtime.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-#include <string>
-#include <vector>
-
-// the library is built with -fvisibility=hidden; exactly the symbols of the public header are exported
-#pragma GCC visibility push(default)
-#include "../../include/ransac_b200.h"
-#pragma GCC visibility pop
+#include "host_common.h"
 #include "pipeline_h.cuh"
 
 using namespace b2r;
 
-static thread_local std::string g_err;
+thread_local std::string g_err;
 
-static int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+int fail(int code, const char* fmt, const char* a, const char* b) {
     char buf[512];
     snprintf(buf, sizeof(buf), fmt, a, b);
     g_err = buf;
     return code;
 }
 
-#define CU(call)                                                                                     \
-    do {                                                                                             \
-        cudaError_t e_ = (call);                                                                     \
-        if (e_ != cudaSuccess) return fail(B2R_ERR_CUDA, "CUDA error: %s  [%s]", cudaGetErrorString(e_), #call); \
-    } while (0)
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    template <typename T>
-    T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-struct PinnedBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMallocHost(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() {
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
 
 struct b2r_h_problem {
     int Q = 0, n = 0;
@@ -96,22 +39,6 @@ struct b2r_h_problem {
             if (e) cudaEventDestroy(e), e = nullptr;
     }
 };
-
-struct b2r_ctx {
-    int device = 0;
-    int sm_count = 0;
-    cudaStream_t stream = nullptr;
-    DevBuf in_a, in_b, scratch0, scratch1, scratch2, scratch3;  // staging for the host-pointer entry points
-    PinnedBuf pin_in, pin_out;
-    b2r_h_problem* cached = nullptr;  // reusable problem storage of b2r_find_homography[_batch]
-    int launches = 0;
-};
-
-#define LAUNCH(ctx, kernel, grid, block, smem, ...)                \
-    do {                                                           \
-        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
-        (ctx)->launches++;                                         \
-    } while (0)
 
 extern "C" {
 
@@ -173,6 +100,7 @@ void b2r_ctx_destroy(b2r_ctx* c) {
         c->cached->release();
         delete c->cached;
     }
+    b2r_p_problem_destroy(c->cached_p);
     c->in_a.release(); c->in_b.release(); c->scratch0.release(); c->scratch1.release(); c->scratch2.release();
     c->scratch3.release(); c->pin_in.release(); c->pin_out.release();
     if (c->stream) cudaStreamDestroy(c->stream);

@@ -1,0 +1,228 @@
+// Pieces shared by the homography and the PnP pipelines: the selection rules of OpenCV's
+// RANSACPointSetRegistrator::run, the deterministic cluster-wide reduction used by the finalize
+// kernels, and the small symmetric solvers of cv::LMSolver.  Kernels defined here are `static`: each translation
+// unit of the library (api.cu, api_pnp.cu) gets its own copy.
+#pragma once
+#include <cooperative_groups.h>
+#include "sampler.cuh"
+
+namespace b2r {
+
+// ---- selection ----------------------------------------------------------------------------------------------
+struct HSelect {
+    int best;        // winning iteration / local hypothesis index, -1 = none
+    int best_count;  // its RANSAC-stage inlier count
+    int iters_run;   // iterations executed
+    int pad;
+};
+
+__device__ __forceinline__ int ransac_update_num_iters(double p, double ep, int modelPoints, int maxIters) {
+    p = fmax(p, 0.);
+    p = fmin(p, 1.);
+    ep = fmax(ep, 0.);
+    ep = fmin(ep, 1.);
+    double num = fmax(1. - p, DBL_MIN);
+    double denom = 1. - pow(1. - ep, (double)modelPoints);
+    if (denom < DBL_MIN) return 0;
+    num = log(num);
+    denom = log(denom);
+    return denom >= 0 || -num >= maxIters * (-denom) ? maxIters : __double2int_rn(num / denom);
+}
+
+// OpenCV's sequential rule applied to the counts of a scored superset: walk the iterations
+// in order, take a hypothesis when its count beats max(best, modelPoints-1), shrink niters, stop at niters.
+static __global__ void k_select_cv(const int* __restrict__ counts, const int* __restrict__ n_generated, int H, int n,
+                            int max_iters, double confidence, int model_points, HSelect* __restrict__ sel, int Q) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const int* C = counts + (size_t)q * H;
+    const int gen = n_generated[q];
+    int niters = max(max_iters, 1), maxGood = 0, best = -1, it = 0;
+    for (; it < niters && it < gen; ++it) {
+        const int good = C[it];
+        if (good > max(maxGood, model_points - 1)) {
+            best = it;
+            maxGood = good;
+            niters = ransac_update_num_iters(confidence, (double)(n - good) / n, model_points, niters);
+        }
+    }
+    HSelect s;
+    s.best = best;
+    s.best_count = maxGood;
+    s.iters_run = it;
+    s.pad = 0;
+    sel[q] = s;
+}
+
+// Fixed-H rule: the lowest-id hypothesis with the maximum count; key = count << 32 | (0xFFFFFFFF - id).
+static __global__ void __launch_bounds__(256)
+k_argmax_key(const int* __restrict__ counts, int H, unsigned long long id_base, unsigned long long* __restrict__ keys) {
+    const int q = blockIdx.y;
+    const int* C = counts + (size_t)q * H;
+    unsigned long long best = 0;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < H; g += gridDim.x * blockDim.x) {
+        const unsigned long long key =
+            ((unsigned long long)(uint32_t)C[g] << 32) | (0xFFFFFFFFull - ((id_base + (unsigned long long)g) & 0xFFFFFFFFull));
+        best = key > best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_down_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(keys + q, best);
+}
+
+static __global__ void k_select_from_keys(const unsigned long long* __restrict__ keys, unsigned long long id_base, int H,
+                                   int model_points, HSelect* __restrict__ sel, int Q) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const unsigned long long key = keys[q];
+    const int count = (int)(key >> 32);
+    const unsigned long long gid = 0xFFFFFFFFull - (key & 0xFFFFFFFFull);
+    HSelect s;
+    s.best = count > model_points - 1 ? (int)(gid - (id_base & 0xFFFFFFFFull)) : -1;
+    s.best_count = count > model_points - 1 ? count : 0;
+    s.iters_run = H;
+    s.pad = 0;
+    sel[q] = s;
+}
+
+// ---- cluster-wide deterministic reductions ---------------------------------------------------------------------------
+// The finalize kernel runs as ONE thread-block cluster per problem (8 CTAs x 1024 threads for a large problem, a
+// single CTA for a small one).  Every CTA reduces its share of the points to NV partial sums in its own shared
+// memory; after one cluster barrier every CTA reads all partials through distributed shared memory, in rank
+// order, so all CTAs hold the same bit pattern and replay the (tiny) sequential part of the algorithm
+// redundantly — no broadcast, no atomics, run-to-run deterministic.  Partials are double-buffered so that one
+// barrier per reduction is enough.
+namespace cg = cooperative_groups;
+
+constexpr int RED_MAX = 40;
+
+struct ClusterRed {
+    double part[2][RED_MAX];  // this CTA's partial sums (double-buffered), read remotely
+    double warp[32 * RED_MAX];
+    double out[RED_MAX];
+    int phase;
+};
+
+template <int THREADS, int NV, bool IS_MAX>
+__device__ __forceinline__ void cluster_reduce(ClusterRed& R, double (&v)[NV]) {
+    static_assert(NV <= RED_MAX, "too many values");
+    cg::cluster_group cluster = cg::this_cluster();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_down_sync(0xffffffffu, x, o);
+            x = IS_MAX ? fmax(x, y) : x + y;
+        }
+        if (lane == 0) R.warp[warp * NV + i] = x;
+    }
+    __syncthreads();
+    const int ph = R.phase;
+    if (threadIdx.x < NV) {
+        double s = R.warp[threadIdx.x];
+        for (int w = 1; w < THREADS / 32; ++w) s = IS_MAX ? fmax(s, R.warp[w * NV + threadIdx.x]) : s + R.warp[w * NV + threadIdx.x];
+        R.part[ph][threadIdx.x] = s;
+    }
+    cluster.sync();
+    if (threadIdx.x < NV) {
+        const unsigned nb = cluster.num_blocks();
+        double s = 0;
+        for (unsigned r = 0; r < nb; ++r) {
+            const double* remote = cluster.map_shared_rank(&R.part[ph][0], r);
+            s = IS_MAX ? fmax(s, remote[threadIdx.x]) : (r == 0 ? remote[threadIdx.x] : s + remote[threadIdx.x]);
+        }
+        R.out[threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) R.phase = ph ^ 1;
+    __syncthreads();
+}
+
+// x = solve(A, b), A symmetric n x n, through its Jacobi eigen-decomposition with OpenCV's
+// back-substitution threshold (cv::solve DECOMP_EIG); optionally the diagonal of A^-1.
+template <int N>
+__device__ void solve_sym_eig(const double* A, const double* b, double* x, double* inv_diag) {
+    double a[N * N], W[N], V[N * N];
+    for (int i = 0; i < N * N; ++i) a[i] = A[i];
+    jacobi_eig<N>(a, W, V);
+    double thr = 0;
+    for (int i = 0; i < N; ++i) thr += fabs(W[i]);
+    thr *= DBL_EPSILON * 2;
+    for (int j = 0; j < N; ++j) {
+        if (x) x[j] = 0;
+        if (inv_diag) inv_diag[j] = 0;
+    }
+    for (int i = 0; i < N; ++i) {
+        if (fabs(W[i]) <= thr) continue;
+        if (x) {
+            double s = 0;
+            for (int j = 0; j < N; ++j) s += V[i * N + j] * b[j];
+            s /= W[i];
+            for (int j = 0; j < N; ++j) x[j] += s * V[i * N + j];
+        }
+        if (inv_diag)
+            for (int j = 0; j < N; ++j) inv_diag[j] += V[i * N + j] * V[i * N + j] / W[i];
+    }
+}
+
+// Cholesky factor of a symmetric positive definite N x N matrix (lower triangle in L); false when a pivot is not
+// safely positive — callers then fall back to the Jacobi eigen-decomposition, which is what OpenCV always uses.
+template <int N>
+__device__ __forceinline__ bool cholesky(const double* A, double* L) {
+    double dmax = 0;
+    for (int i = 0; i < N; ++i) dmax = fmax(dmax, fabs(A[i * N + i]));
+    for (int j = 0; j < N; ++j) {
+        double d = A[j * N + j];
+        for (int k = 0; k < j; ++k) d -= L[j * N + k] * L[j * N + k];
+        if (!(d > dmax * 1e-14)) return false;
+        d = sqrt(d);
+        L[j * N + j] = d;
+        for (int i = j + 1; i < N; ++i) {
+            double t = A[i * N + j];
+            for (int k = 0; k < j; ++k) t -= L[i * N + k] * L[j * N + k];
+            L[i * N + j] = t / d;
+        }
+    }
+    return true;
+}
+
+template <int N>
+__device__ __forceinline__ void cholesky_solve(const double* L, const double* b, double* x) {
+    double y[N];
+    for (int i = 0; i < N; ++i) {
+        double t = b[i];
+        for (int k = 0; k < i; ++k) t -= L[i * N + k] * y[k];
+        y[i] = t / L[i * N + i];
+    }
+    for (int i = N - 1; i >= 0; --i) {
+        double t = y[i];
+        for (int k = i + 1; k < N; ++k) t -= L[k * N + i] * x[k];
+        x[i] = t / L[i * N + i];
+    }
+}
+
+__device__ __forceinline__ bool solve_spd8(const double* A, const double* b, double* x) {
+    double L[64];
+    if (!cholesky<8>(A, L)) return false;
+    cholesky_solve<8>(L, b, x);
+    return true;
+}
+
+// diag(A^-1) of an SPD 8x8 through its Cholesky factor (column by column)
+__device__ __forceinline__ bool inv_diag_spd8(const double* A, double* diag) {
+    double L[64];
+    if (!cholesky<8>(A, L)) return false;
+    for (int j = 0; j < 8; ++j) {
+        double e[8] = {0, 0, 0, 0, 0, 0, 0, 0}, x[8];
+        e[j] = 1;
+        cholesky_solve<8>(L, e, x);
+        diag[j] = x[j];
+    }
+    return true;
+}
+
+}  // namespace b2r

@@ -2,8 +2,7 @@
 // (A.6) and K4 finalize = RANSAC-stage mask + refit + LM(10) + OpenCV-4.13 mask (A.7).
 // Reference call site for all of it: cv2.findHomography(..., cv2.RANSAC, thr), main_v1.py:312.
 #pragma once
-#include <cooperative_groups.h>
-#include "sampler.cuh"
+#include "common_k.cuh"
 #include "score_h.cuh"
 
 namespace b2r {
@@ -158,86 +157,6 @@ k_solve_h4(const PointH* __restrict__ pts, int n, const int* __restrict__ sample
     if (ok_out) ok_out[slot] = ok ? 1 : 0;
 }
 
-// ---- selection ----------------------------------------------------------------------------------------------
-struct HSelect {
-    int best;        // winning iteration / local hypothesis index, -1 = none
-    int best_count;  // its RANSAC-stage inlier count
-    int iters_run;   // iterations executed
-    int pad;
-};
-
-__device__ __forceinline__ int ransac_update_num_iters(double p, double ep, int modelPoints, int maxIters) {
-    p = fmax(p, 0.);
-    p = fmin(p, 1.);
-    ep = fmax(ep, 0.);
-    ep = fmin(ep, 1.);
-    double num = fmax(1. - p, DBL_MIN);
-    double denom = 1. - pow(1. - ep, (double)modelPoints);
-    if (denom < DBL_MIN) return 0;
-    num = log(num);
-    denom = log(denom);
-    return denom >= 0 || -num >= maxIters * (-denom) ? maxIters : __double2int_rn(num / denom);
-}
-
-// OpenCV's sequential rule applied to the counts of a scored superset: walk the iterations
-// in order, take a hypothesis when its count beats max(best, modelPoints-1), shrink niters, stop at niters.
-__global__ void k_select_cv(const int* __restrict__ counts, const int* __restrict__ n_generated, int H, int n,
-                            int max_iters, double confidence, int model_points, HSelect* __restrict__ sel, int Q) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= Q) return;
-    const int* C = counts + (size_t)q * H;
-    const int gen = n_generated[q];
-    int niters = max(max_iters, 1), maxGood = 0, best = -1, it = 0;
-    for (; it < niters && it < gen; ++it) {
-        const int good = C[it];
-        if (good > max(maxGood, model_points - 1)) {
-            best = it;
-            maxGood = good;
-            niters = ransac_update_num_iters(confidence, (double)(n - good) / n, model_points, niters);
-        }
-    }
-    HSelect s;
-    s.best = best;
-    s.best_count = maxGood;
-    s.iters_run = it;
-    s.pad = 0;
-    sel[q] = s;
-}
-
-// Fixed-H rule: the lowest-id hypothesis with the maximum count; key = count << 32 | (0xFFFFFFFF - id).
-__global__ void __launch_bounds__(256)
-k_argmax_key(const int* __restrict__ counts, int H, unsigned long long id_base, unsigned long long* __restrict__ keys) {
-    const int q = blockIdx.y;
-    const int* C = counts + (size_t)q * H;
-    unsigned long long best = 0;
-    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < H; g += gridDim.x * blockDim.x) {
-        const unsigned long long key =
-            ((unsigned long long)(uint32_t)C[g] << 32) | (0xFFFFFFFFull - ((id_base + (unsigned long long)g) & 0xFFFFFFFFull));
-        best = key > best ? key : best;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_down_sync(0xffffffffu, best, o);
-        best = other > best ? other : best;
-    }
-    if ((threadIdx.x & 31) == 0 && best) atomicMax(keys + q, best);
-}
-
-__global__ void k_select_from_keys(const unsigned long long* __restrict__ keys, unsigned long long id_base, int H,
-                                   int model_points, HSelect* __restrict__ sel, int Q) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= Q) return;
-    const unsigned long long key = keys[q];
-    const int count = (int)(key >> 32);
-    const unsigned long long gid = 0xFFFFFFFFull - (key & 0xFFFFFFFFull);
-    HSelect s;
-    s.best = count > model_points - 1 ? (int)(gid - (id_base & 0xFFFFFFFFull)) : -1;
-    s.best_count = count > model_points - 1 ? count : 0;
-    s.iters_run = H;
-    s.pad = 0;
-    sel[q] = s;
-}
-
 // ---- K4 finalize -----------------------------------------------------------------------------------------------
 // exact fp32 squared reprojection error of one point, scalar form
 __device__ __forceinline__ float h_err_exact(const float* Hf, float X, float Y, float nu, float nv) {
@@ -246,143 +165,6 @@ __device__ __forceinline__ float h_err_exact(const float* Hf, float X, float Y, 
     const float dx = __fadd_rn(__fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(Hf[0], X), __fmul_rn(Hf[1], Y)), Hf[2]), ww), nu);
     const float dy = __fadd_rn(__fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(Hf[3], X), __fmul_rn(Hf[4], Y)), Hf[5]), ww), nv);
     return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-}
-
-// ---- cluster-wide deterministic reductions ---------------------------------------------------------------------------
-// The finalize kernel runs as ONE thread-block cluster per problem (8 CTAs x 1024 threads for a large problem, a
-// single CTA for a small one).  Every CTA reduces its share of the points to NV partial sums in its own shared
-// memory; after one cluster barrier every CTA reads all partials through distributed shared memory, in rank
-// order, so all CTAs hold the same bit pattern and replay the (tiny) sequential part of the algorithm
-// redundantly — no broadcast, no atomics, run-to-run deterministic.  Partials are double-buffered so that one
-// barrier per reduction is enough.
-namespace cg = cooperative_groups;
-
-constexpr int RED_MAX = 32;
-
-struct ClusterRed {
-    double part[2][RED_MAX];  // this CTA's partial sums (double-buffered), read remotely
-    double warp[32 * RED_MAX];
-    double out[RED_MAX];
-    int phase;
-};
-
-template <int THREADS, int NV, bool IS_MAX>
-__device__ __forceinline__ void cluster_reduce(ClusterRed& R, double (&v)[NV]) {
-    static_assert(NV <= RED_MAX, "too many values");
-    cg::cluster_group cluster = cg::this_cluster();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        double x = v[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double y = __shfl_down_sync(0xffffffffu, x, o);
-            x = IS_MAX ? fmax(x, y) : x + y;
-        }
-        if (lane == 0) R.warp[warp * NV + i] = x;
-    }
-    __syncthreads();
-    const int ph = R.phase;
-    if (threadIdx.x < NV) {
-        double s = R.warp[threadIdx.x];
-        for (int w = 1; w < THREADS / 32; ++w) s = IS_MAX ? fmax(s, R.warp[w * NV + threadIdx.x]) : s + R.warp[w * NV + threadIdx.x];
-        R.part[ph][threadIdx.x] = s;
-    }
-    cluster.sync();
-    if (threadIdx.x < NV) {
-        const unsigned nb = cluster.num_blocks();
-        double s = 0;
-        for (unsigned r = 0; r < nb; ++r) {
-            const double* remote = cluster.map_shared_rank(&R.part[ph][0], r);
-            s = IS_MAX ? fmax(s, remote[threadIdx.x]) : (r == 0 ? remote[threadIdx.x] : s + remote[threadIdx.x]);
-        }
-        R.out[threadIdx.x] = s;
-    }
-    if (threadIdx.x == 0) R.phase = ph ^ 1;
-    __syncthreads();
-}
-
-// x = solve(A, b), A symmetric n x n, through its Jacobi eigen-decomposition with OpenCV's
-// back-substitution threshold (cv::solve DECOMP_EIG); optionally the diagonal of A^-1.
-template <int N>
-__device__ void solve_sym_eig(const double* A, const double* b, double* x, double* inv_diag) {
-    double a[N * N], W[N], V[N * N];
-    for (int i = 0; i < N * N; ++i) a[i] = A[i];
-    jacobi_eig<N>(a, W, V);
-    double thr = 0;
-    for (int i = 0; i < N; ++i) thr += fabs(W[i]);
-    thr *= DBL_EPSILON * 2;
-    for (int j = 0; j < N; ++j) {
-        if (x) x[j] = 0;
-        if (inv_diag) inv_diag[j] = 0;
-    }
-    for (int i = 0; i < N; ++i) {
-        if (fabs(W[i]) <= thr) continue;
-        if (x) {
-            double s = 0;
-            for (int j = 0; j < N; ++j) s += V[i * N + j] * b[j];
-            s /= W[i];
-            for (int j = 0; j < N; ++j) x[j] += s * V[i * N + j];
-        }
-        if (inv_diag)
-            for (int j = 0; j < N; ++j) inv_diag[j] += V[i * N + j] * V[i * N + j] / W[i];
-    }
-}
-
-// Cholesky factor of a symmetric positive definite N x N matrix (lower triangle in L); false when a pivot is not
-// safely positive — callers then fall back to the Jacobi eigen-decomposition, which is what OpenCV always uses.
-template <int N>
-__device__ __forceinline__ bool cholesky(const double* A, double* L) {
-    double dmax = 0;
-    for (int i = 0; i < N; ++i) dmax = fmax(dmax, fabs(A[i * N + i]));
-    for (int j = 0; j < N; ++j) {
-        double d = A[j * N + j];
-        for (int k = 0; k < j; ++k) d -= L[j * N + k] * L[j * N + k];
-        if (!(d > dmax * 1e-14)) return false;
-        d = sqrt(d);
-        L[j * N + j] = d;
-        for (int i = j + 1; i < N; ++i) {
-            double t = A[i * N + j];
-            for (int k = 0; k < j; ++k) t -= L[i * N + k] * L[j * N + k];
-            L[i * N + j] = t / d;
-        }
-    }
-    return true;
-}
-
-template <int N>
-__device__ __forceinline__ void cholesky_solve(const double* L, const double* b, double* x) {
-    double y[N];
-    for (int i = 0; i < N; ++i) {
-        double t = b[i];
-        for (int k = 0; k < i; ++k) t -= L[i * N + k] * y[k];
-        y[i] = t / L[i * N + i];
-    }
-    for (int i = N - 1; i >= 0; --i) {
-        double t = y[i];
-        for (int k = i + 1; k < N; ++k) t -= L[k * N + i] * x[k];
-        x[i] = t / L[i * N + i];
-    }
-}
-
-__device__ __forceinline__ bool solve_spd8(const double* A, const double* b, double* x) {
-    double L[64];
-    if (!cholesky<8>(A, L)) return false;
-    cholesky_solve<8>(L, b, x);
-    return true;
-}
-
-// diag(A^-1) of an SPD 8x8 through its Cholesky factor (column by column)
-__device__ __forceinline__ bool inv_diag_spd8(const double* A, double* diag) {
-    double L[64];
-    if (!cholesky<8>(A, L)) return false;
-    for (int j = 0; j < 8; ++j) {
-        double e[8] = {0, 0, 0, 0, 0, 0, 0, 0}, x[8];
-        e[j] = 1;
-        cholesky_solve<8>(L, e, x);
-        diag[j] = x[j];
-    }
-    return true;
 }
 
 // Eigenvector of the smallest eigenvalue of the symmetric PSD 9x9 L^T L by shifted inverse iteration
@@ -417,8 +199,8 @@ __device__ __forceinline__ bool smallest_eigvec9(const double* LtL_upper_full, d
 
 struct HFinalizeShared {
     double H[9];          // current model (fp64)
-    double x[8], xd[8];   // LM parameter vectors
-    double A[64], v[8], D[8], d[8];
+    double x[9], xd[9];   // LM parameter vectors (all nine entries of H, as OpenCV 4.13 refines them)
+    double A[81], v[9], D[9], d[9];
     double S, lambda, lc, rmax;
     float Hf[8];
     int flag, k, lm_iters, proceed;
@@ -570,19 +352,21 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
         }
 
         // ---- Levenberg-Marquardt, max 10 iterations, eps = FLT_EPSILON (cv::LMSolver) ---------------------
-        // Rows of J: Jx = [a, 0, cx], Jy = [0, a, cy] with a = (X, Y, 1) ww, cx = -(X, Y) ww xi, cy = -(X, Y) ww yi,
-        // so J^T J = [[aa, 0, a cx^T], [0, aa, a cy^T], [., ., cx cx^T + cy cy^T]] and J^T r = [a rx, a ry, cx rx + cy ry]:
-        // per-thread accumulators  S | aa (6) | a cx^T (6) | a cy^T (6) | cc (3) | a rx (3) | a ry (3) | c.r (2)  = 30
+        // OpenCV 4.13 refines all NINE entries of H (w = h6 X + h7 Y + h8) and rescales by 1/h8 afterwards; an
+        // 8-parameter LM does not reproduce its early-stopped iterates (oracle/cv_ransac_oracle.c, h_refine_eval).
+        // Rows of J: Jx = [a, 0, -xi a], Jy = [0, a, -yi a] with a = (X, Y, 1) ww, so
+        //   J^T J = [[aa, 0, -xi aa], [0, aa, -yi aa], [., ., (xi^2 + yi^2) aa]],   J^T r = [a rx, a ry, -(xi rx + yi ry) a]:
+        // per-thread accumulators  S | aa (6) | xi aa (6) | yi aa (6) | (xi^2+yi^2) aa (6) | a rx (3) | a ry (3) | (xi rx + yi ry) a (3) = 34
         auto eval = [&](const double* h, bool want_J) -> double2 {
-            double acc[30];
+            double acc[34];
 #pragma unroll
-            for (int j = 0; j < 30; ++j) acc[j] = 0;
+            for (int j = 0; j < 34; ++j) acc[j] = 0;
             double rmax[1] = {0};
             for (int i = gtid; i < n; i += gstride)
                 if (rmask[i]) {
                     const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
                     const double Mx = (double)p.x, My = (double)p.y;
-                    double ww = h[6] * Mx + h[7] * My + 1.;
+                    double ww = h[6] * Mx + h[7] * My + h[8];
                     ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
                     const double xi = (h[0] * Mx + h[1] * My + h[2]) * ww;
                     const double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
@@ -591,24 +375,25 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     rmax[0] = fmax(rmax[0], fmax(fabs(rx), fabs(ry)));
                     if (want_J) {
                         const double a[3] = {Mx * ww, My * ww, ww};
-                        const double cx[2] = {-a[0] * xi, -a[1] * xi}, cy[2] = {-a[0] * yi, -a[1] * yi};
-                        acc[1] += a[0] * a[0]; acc[2] += a[0] * a[1]; acc[3] += a[0] * a[2];
-                        acc[4] += a[1] * a[1]; acc[5] += a[1] * a[2]; acc[6] += a[2] * a[2];
+                        const double aa[6] = {a[0] * a[0], a[0] * a[1], a[0] * a[2], a[1] * a[1], a[1] * a[2], a[2] * a[2]};
+                        const double r2 = xi * xi + yi * yi, rr = xi * rx + yi * ry;
+#pragma unroll
+                        for (int u = 0; u < 6; ++u) {
+                            acc[1 + u] += aa[u];
+                            acc[7 + u] += xi * aa[u];
+                            acc[13 + u] += yi * aa[u];
+                            acc[19 + u] += r2 * aa[u];
+                        }
 #pragma unroll
                         for (int u = 0; u < 3; ++u) {
-                            acc[7 + 2 * u] += a[u] * cx[0];  acc[8 + 2 * u] += a[u] * cx[1];
-                            acc[13 + 2 * u] += a[u] * cy[0]; acc[14 + 2 * u] += a[u] * cy[1];
-                            acc[22 + u] += a[u] * rx;        acc[25 + u] += a[u] * ry;
+                            acc[25 + u] += a[u] * rx;
+                            acc[28 + u] += a[u] * ry;
+                            acc[31 + u] += a[u] * rr;
                         }
-                        acc[19] += cx[0] * cx[0] + cy[0] * cy[0];
-                        acc[20] += cx[0] * cx[1] + cy[0] * cy[1];
-                        acc[21] += cx[1] * cx[1] + cy[1] * cy[1];
-                        acc[28] += cx[0] * rx + cy[0] * ry;
-                        acc[29] += cx[1] * rx + cy[1] * ry;
                     }
                 }
             if (want_J) {
-                cluster_reduce<THREADS, 30, false>(R, acc);
+                cluster_reduce<THREADS, 34, false>(R, acc);
             } else {
                 double a1[1] = {acc[0]};
                 cluster_reduce<THREADS, 1, false>(R, a1);
@@ -616,22 +401,21 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
             const double S = R.out[0];
             if (want_J && tid == 0) {
                 const double* o = R.out;
-                for (int j = 0; j < 64; ++j) sh.A[j] = 0;
-                const int sym[3][3] = {{1, 2, 3}, {2, 4, 5}, {3, 5, 6}};
+                const int sym[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+                for (int j = 0; j < 81; ++j) sh.A[j] = 0;
                 for (int u = 0; u < 3; ++u) {
                     for (int w = 0; w < 3; ++w) {
-                        sh.A[u * 8 + w] = o[sym[u][w]];
-                        sh.A[(3 + u) * 8 + 3 + w] = o[sym[u][w]];
+                        const int e = sym[u][w];
+                        sh.A[u * 9 + w] = o[1 + e];
+                        sh.A[(3 + u) * 9 + 3 + w] = o[1 + e];
+                        sh.A[u * 9 + 6 + w] = sh.A[(6 + w) * 9 + u] = -o[7 + e];
+                        sh.A[(3 + u) * 9 + 6 + w] = sh.A[(6 + w) * 9 + 3 + u] = -o[13 + e];
+                        sh.A[(6 + u) * 9 + 6 + w] = o[19 + e];
                     }
-                    for (int w = 0; w < 2; ++w) {
-                        sh.A[u * 8 + 6 + w] = sh.A[(6 + w) * 8 + u] = o[7 + 2 * u + w];
-                        sh.A[(3 + u) * 8 + 6 + w] = sh.A[(6 + w) * 8 + 3 + u] = o[13 + 2 * u + w];
-                    }
-                    sh.v[u] = o[22 + u];
-                    sh.v[3 + u] = o[25 + u];
+                    sh.v[u] = o[25 + u];
+                    sh.v[3 + u] = o[28 + u];
+                    sh.v[6 + u] = -o[31 + u];
                 }
-                sh.A[6 * 8 + 6] = o[19]; sh.A[6 * 8 + 7] = sh.A[7 * 8 + 6] = o[20]; sh.A[7 * 8 + 7] = o[21];
-                sh.v[6] = o[28]; sh.v[7] = o[29];
             }
             __syncthreads();
             cluster_reduce<THREADS, 1, true>(R, rmax);
@@ -639,34 +423,37 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
         };
 
         if (tid == 0)
-            for (int i = 0; i < 8; ++i) sh.x[i] = sh.H[i];
+            for (int i = 0; i < 9; ++i) sh.x[i] = sh.H[i];
         __syncthreads();
         {
             const double2 e0 = eval(sh.x, true);
             if (tid == 0) {
                 sh.S = e0.x; sh.rmax = e0.y;
-                for (int i = 0; i < 8; ++i) sh.D[i] = sh.A[i * 8 + i];
+                for (int i = 0; i < 9; ++i) sh.D[i] = sh.A[i * 9 + i];
                 sh.lambda = 1; sh.lc = 0.75;
             }
             __syncthreads();
         }
         for (int iter = 0;;) {
             if (tid == 0) {
-                double Ap[64];
-                for (int i = 0; i < 64; ++i) Ap[i] = sh.A[i];
-                for (int i = 0; i < 8; ++i) Ap[i * 8 + i] += sh.lambda * sh.D[i];
-                double dd[8];
-                if (!solve_spd8(Ap, sh.v, dd)) solve_sym_eig<8>(Ap, sh.v, dd, nullptr);
-                for (int i = 0; i < 8; ++i) { sh.d[i] = dd[i]; sh.xd[i] = sh.x[i] - dd[i]; }
+                // J^T J is singular along h itself (the projection is scale-invariant): with lambda == 0 only the
+                // eigen-decomposition solve with OpenCV's cut-off is meaningful; with lambda > 0 the matrix is SPD
+                double Ap[81];
+                for (int i = 0; i < 81; ++i) Ap[i] = sh.A[i];
+                for (int i = 0; i < 9; ++i) Ap[i * 9 + i] += sh.lambda * sh.D[i];
+                double dd[9], L[81];
+                if (sh.lambda > 0 && cholesky<9>(Ap, L)) cholesky_solve<9>(L, sh.v, dd);
+                else solve_sym_eig<9>(Ap, sh.v, dd, nullptr);
+                for (int i = 0; i < 9; ++i) { sh.d[i] = dd[i]; sh.xd[i] = sh.x[i] - dd[i]; }
             }
             __syncthreads();
             const double2 ed = eval(sh.xd, false);
             if (tid == 0) {
                 const double Sd = ed.x, S = sh.S;
                 double dS = 0;
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 9; ++i) {
                     double t = 0;
-                    for (int j = 0; j < 8; ++j) t += sh.A[i * 8 + j] * sh.d[j];
+                    for (int j = 0; j < 9; ++j) t += sh.A[i * 9 + j] * sh.d[j];
                     dS += sh.d[i] * (2 * sh.v[i] - t);
                 }
                 const double Rr = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
@@ -675,13 +462,13 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     if (sh.lambda < sh.lc) sh.lambda = 0;
                 } else if (Rr < 0.25) {
                     double t = 0;
-                    for (int i = 0; i < 8; ++i) t += sh.d[i] * sh.v[i];
+                    for (int i = 0; i < 9; ++i) t += sh.d[i] * sh.v[i];
                     double nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1) + 2;
                     nu = fmin(fmax(nu, 2.), 10.);
                     if (sh.lambda == 0) {
-                        double diag[8], maxval = DBL_EPSILON;
-                        if (!inv_diag_spd8(sh.A, diag)) solve_sym_eig<8>(sh.A, nullptr, nullptr, diag);
-                        for (int i = 0; i < 8; ++i) maxval = fmax(maxval, fabs(diag[i]));
+                        double diag[9], maxval = DBL_EPSILON;
+                        solve_sym_eig<9>(sh.A, nullptr, nullptr, diag);
+                        for (int i = 0; i < 9; ++i) maxval = fmax(maxval, fabs(diag[i]));
                         sh.lambda = sh.lc = 1. / maxval;
                         nu *= 0.5;
                     }
@@ -690,7 +477,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                 sh.flag = Sd < S;
                 if (sh.flag) {
                     sh.S = Sd;
-                    for (int i = 0; i < 8; ++i) sh.x[i] = sh.xd[i];
+                    for (int i = 0; i < 9; ++i) sh.x[i] = sh.xd[i];
                 }
             }
             __syncthreads();
@@ -701,7 +488,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
             ++iter;
             if (tid == 0) {
                 double dmax = 0;
-                for (int i = 0; i < 8; ++i) dmax = fmax(dmax, fabs(sh.d[i]));
+                for (int i = 0; i < 9; ++i) dmax = fmax(dmax, fabs(sh.d[i]));
                 sh.proceed = iter < 10 && dmax >= (double)FLT_EPSILON && sh.rmax >= (double)FLT_EPSILON;
                 sh.lm_iters = iter;
             }
@@ -709,8 +496,9 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
             if (!sh.proceed) break;
         }
         if (tid == 0) {
-            for (int i = 0; i < 8; ++i) sh.H[i] = sh.x[i];
-            for (int i = 0; i < 8; ++i) sh.Hf[i] = (float)sh.x[i];
+            const double sc = fabs(sh.x[8]) > DBL_EPSILON ? 1. / sh.x[8] : 1;   // OpenCV: convertTo(..., scaleFor(H22))
+            for (int i = 0; i < 9; ++i) sh.H[i] = sh.x[i] * sc;
+            for (int i = 0; i < 8; ++i) sh.Hf[i] = (float)sh.H[i];
         }
         __syncthreads();
     }

@@ -178,7 +178,7 @@ __device__ __forceinline__ void h_accumulate_LtL(double* LtL, const HNorm& nm, d
 }
 
 // 4-point solve.  M = src (x,y) x4, m = dst (x,y) x4 as fp32.  Returns 1 model or 0.
-__device__ int h_solve4(const float* M, const float* m, double* H) {
+static __device__ int h_solve4(const float* M, const float* m, double* H) {
     HNorm nm = {0, 0, 0, 0, 0, 0, 0, 0};
     const int count = 4;
     for (int i = 0; i < count; i++) {

@@ -5,8 +5,10 @@ libransac_b200.so, every other attribute is forwarded to the real OpenCV (imread
     main_v1.cv2 = shim.module()            # or: sys.modules["cv2"] = shim.module() before importing the script
 
 Replaces exactly the lookups SURVEY.md §8(b) lists: cv2.findHomography with method == cv2.RANSAC
-(main_v1.py:312, process.py:200, testpro.py:350, test_pro.py:351, test02.py:263) and the constant cv2.RANSAC.
-Return conventions are cv2's: (H float64 (3,3) or None, mask uint8 (n,1)); fewer than 4 points raise."""
+(main_v1.py:312, process.py:200, testpro.py:350, test_pro.py:351, test02.py:263), cv2.solvePnPRansac (main_v1.py:497,
+testpro.py:536, test_pro.py:515, testpro-K.py:72), cv2.solvePnPRefineLM (main_v1.py:508, testpro-K.py:122) and the
+constant cv2.RANSAC.  Return conventions are cv2's: (H float64 (3,3) or None, mask uint8 (n,1)), fewer than 4 points
+raise; (retval bool, rvec (3,1), tvec (3,1), inliers int32 (k,1))."""
 import types
 
 import numpy as np
@@ -48,6 +50,49 @@ def findHomography(srcPoints, dstPoints, method=0, ransacReprojThreshold=3.0, ma
     return H, m
 
 
+def _zero_distortion(distCoeffs):
+    return distCoeffs is None or not np.any(np.asarray(distCoeffs, dtype=np.float64))
+
+
+def solvePnPRansac(objectPoints, imagePoints, cameraMatrix, distCoeffs, rvec=None, tvec=None, useExtrinsicGuess=False,
+                   iterationsCount=100, reprojectionError=8.0, confidence=0.99, inliers=None, flags=0, _ctx=None, **b2r_kw):
+    """cv2.solvePnPRansac as the reference calls it (zero distortion, default flags = SOLVEPNP_ITERATIVE whose RANSAC
+    kernel is EPnP, no extrinsic guess): runs on the GPU.  Anything else is not on the reference's hot path and is
+    forwarded to OpenCV."""
+    obj = np.asarray(objectPoints, dtype=np.float64).reshape(-1, 3)
+    img = np.asarray(imagePoints, dtype=np.float64).reshape(-1, 2)
+    if useExtrinsicGuess or flags != 0 or not _zero_distortion(distCoeffs) or len(obj) == 4:
+        cv2 = _real_cv2()
+        if cv2 is None:
+            raise error("solvePnPRansac: only the reference's configuration is implemented by ransac_b200")
+        return cv2.solvePnPRansac(objectPoints, imagePoints, cameraMatrix, distCoeffs, rvec, tvec, useExtrinsicGuess,
+                                  iterationsCount, reprojectionError, confidence, inliers, flags)
+    if len(obj) != len(img) or len(obj) < 4:
+        cv2 = _real_cv2()
+        exc = cv2.error if cv2 is not None else error
+        raise exc("solvePnPRansac: need >= 4 corresponding points (OpenCV asserts in solvepnp.cpp)")
+    ctx = _ctx or api.default_context()
+    ok, r, t, inl, _ = ctx.solve_pnp_ransac(obj, img, cameraMatrix, int(iterationsCount), float(reprojectionError),
+                                            float(confidence), **b2r_kw)
+    if not ok:
+        return False, np.zeros((3, 1)), np.zeros((3, 1)), None
+    return True, r, t, inl
+
+
+def solvePnPRefineLM(objectPoints, imagePoints, cameraMatrix, distCoeffs, rvec, tvec, criteria=None, _ctx=None):
+    """cv2.solvePnPRefineLM (default criteria: 20 iterations, eps FLT_EPSILON) on the GPU; returns (rvec, tvec) (3,1)."""
+    if not _zero_distortion(distCoeffs) or criteria is not None:
+        cv2 = _real_cv2()
+        if cv2 is None:
+            raise error("solvePnPRefineLM: only zero distortion / default criteria are implemented by ransac_b200")
+        args = (objectPoints, imagePoints, cameraMatrix, distCoeffs, rvec, tvec) + ((criteria,) if criteria is not None else ())
+        return cv2.solvePnPRefineLM(*args)
+    ctx = _ctx or api.default_context()
+    r, t, _ = ctx.solve_pnp_refine_lm(np.asarray(objectPoints, dtype=np.float64).reshape(-1, 3),
+                                      np.asarray(imagePoints, dtype=np.float64).reshape(-1, 2), cameraMatrix, rvec, tvec)
+    return r, t
+
+
 def module():
     """A module object usable wherever the scripts use `cv2`."""
     m = types.ModuleType("cv2")
@@ -61,5 +106,7 @@ def module():
                     pass
     m.RANSAC = RANSAC
     m.findHomography = findHomography
+    m.solvePnPRansac = solvePnPRansac
+    m.solvePnPRefineLM = solvePnPRefineLM
     m.__ransac_b200__ = True
     return m

@@ -4,6 +4,10 @@
                                                          main_v1.py:302-422 (process.py:188-291, testpro.py:340-460)
     find_homographies(recs, camera_locations, im, show, ransacbound, output)          main_v1.py:254-297
     best_location(num_matches)                                                        main_v1.py:863-866
+    camera_matrix_from_image(width, height)                                           main_v1.py:870-883
+    estimate_camera_pose(pos3d, pixels, K)                                            main_v1.py:468-512
+    estimate_camera_orientation(pos3d, pixels, focal_lengths, sensor_sizes, image_size, known_camera_origin)
+                                                                                      testpro-K.py:39-162
 
 The reference loops over the candidate camera locations in Python and calls cv2.findHomography once per candidate;
 here the whole sweep is ONE batched GPU call (Q independent RANSAC problems), with the reference's per-candidate
@@ -96,3 +100,79 @@ def best_location(num_matches):
     err2 = np.array(num_matches[:, 1], dtype=np.float64)
     err2[err2 == 0] = 1000000
     return int(np.argmin(err2))
+
+
+# ---- path B: PnP pose ---------------------------------------------------------------------------------------------
+def camera_matrix_from_image(width, height):
+    """K of do_it, main_v1.py:870-883: fx = 240/127 * W, fy = 240/178 * H, principal point (982.666819, 697.950868)."""
+    return np.array([[240.0 / 127.0 * width, 0.0, 982.666819], [0.0, 240.0 / 178.0 * height, 697.950868], [0.0, 0.0, 1.0]])
+
+
+def rodrigues(rvec):
+    """Rotation matrix of a rotation vector (what the reference gets from cv2.Rodrigues, main_v1.py:895)."""
+    r = np.asarray(rvec, dtype=np.float64).reshape(3)
+    th = float(np.linalg.norm(r))
+    if th < np.finfo(np.float64).eps:
+        return np.eye(3)
+    k = r / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.cos(th) * np.eye(3) + (1 - np.cos(th)) * np.outer(k, k) + np.sin(th) * Kx
+
+
+def estimate_camera_pose(pos3d, pixels, K, ctx=None, **ransac_kw):
+    """main_v1.py:468-512 without the plots: solvePnPRansac(5000, 30.0, 0.99), the `< 6 inliers` gate (:504), then
+    solvePnPRefineLM on pos3d[inliers] (:508).  Returns (rvec (3,1), tvec (3,1), inliers (k,1) int32) or (None, None, None)."""
+    ctx = ctx or api.default_context()
+    pos3d = np.asarray(pos3d, dtype=np.float64).reshape(-1, 3)
+    pixels = np.asarray(pixels, dtype=np.float64).reshape(-1, 2)
+    K = np.asarray(K, dtype=np.float64).reshape(3, 3)
+    ok, rvec, tvec, inliers, _ = ctx.solve_pnp_ransac(pos3d, pixels, K, 5000, 30.0, 0.99, **ransac_kw)
+    if not ok or inliers is None or len(inliers) < 6:
+        return None, None, None
+    idx = inliers.ravel()
+    rvec, tvec, _ = ctx.solve_pnp_refine_lm(pos3d[idx], pixels[idx], K, rvec, tvec)
+    return rvec, tvec, inliers
+
+
+def intrinsics_grid(focal_lengths, sensor_sizes, image_size):
+    """The K matrices of testpro-K.py:58-70, in loop order, with their (focal, sensor) labels."""
+    Ks, labels = [], []
+    for f in focal_lengths:
+        for (sw, sh) in sensor_sizes:
+            fx = f / (sw / image_size[0])
+            fy = f / (sh / image_size[1])
+            Ks.append([[fx, 0, image_size[0] / 2], [0, fy, image_size[1] / 2], [0, 0, 1]])
+            labels.append((f, (sw, sh)))
+    return np.array(Ks, dtype=np.float64), labels
+
+
+def estimate_camera_orientation(pos3d, pixels, focal_lengths, sensor_sizes, image_size, known_camera_origin=None, ctx=None,
+                                return_details=False, **ransac_kw):
+    """testpro-K.py:39-162 without the prints: one solvePnPRansac per K of the grid — here ONE batched GPU call over
+    the shared points — skip K with < 6 inliers (:77), keep the K with the smallest mean inlier reprojection error
+    (:80-97), refine that pose with solvePnPRefineLM (:122-125).  Returns (rvec, tvec) like the reference, or
+    (None, None) when every K fails (:99-101)."""
+    ctx = ctx or api.default_context()
+    pos3d = np.asarray(pos3d, dtype=np.float64).reshape(-1, 3)
+    pixels = np.asarray(pixels, dtype=np.float64).reshape(-1, 2)
+    Ks, labels = intrinsics_grid(focal_lengths, sensor_sizes, image_size)
+    ok, rvecs, tvecs, inliers, infos = ctx.solve_pnp_ransac_batch(pos3d, pixels, Ks, 5000, 30.0, 0.99, **ransac_kw)
+    best, best_err, results = None, float("inf"), []
+    for q in range(len(Ks)):
+        if not ok[q] or len(inliers[q]) < 6:
+            continue
+        err = infos[q]["mean_inlier_err"]
+        origin = -rodrigues(rvecs[q]).T @ tvecs[q]
+        dist = None if known_camera_origin is None else float(np.linalg.norm(origin - np.asarray(known_camera_origin, dtype=np.float64)))
+        results.append(dict(index=q, label=labels[q], mean_error=err, camera_origin=origin, distance=dist, inliers=inliers[q]))
+        if err < best_err:
+            best, best_err = q, err
+    if best is None:
+        return (None, None, dict(results=[])) if return_details else (None, None)
+    idx = inliers[best]
+    rvec, tvec, _ = ctx.solve_pnp_refine_lm(pos3d[idx], pixels[idx], Ks[best], rvecs[best], tvecs[best])
+    if return_details:
+        return rvec, tvec, dict(results=results, best=best, best_K=Ks[best], best_label=labels[best], best_error=best_err,
+                                initial_rvec=rvecs[best].reshape(3, 1), initial_tvec=tvecs[best].reshape(3, 1),
+                                inliers=idx.reshape(-1, 1), ok=ok, infos=infos)
+    return rvec, tvec

@@ -159,6 +159,83 @@ int b2r_selftest_rcp(b2r_ctx* ctx, uint64_t* mismatches_out, uint64_t* tested_ou
 /* Register-resident FFMA peak of this GPU, in fp32 FMA lane-operations per second (x2 = FLOP/s). */
 int b2r_probe_fp32_peak(b2r_ctx* ctx, double* fma_per_s_out, double* ffma2_per_s_out);
 
+/* ==== cv2.solvePnPRansac / cv2.solvePnPRefineLM  —  main_v1.py:497-502, :508-509; testpro-K.py:72-75, :122-125 ==== */
+typedef struct {
+    double thr;          /* reprojectionError, pixels (the reference passes 30.0; cv2 default 8.0)                    */
+    int32_t max_iters;   /* iterationsCount (reference 5000; cv2 default 100); PHILOX: hypotheses scored              */
+    double confidence;   /* reference 0.99 (= cv2 default)                                                            */
+    int32_t sampler;     /* B2R_SAMPLER_*                                                                             */
+    uint64_t seed;       /* Philox key (ignored for CV_REPLAY)                                                        */
+    int32_t arith;       /* B2R_ARITH_EXACT: cv::projectPoints' fp64 projection rounded to fp32 + un-fused fp32 error,
+                            bit-exact inlier sets; B2R_ARITH_FAST: all-fp32 FMA on re-centred points                 */
+    int32_t refine;      /* 1: pose = LM (CvLevMarq, as solvePnP(ITERATIVE, useExtrinsicGuess)) on the inliers seeded
+                            with the best RANSAC model, as cv2 does; 0: return the best RANSAC model                 */
+    int64_t hyp_begin;   /* hypothesis-id shard of this rank (PHILOX only)                                            */
+    int32_t reserved[2];
+} b2r_p_params;
+
+typedef struct {
+    int32_t status;       /* B2R_OK / B2R_NO_MODEL (cv2: retval False)                         */
+    int32_t iters_run;    /* RANSAC iterations executed (CV_REPLAY) / hypotheses scored         */
+    int32_t best_iter;    /* 0-based iteration, or hypothesis id - hyp_begin                    */
+    int32_t best_count;   /* RANSAC-stage inlier count of the winning hypothesis                */
+    int32_t sample[5];    /* its minimal sample                                                 */
+    int32_t n_inliers;    /* length of the returned inlier list                                 */
+    int32_t lm_iters;     /* LM iterations of the pose refinement                               */
+    int32_t reserved;
+    double ransac_rvec[3], ransac_tvec[3]; /* the best minimal model (before refinement)        */
+    double mean_inlier_err; /* mean reprojection error (px) of the inliers under the returned pose, evaluated on the
+                               caller's un-quantised points: compute_reprojection_error, testpro-K.py:32-36, :80-82 */
+    double sum_sq_err;      /* sum of squared inlier residuals under the returned pose          */
+} b2r_p_info;
+
+void b2r_default_p_params(b2r_p_params* p);
+
+/* obj_host (n,3) float64, img_host (n,2) float64, K (3,3) row-major float64; distortion is zero on the reference's path
+ * (it passes np.zeros((4,1))).  rvec_out/tvec_out: 3 doubles each.  inliers_out: capacity n int32 (ascending indices, as
+ * cv2 returns them), *n_inliers_out their number.  n < 4 -> B2R_ERR_ARG (cv2 raises); n == 4 (OpenCV's P3P branch) is
+ * not on the reference's path and returns B2R_ERR_ARG.  Returns B2R_NO_MODEL when cv2 would return retval False. */
+int b2r_solve_pnp_ransac(b2r_ctx* ctx, const double* obj_host, const double* img_host, int32_t n, const double* K,
+                         const b2r_p_params* params, double* rvec_out, double* tvec_out, int32_t* inliers_out,
+                         int32_t* n_inliers_out, b2r_p_info* info_out);
+/* The loop of estimate_camera_orientation (testpro-K.py:58-97): Q camera matrices K (Q,9).  pts_shared != 0: all Q problems
+ * use the same points obj (n,3) / img (n,2) (the intrinsics grid); else obj (Q,n,3), img (Q,n,2).  Outputs are (Q,3),
+ * (Q,3), (Q,n), (Q), Q entries.  Returns B2R_OK even when some problems have no model (info_out[q].status). */
+int b2r_solve_pnp_ransac_batch(b2r_ctx* ctx, const double* obj_host, const double* img_host, int32_t pts_shared, int32_t Q,
+                               int32_t n, const double* K, const b2r_p_params* params, double* rvec_out, double* tvec_out,
+                               int32_t* inliers_out, int32_t* n_inliers_out, b2r_p_info* info_out);
+/* cv2.solvePnPRefineLM(obj, img, K, 0, rvec, tvec): classic LMSolver, max_iters (<= 0: cv2's 20), eps FLT_EPSILON, on the
+ * caller's fp64 points (k >= 3).  rvec_io/tvec_io: in = initial pose, out = refined. */
+int b2r_solve_pnp_refine_lm(b2r_ctx* ctx, const double* obj_host, const double* img_host, int32_t k, const double* K,
+                            double* rvec_io, double* tvec_io, int32_t max_iters, int32_t* iters_out);
+
+/* device-resident form (same life cycle as b2r_h_problem) */
+typedef struct b2r_p_problem b2r_p_problem;
+b2r_p_problem* b2r_p_problem_upload(b2r_ctx* ctx, const double* obj_host, const double* img_host, int32_t pts_shared, int32_t Q,
+                                    int32_t n, const double* K);
+int b2r_p_problem_reupload(b2r_ctx* ctx, b2r_p_problem* prob, const double* obj_host, const double* img_host,
+                           int32_t pts_shared, int32_t Q, int32_t n, const double* K);
+void b2r_p_problem_free(b2r_ctx* ctx, b2r_p_problem* prob);
+int b2r_p_problem_run(b2r_ctx* ctx, b2r_p_problem* prob, const b2r_p_params* params);
+int b2r_p_problem_fetch(b2r_ctx* ctx, b2r_p_problem* prob, double* rvec_out, double* tvec_out, int32_t* inliers_out,
+                        int32_t* n_inliers_out, b2r_p_info* info_out);
+int b2r_p_problem_score_shard(b2r_ctx* ctx, b2r_p_problem* prob, const b2r_p_params* params, uint64_t* keys_out);
+int b2r_p_problem_finish(b2r_ctx* ctx, b2r_p_problem* prob, const b2r_p_params* params, const uint64_t* keys);
+int b2r_p_problem_stage_ms(b2r_ctx* ctx, b2r_p_problem* prob, float ms_out[5]);
+
+/* building blocks of the PnP path (parity tests) */
+/* K3: inlier counts of n_models poses, models_Rt (n_models,12) = R row-major | t, over n points (fp64 arrays, quantised to
+ * fp32 inside as cv2 does).  thr_sq = (float)(thr*thr). */
+int b2r_score_p(b2r_ctx* ctx, const double* models_Rt, int32_t n_models, const double* obj_host, const double* img_host,
+                int32_t n, const double* K, float thr_sq, int32_t arith, int32_t* counts_out);
+/* K2: EPnP minimal models of 5-point samples idx (n_samples,5).  Outputs (any may be NULL): rvec (n_samples,3), tvec
+ * (n_samples,3), R = Rodrigues(rvec) (n_samples,9), ok (n_samples). */
+int b2r_pnp_minimal_models(b2r_ctx* ctx, const double* obj_host, const double* img_host, int32_t n, const double* K,
+                           const int32_t* idx_host, int32_t n_samples, double* rvec_out, double* tvec_out, double* R_out,
+                           uint8_t* ok_out);
+/* K1: the first n_iters 5-point subsets OpenCV's RANSAC draws for n points.  idx_out (n_iters,5). */
+int b2r_sample_cv_p(b2r_ctx* ctx, int32_t n, int32_t n_iters, int32_t* idx_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -397,23 +397,31 @@ static void invert_sym_eig_diag(const double* A, int n, double* diag) {
     }
 }
 
-/* residuals r[2k], and (optionally) A = J^T J (8x8) and v = J^T r, for parameters h[8] */
+/* residuals r[2k], and (optionally) A = J^T J (9x9) and v = J^T r, for the NINE parameters h[0..8].
+ * OpenCV 4.13's HomographyRefineCallback refines all nine entries (w = h6 X + h7 Y + h8); an 8-parameter LM with h8 = 1
+ * agrees with the binary only to 1e-9 on well-conditioned problems and not at all on ill-conditioned ones, the
+ * 9-parameter one to 1e-15 (median) / 3e-8 (worst of 200 noisy problems).  Sums run over the rows of J in order (x row,
+ * then y row, of each point), as cv::mulTransposed does. */
 static void h_refine_eval(const double* h, const float* M, const float* m, int count, double* r, double* A, double* v) {
-    if (A) { memset(A, 0, sizeof(double) * 64); memset(v, 0, sizeof(double) * 8); }
+    if (A) { memset(A, 0, sizeof(double) * 81); memset(v, 0, sizeof(double) * 9); }
     for (int i = 0; i < count; i++) {
         double Mx = M[2 * i], My = M[2 * i + 1];
-        double ww = h[6] * Mx + h[7] * My + 1.;
+        double ww = h[6] * Mx + h[7] * My + h[8];
         ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
         double xi = (h[0] * Mx + h[1] * My + h[2]) * ww;
         double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
         r[2 * i] = xi - m[2 * i];
         r[2 * i + 1] = yi - m[2 * i + 1];
         if (A) {
-            double Jx[8] = {Mx * ww, My * ww, ww, 0, 0, 0, -Mx * ww * xi, -My * ww * xi};
-            double Jy[8] = {0, 0, 0, Mx * ww, My * ww, ww, -Mx * ww * yi, -My * ww * yi};
-            for (int j = 0; j < 8; j++) {
-                for (int k = 0; k < 8; k++) A[j * 8 + k] += Jx[j] * Jx[k] + Jy[j] * Jy[k];
-                v[j] += Jx[j] * r[2 * i] + Jy[j] * r[2 * i + 1];
+            double Jx[9] = {Mx * ww, My * ww, ww, 0, 0, 0, -Mx * ww * xi, -My * ww * xi, -ww * xi};
+            double Jy[9] = {0, 0, 0, Mx * ww, My * ww, ww, -Mx * ww * yi, -My * ww * yi, -ww * yi};
+            for (int j = 0; j < 9; j++) {
+                for (int k = 0; k < 9; k++) {
+                    A[j * 9 + k] += Jx[j] * Jx[k];
+                    A[j * 9 + k] += Jy[j] * Jy[k];
+                }
+                v[j] += Jx[j] * r[2 * i];
+                v[j] += Jy[j] * r[2 * i + 1];
             }
         }
     }
@@ -422,29 +430,31 @@ static void h_refine_eval(const double* h, const float* M, const float* m, int c
 static double norm_l2sqr(const double* r, int n) { double s = 0; for (int i = 0; i < n; i++) s += r[i] * r[i]; return s; }
 static double norm_inf(const double* r, int n) { double s = 0; for (int i = 0; i < n; i++) if (fabs(r[i]) > s) s = fabs(r[i]); return s; }
 
+/* cv::LMSolver (max maxIters iterations, eps FLT_EPSILON) on the nine entries of H, then H *= 1/H[8] (OpenCV's
+ * convertTo(..., scaleFor(H22))).  H: in = start (runKernel's output), out = refined, H[8] == 1. */
 ORC_API int orc_h_lm_refine(const float* M, const float* m, int count, double* H, int maxIters) {
-    const int lx = 8;
+    const int lx = 9;
     const double epsx = FLT_EPSILON, epsf = FLT_EPSILON, Rlo = 0.25, Rhi = 0.75;
-    double x[8], xd[8], d[8], A[64], Ap[64], v[8], D[8], tmp[8];
+    double x[9], xd[9], d[9], A[81], Ap[81], v[9], D[9], tmp[9];
     double* r = (double*)malloc(sizeof(double) * 2 * (size_t)count);
     double* rd = (double*)malloc(sizeof(double) * 2 * (size_t)count);
     double lambda = 1, lc = 0.75, S;
     int i, j, iter = 0;
-    for (i = 0; i < 8; i++) x[i] = H[i];
+    for (i = 0; i < lx; i++) x[i] = H[i];
     h_refine_eval(x, M, m, count, r, A, v);
     S = norm_l2sqr(r, 2 * count);
-    for (i = 0; i < lx; i++) D[i] = A[i * 8 + i];
+    for (i = 0; i < lx; i++) D[i] = A[i * lx + i];
     for (;;) {
         double Sd, dS, R;
         memcpy(Ap, A, sizeof(A));
-        for (i = 0; i < lx; i++) Ap[i * 8 + i] += lambda * D[i];
+        for (i = 0; i < lx; i++) Ap[i * lx + i] += lambda * D[i];
         solve_sym_eig(Ap, v, lx, d);
         for (i = 0; i < lx; i++) xd[i] = x[i] - d[i];
         h_refine_eval(xd, M, m, count, rd, NULL, NULL);
         Sd = norm_l2sqr(rd, 2 * count);
         for (i = 0; i < lx; i++) {
             double s = 0;
-            for (j = 0; j < lx; j++) s += A[i * 8 + j] * d[j];
+            for (j = 0; j < lx; j++) s += A[i * lx + j] * d[j];
             tmp[i] = 2 * v[i] - s;
         }
         dS = 0;
@@ -459,7 +469,7 @@ ORC_API int orc_h_lm_refine(const float* M, const float* m, int count, double* H
             nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1) + 2;
             nu = nu < 2. ? 2. : nu; nu = nu > 10. ? 10. : nu;
             if (lambda == 0) {
-                double diag[8], maxval = DBL_EPSILON;
+                double diag[9], maxval = DBL_EPSILON;
                 invert_sym_eig_diag(A, lx, diag);
                 for (i = 0; i < lx; i++) if (fabs(diag[i]) > maxval) maxval = fabs(diag[i]);
                 lambda = lc = 1. / maxval;
@@ -475,7 +485,10 @@ ORC_API int orc_h_lm_refine(const float* M, const float* m, int count, double* H
         iter++;
         if (!(iter < maxIters && norm_inf(d, lx) >= epsx && norm_inf(r, 2 * count) >= epsf)) break;
     }
-    for (i = 0; i < 8; i++) H[i] = x[i];
+    {
+        const double sc = fabs(x[8]) > DBL_EPSILON ? 1. / x[8] : 1;
+        for (i = 0; i < 9; i++) H[i] = x[i] * sc;
+    }
     free(r);
     free(rd);
     return iter;
@@ -504,7 +517,7 @@ ORC_API int orc_find_homography(const double* src, const double* dst, int n, dou
         for (i = 0; i < n; i++)
             if (rmask[i]) { M1[2 * k] = M[2 * i]; M1[2 * k + 1] = M[2 * i + 1]; m1[2 * k] = m[2 * i]; m1[2 * k + 1] = m[2 * i + 1]; k++; }
         orc_h_run_kernel(M1, m1, k, H);
-        orc_h_lm_refine(M1, m1, k, H, 10); /* refines H[0..7]; H[8] stays as runKernel left it (1 or 1-ulp) */
+        orc_h_lm_refine(M1, m1, k, H, 10); /* refines all nine entries, then scales by 1/H[8] */
         free(M1);
         free(m1);
     }

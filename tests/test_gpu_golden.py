@@ -25,8 +25,8 @@ def relerr(a, b):
 
 def test_camera_location_sweep_on_repo_data(ctx, oracle, gold):
     """find_homographies (main_v1.py:254-297) over the 458 candidates of potential_camera_locations.csv with the
-    12 correspondences of testpro-K.py:198-225, thr 75: one batched GPU call.  RANSAC-stage results are exact
-    for every candidate; the refined H follows the oracle's; the winning location is the reference's (#181)."""
+    12 correspondences of testpro-K.py:198-225, thr 75: one batched GPU call, every candidate against the cv2 binary
+    (golden file) — identical final masks, refined H within 1e-5, err1/err2, and the winning location (#181)."""
     s = gold["fixture_a_sweep"]
     pos3d, pixels, loc3ds = np.array(s["pos3d"]), np.array(s["pixels"]), np.array(s["loc3ds"])
     recs = [dict(symbol=str(i), name="", pixel=pixels[i], pos3d=pos3d[i]) for i in range(len(pixels))]
@@ -34,27 +34,34 @@ def test_camera_location_sweep_on_repo_data(ctx, oracle, gold):
     nm, det = pipeline.find_homographies(recs, locs, None, False, s["thr"], None, ctx=ctx, return_details=True)
     # legacy semantics expose the RANSAC-stage mask
     _, _, mask_legacy, _ = ctx.find_homography_batch(det["pos2"], pixels, s["thr"], mask_semantics=ransac_b200.MASK_LEGACY)
-    close = 0
+    worst = 0.0
     for i in range(len(locs)):
         Hr, mr, d = oracle.find_homography(det["pos2"][i], pixels, s["thr"], details=True)
         assert det["infos"][i]["iters_run"] == d["iters"]
         assert det["infos"][i]["best_count"] == int(d["ransac_mask"].sum())
         np.testing.assert_array_equal(mask_legacy[i], d["ransac_mask"])
-        if relerr(det["H"][i], Hr) < 1e-5:
-            close += 1
-            np.testing.assert_array_equal(det["mask"][i], mr.ravel())
-    assert close >= 0.95 * len(locs)
+        np.testing.assert_array_equal(det["mask"][i], np.array(s["mask"][i], dtype=np.uint8))   # cv2's own mask
+        worst = max(worst, relerr(det["H"][i], s["H"][i]))                                     # cv2's own H
+    assert worst < 1e-5
+    np.testing.assert_allclose(nm[:, 0], np.array(s["err1"]), rtol=1e-5)
+    np.testing.assert_allclose(nm[:, 1], np.array(s["err2"]), rtol=1e-5)
     assert pipeline.best_location(nm) == s["best_index"] == 180
     assert abs(nm[180, 1] - s["err2"][180]) < 1e-6 * s["err2"][180]
-    assert relerr(det["H"][180], s["H"][180]) < 1e-5          # against the cv2 binary itself
 
 
 def test_debug_log_ransac_stage(ctx, gold):
+    """The reference's recorded run: logged (legacy) masks and logged matrices M, plus what cv2 4.13 returns."""
     for b in gold["debug_log"]:
         H, mask, info = ctx.find_homography(np.array(b["pos2"]), np.array(b["p1"]), 120.0,
                                             mask_semantics=ransac_b200.MASK_LEGACY)
         assert H is not None
         assert mask.ravel().tolist() == b["logged_mask"]
+        M = np.linalg.inv(H)
+        assert relerr(M * (np.array(b["logged_M"])[2, 2] / M[2, 2]), b["logged_M"]) < 1e-3     # the log prints 9 digits
+        H413, mask413, _ = ctx.find_homography(np.array(b["pos2"]), np.array(b["p1"]), 120.0)
+        assert mask413.ravel().tolist() == b["cv413_mask"]
+        # ill-conditioned 28-point blocks (tests/test_oracle_golden.py): the early-stopped LM amplifies last-bit differences
+        assert relerr(H413, b["cv413_H"]) < 2e-3
 
 
 def test_golden_random_problems(ctx, gold):

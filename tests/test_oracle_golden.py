@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cv2_golden.json")
-REL_H_TOL = 1e-5   # north star tolerance; observed agreement is ~1e-9
+REL_H_TOL = 1e-5   # north star tolerance; observed agreement: median 1e-10, worst 2.6e-7
 
 
 @pytest.fixture(scope="module")
@@ -54,27 +54,25 @@ def test_find_homography_random_problems(oracle, gold):
 def test_fixture_a_sweep(oracle, gold):
     """The repo's own data: testpro-K.py:198-225 points x 458 candidate cameras, thr 75 (main_v1.py:862).
 
-    With 12 points and a 75 px threshold most candidates keep only 6-8 inliers, and OpenCV 4.13's final
-    Levenberg-Marquardt refinement is a black box there (DESIGN.md "Parity status"): the restated LM agrees with
-    the binary to 1e-5 on the well-conditioned candidates (75 % of the sweep) and lands in a different local
-    minimum on the others.  What the reference consumes downstream — the arg-min of err2 — is identical."""
+    With 12 points and a 75 px threshold most candidates keep only 6-8 inliers, so the answer depends on every detail of
+    OpenCV's final Levenberg-Marquardt pass (it is stopped after 10 iterations, far from converged).  With the LM
+    restated as the binary runs it — all NINE entries of H are refined, then H is rescaled by 1/H22 — every one of the
+    458 candidates agrees with cv2: identical masks, H within 1e-5 (observed max 2.6e-7), err1/err2 and the arg-min."""
     from ransac_b200 import pipeline
     s = gold["fixture_a_sweep"]
     pos3d, pixels, loc3ds = np.array(s["pos3d"]), np.array(s["pixels"]), np.array(s["loc3ds"])
     nm = np.zeros((len(loc3ds), 2))
-    close = np.zeros(len(loc3ds), dtype=bool)
+    worst = 0.0
     for i in range(len(loc3ds)):
         pos2 = pipeline.candidate_pos2(pos3d, loc3ds[i])
         H, mask = oracle.find_homography(pos2, pixels, s["thr"])
         assert H is not None
-        close[i] = relerr(H, s["H"][i]) < REL_H_TOL
-        if close[i]:
-            np.testing.assert_array_equal(mask.ravel(), np.array(s["mask"][i], dtype=np.uint8))
+        worst = max(worst, relerr(H, s["H"][i]))
+        np.testing.assert_array_equal(mask.ravel(), np.array(s["mask"][i], dtype=np.uint8))
         _, nm[i, 0], nm[i, 1] = pipeline._score(H, mask, pos2, pixels, s["thr"])
-    assert close.mean() >= 0.70
-    np.testing.assert_allclose(nm[close, 0], np.array(s["err1"])[close], rtol=1e-4)
-    np.testing.assert_allclose(nm[close, 1], np.array(s["err2"])[close], rtol=1e-4)
-    assert close[180]
+    assert worst < REL_H_TOL
+    np.testing.assert_allclose(nm[:, 0], np.array(s["err1"]), rtol=1e-5)
+    np.testing.assert_allclose(nm[:, 1], np.array(s["err2"]), rtol=1e-5)
     assert pipeline.best_location(nm) == s["best_index"] == 180      # Pointid 181, SURVEY.md Appendix C
     assert abs(nm[180, 1] - 75.212638) < 1e-5
 
@@ -83,13 +81,14 @@ def test_debug_log_known_answers(oracle, gold):
     """The reference's recorded run (thr 120, process.py:374; older OpenCV -> RANSAC-stage "legacy" mask).
 
     The RANSAC stage (sampler replay, degeneracy tests, 4-point solver, fp32 scoring, termination) reproduces the
-    logged mask in all 24 complete blocks.  The logged matrix M = inv(refined H) depends on OpenCV's final
-    Levenberg-Marquardt pass, which is not reproducible from outside the binary on this ill-conditioned 12-point
-    data (DESIGN.md "Parity status"): the restated LM lands within ~10 % of it, not within tolerance, so M is only
-    held to a loose bound here and the failure to pin it is reported, not hidden."""
+    logged mask in all 24 complete blocks, and the logged matrix M = inv(refined H) to the log's printing precision
+    and conditioning (<= 1e-3 relative, the same band in which the 4.13 binary reproduces it; SURVEY.md finding 5).
+    With OpenCV 4.13 semantics the oracle returns the binary's mask in 24/24 blocks; the refined H agrees to 1e-5 in
+    most blocks and to 5e-4 in all: these 28-point, 120 px problems are ill-conditioned and the 10-iteration LM
+    amplifies last-bit differences in J^T J (the restatement is not bit-identical to the binary's LM)."""
     blocks = gold["debug_log"]
     assert len(blocks) == 24
-    rel_M, masks413 = [], 0
+    rel_M, rel_H = [], []
     for b in blocks:
         pos2, p1 = np.array(b["pos2"]), np.array(b["p1"])
         H, mask_legacy = oracle.find_homography(pos2, p1, 120.0, mask_semantics=1)
@@ -98,9 +97,10 @@ def test_debug_log_known_answers(oracle, gold):
         M = M * (np.array(b["logged_M"])[2, 2] / M[2, 2])
         rel_M.append(relerr(M, b["logged_M"]))
         H413, mask413 = oracle.find_homography(pos2, p1, 120.0, mask_semantics=0)
-        masks413 += mask413.ravel().tolist() == b["cv413_mask"]
-    assert np.median(rel_M) < 0.2
-    assert masks413 >= 20
+        assert mask413.ravel().tolist() == b["cv413_mask"]
+        rel_H.append(relerr(H413, b["cv413_H"]))
+    assert max(rel_M) < 1e-3 and np.median(rel_M) < 1e-6
+    assert max(rel_H) < 5e-4 and np.sum(np.array(rel_H) < REL_H_TOL) >= 18
 
 
 def test_project_points_bit_exact(oracle, gold):
@@ -148,9 +148,9 @@ def test_solve_pnp_ransac_fixture_a(oracle, gold):
     assert ok and inl.ravel().tolist() == p["inliers"] == [0, 1, 2, 3, 7, 9]
     assert inl.dtype == np.int32 and inl.shape == (6, 1)
     assert det["iters"] == 145
-    assert relerr(rvec, p["rvec"]) < 1e-5 and relerr(tvec, p["tvec"]) < 1e-5
+    assert relerr(rvec, p["rvec"]) < 1e-12 and relerr(tvec, p["tvec"]) < 1e-12
     r2, t2 = oracle.pnp_refine_lm(pos3d[inl.ravel()], pixels[inl.ravel()], K, p["rvec"], p["tvec"])
-    assert relerr(r2, p["refined_rvec"]) < 1e-5 and relerr(t2, p["refined_tvec"]) < 1e-5
+    assert relerr(r2, p["refined_rvec"]) < 1e-11 and relerr(t2, p["refined_tvec"]) < 1e-11
 
 
 def test_solve_pnp_ransac_random(oracle, gold):
@@ -161,7 +161,11 @@ def test_solve_pnp_ransac_random(oracle, gold):
         if not ok:
             continue
         assert inl.ravel().tolist() == c["inliers"]                      # identical inlier index set
-        assert relerr(rvec, c["rvec"]) < 1e-5 and relerr(tvec, c["tvec"]) < 1e-5
+        assert relerr(rvec, c["rvec"]) < 1e-12 and relerr(tvec, c["tvec"]) < 1e-12      # north star: 1e-5
+        if "refined_rvec" in c:                                            # solvePnPRefineLM on the un-quantised inliers
+            idx = inl.ravel()
+            r2, t2 = oracle.pnp_refine_lm(np.array(c["obj"])[idx], np.array(c["img"])[idx], K, c["rvec"], c["tvec"])
+            assert relerr(r2, c["refined_rvec"]) < 1e-11 and relerr(t2, c["refined_tvec"]) < 1e-11
 
 
 def test_cv_svd_restatement(oracle):
@@ -183,3 +187,21 @@ def test_update_num_iters(oracle):
     assert oracle.update_num_iters(0.995, 0.0, 4, 2000) == 0
     assert oracle.update_num_iters(0.995, 1.0, 4, 2000) == 2000
     assert oracle.update_num_iters(0.99, 0.5, 5, 5000) == 145   # the PnP run on the repo data executes 145 iterations
+
+
+def test_intrinsics_grid_testpro_k(oracle):
+    """testpro-K.py:58-97 run with the cv2 binary (tests/golden/cv2_kgrid.json): the oracle reproduces, for each of the
+    27 camera matrices, success, the inlier index set and the pose; hence the same K wins (f=300, 102x127, 13.41 px)."""
+    with open(os.path.join(os.path.dirname(GOLD), "cv2_kgrid.json")) as f:
+        kg = json.load(f)
+    pos3d, pixels = np.array(kg["pos3d"]), np.array(kg["pixels"])
+    used = 0
+    for g in kg["grid"]:
+        ok, rvec, tvec, inl = oracle.solve_pnp_ransac(pos3d, pixels, np.array(g["K"]), 5000, 30.0, 0.99)
+        assert ok == g["ok"]
+        if not ok:
+            continue
+        assert inl.ravel().tolist() == g["inliers"]
+        assert relerr(rvec, g["rvec"]) < 1e-12 and relerr(tvec, g["tvec"]) < 1e-12
+        used += len(g["inliers"]) >= 6
+    assert used == 16 and kg["best"] == 21 and abs(kg["best_error"] - 13.412324744862097) < 1e-9
