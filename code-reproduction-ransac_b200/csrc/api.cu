@@ -22,7 +22,7 @@ struct b2r_h_problem {
     DevBuf samples;   // [Q][H][4] int32
     DevBuf models;    // [Q][H][8] fp32
     DevBuf counts;    // [Q][H] int32
-    DevBuf ngen;      // [Q] int32
+    DevBuf state;     // [Q] RansacState (replay path) + one int32 "problems not done" counter behind it
     DevBuf keys;      // [Q] u64
     DevBuf sel;       // [Q] HSelect
     DevBuf H;         // [Q][9] fp64
@@ -33,7 +33,7 @@ struct b2r_h_problem {
     float stage_ms[5] = {0, 0, 0, 0, 0};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     void release() {
-        pts.release(); samples.release(); models.release(); counts.release(); ngen.release(); keys.release();
+        pts.release(); samples.release(); models.release(); counts.release(); state.release(); keys.release();
         sel.release(); H.release(); mask.release(); rmask.release(); info.release();
         for (auto& e : ev)
             if (e) cudaEventDestroy(e), e = nullptr;
@@ -148,8 +148,8 @@ static int check_params(const b2r_h_params* p) {
 }
 
 template <int NPAIR>
-static int launch_k3(b2r_ctx* c, const float4* models, int H, const PointH* pts, int n, float thr_sq, int* counts, int Q,
-                     int arith) {
+static int launch_k3(b2r_ctx* c, const float4* models, int H, int H_stride, const PointH* pts, int n, float thr_sq, int* counts,
+                     int Q, int arith) {
     // tile: as many points per CTA as keeps >= ~4 CTAs per SM slot in flight, capped by 2048 (32 KB)
     int tile = 1024;
     const long long hyp_blocks = (H + K3_THREADS * 2 * NPAIR - 1) / (K3_THREADS * 2 * NPAIR);
@@ -158,19 +158,26 @@ static int launch_k3(b2r_ctx* c, const float4* models, int H, const PointH* pts,
     const size_t smem = 128 + (size_t)tile * 16;
     dim3 grid((unsigned)hyp_blocks, (unsigned)((n + tile - 1) / tile), (unsigned)Q);
     if (arith == B2R_ARITH_EXACT)
-        LAUNCH(c, (k3_score_h<NPAIR, true>), grid, K3_THREADS, smem, models, H, pts, n, thr_sq, counts, tile);
+        LAUNCH(c, (k3_score_h<NPAIR, true>), grid, K3_THREADS, smem, models, H, H_stride, pts, n, thr_sq, counts, tile);
     else
-        LAUNCH(c, (k3_score_h<NPAIR, false>), grid, K3_THREADS, smem, models, H, pts, n, thr_sq, counts, tile);
+        LAUNCH(c, (k3_score_h<NPAIR, false>), grid, K3_THREADS, smem, models, H, H_stride, pts, n, thr_sq, counts, tile);
     CU(cudaGetLastError());
     return B2R_OK;
 }
 
+// Scores hypotheses [begin, begin+H) of every problem; models/counts are [Q][H_stride] arrays.
 static int score_models(b2r_ctx* c, const float4* models, int H, const PointH* pts, int n, float thr_sq, int* counts,
-                        int Q, int arith) {
-    CU(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)Q * H, c->stream));
+                        int Q, int arith, int H_stride = 0, int begin = 0) {
+    if (H_stride == 0) H_stride = H;
+    if (begin == 0 && H == H_stride) {
+        CU(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)Q * H, c->stream));
+    } else {
+        CU(cudaMemset2DAsync(counts + begin, sizeof(int) * (size_t)H_stride, 0, sizeof(int) * (size_t)H, (size_t)Q, c->stream));
+    }
     // few hypotheses per problem: 2 pairs per thread keeps more CTAs in flight; otherwise 4 pairs (fewer LDS per eval)
-    if ((long long)H * Q <= 2048LL * c->sm_count) return launch_k3<2>(c, models, H, pts, n, thr_sq, counts, Q, arith);
-    return launch_k3<4>(c, models, H, pts, n, thr_sq, counts, Q, arith);
+    if ((long long)H * Q <= 2048LL * c->sm_count)
+        return launch_k3<2>(c, models + 2 * (size_t)begin, H, H_stride, pts, n, thr_sq, counts + begin, Q, arith);
+    return launch_k3<4>(c, models + 2 * (size_t)begin, H, H_stride, pts, n, thr_sq, counts + begin, Q, arith);
 }
 
 static int problem_reserve(b2r_h_problem* pr, int Q, int n, int H) {
@@ -178,7 +185,7 @@ static int problem_reserve(b2r_h_problem* pr, int Q, int n, int H) {
     CU(pr->samples.reserve(sizeof(int) * 4 * (size_t)Q * H));
     CU(pr->models.reserve(sizeof(float) * 8 * (size_t)Q * H));
     CU(pr->counts.reserve(sizeof(int) * (size_t)Q * H));
-    CU(pr->ngen.reserve(sizeof(int) * (size_t)Q));
+    CU(pr->state.reserve(sizeof(RansacState) * (size_t)Q + 64));
     CU(pr->keys.reserve(sizeof(unsigned long long) * (size_t)Q));
     CU(pr->sel.reserve(sizeof(HSelect) * (size_t)Q));
     CU(pr->H.reserve(sizeof(double) * 9 * (size_t)Q));
@@ -205,7 +212,8 @@ static int upload_points(b2r_ctx* c, b2r_h_problem* pr, const double* src, const
     return B2R_OK;
 }
 
-// stage 1: sample + solve + score (+ per-problem argmax key for PHILOX)
+// stage 1: sample + solve + score (+ per-problem argmax key for PHILOX).  The replay path runs OpenCV's sequential loop
+// in growing chunks of iterations and stops as soon as every problem of the batch has reached its iteration bound.
 static int run_score(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p) {
     const int Q = pr->Q, n = pr->n, H = p->max_iters > 1 ? p->max_iters : 1;
     int rc = problem_reserve(pr, Q, n, H);
@@ -213,34 +221,51 @@ static int run_score(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p) {
     pr->H_last = H;
     const float thr_sq = (float)(p->thr * p->thr);
     CU(cudaEventRecord(pr->ev[0], c->stream));
-    if (n > 4) {
-        if (p->sampler == B2R_SAMPLER_PHILOX) {
-            dim3 grid((unsigned)((H + 127) / 128), (unsigned)Q);
-            LAUNCH(c, k_philox_sample_solve_h, grid, 128, 0, pr->pts.as<PointH>(), n, H, (long long)p->hyp_begin, p->seed,
-                   pr->samples.as<int>(), pr->models.as<float4>(), 1, p->solver);
-        } else {
-            LAUNCH(c, k_cv_sample_h, (unsigned)((Q + 31) / 32), 32, 0, pr->pts.as<PointH>(), n, H, pr->samples.as<int>(),
-                   pr->ngen.as<int>(), Q);
-            dim3 grid((unsigned)((H + 127) / 128), (unsigned)Q);
-            LAUNCH(c, k_solve_h4, grid, 128, 0, pr->pts.as<PointH>(), n, pr->samples.as<int>(), H, pr->ngen.as<int>(),
-                   pr->models.as<float4>(), (double*)nullptr, (uint8_t*)nullptr, (uint8_t*)nullptr, p->solver);
-        }
+    if (n > 4 && p->sampler == B2R_SAMPLER_PHILOX) {
+        dim3 grid((unsigned)((H + 127) / 128), (unsigned)Q);
+        LAUNCH(c, k_philox_sample_solve_h, grid, 128, 0, pr->pts.as<PointH>(), n, H, (long long)p->hyp_begin, p->seed,
+               pr->samples.as<int>(), pr->models.as<float4>(), 1, p->solver);
         CU(cudaGetLastError());
-    }
-    CU(cudaEventRecord(pr->ev[1], c->stream));
-    if (n > 4) {
+        CU(cudaEventRecord(pr->ev[1], c->stream));
         rc = score_models(c, pr->models.as<float4>(), H, pr->pts.as<PointH>(), n, thr_sq, pr->counts.as<int>(), Q, p->arith);
         if (rc) return rc;
-    }
-    CU(cudaEventRecord(pr->ev[2], c->stream));
-    if (n > 4 && p->sampler == B2R_SAMPLER_PHILOX) {
+        CU(cudaEventRecord(pr->ev[2], c->stream));
         CU(cudaMemsetAsync(pr->keys.p, 0, sizeof(unsigned long long) * Q, c->stream));
         int gx = (H + 255) / 256;
         if (gx > 4 * c->sm_count) gx = 4 * c->sm_count;
         LAUNCH(c, k_argmax_key, dim3((unsigned)gx, (unsigned)Q), 256, 0, pr->counts.as<int>(), H,
                (unsigned long long)p->hyp_begin, pr->keys.as<unsigned long long>());
         CU(cudaGetLastError());
+        return B2R_OK;
     }
+    if (n > 4) {
+        RansacState* st = pr->state.as<RansacState>();
+        int* not_done = reinterpret_cast<int*>(st + Q);
+        LAUNCH(c, k_state_init, (unsigned)((Q + 127) / 128), 128, 0, st, p->max_iters, Q);
+        for (int begin = 0, len = 128; begin < H; begin += len, len *= 2) {
+            if (len > H - begin) len = H - begin;
+            CU(cudaMemsetAsync(not_done, 0, sizeof(int), c->stream));
+            LAUNCH(c, k_cv_sample_h, (unsigned)((Q + 31) / 32), 32, 0, pr->pts.as<PointH>(), n, H, begin, len,
+                   pr->samples.as<int>(), st, Q);
+            dim3 grid((unsigned)((len + 127) / 128), (unsigned)Q);
+            LAUNCH(c, k_solve_h4, grid, 128, 0, pr->pts.as<PointH>(), n, pr->samples.as<int>(), H, begin, len,
+                   (const RansacState*)st, pr->models.as<float4>(), (double*)nullptr, (uint8_t*)nullptr, (uint8_t*)nullptr, p->solver);
+            CU(cudaGetLastError());
+            rc = score_models(c, pr->models.as<float4>(), len, pr->pts.as<PointH>(), n, thr_sq, pr->counts.as<int>(), Q, p->arith, H,
+                              begin);
+            if (rc) return rc;
+            LAUNCH(c, k_select_cv_chunk, (unsigned)((Q + 127) / 128), 128, 0, pr->counts.as<int>(), H, begin, len, n, p->confidence, 4,
+                   st, pr->sel.as<HSelect>(), Q, not_done);
+            CU(cudaGetLastError());
+            if (begin + len >= H) break;
+            int nd = 0;
+            CU(cudaMemcpyAsync(&nd, not_done, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            if (nd == 0) break;
+        }
+    }
+    CU(cudaEventRecord(pr->ev[1], c->stream));  // replay path: the whole loop is accounted to stage 0
+    CU(cudaEventRecord(pr->ev[2], c->stream));
     return B2R_OK;
 }
 
@@ -329,10 +354,7 @@ static int run_finish(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p, cons
             LAUNCH(c, k_select_from_keys, (unsigned)((Q + 127) / 128), 128, 0, pr->keys.as<unsigned long long>(),
                    (unsigned long long)p->hyp_begin, H, 4, pr->sel.as<HSelect>(), Q);
         }
-    } else {
-        LAUNCH(c, k_select_cv, (unsigned)((Q + 127) / 128), 128, 0, pr->counts.as<int>(), pr->ngen.as<int>(), H, n,
-               p->max_iters, p->confidence, 4, pr->sel.as<HSelect>(), Q);
-    }
+    }   // CV_REPLAY: run_score's last k_select_cv_chunk already left the selection in pr->sel
     CU(cudaGetLastError());
     CU(cudaEventRecord(pr->ev[3], c->stream));
     const int Hs = n == 4 ? 1 : H;
@@ -516,7 +538,8 @@ int b2r_solve_h4(b2r_ctx* c, const float* src, const float* dst, int32_t n, cons
     uint8_t* ok_d = c->scratch3.as<uint8_t>();
     uint8_t* sub_d = ok_d + n_samples;
     LAUNCH(c, k_solve_h4, dim3((unsigned)((n_samples + 127) / 128), 1), 128, 0, c->scratch0.as<PointH>(), n,
-           c->scratch1.as<int>(), n_samples, (const int*)nullptr, (float4*)nullptr, c->scratch2.as<double>(), ok_d, sub_d, solver);
+           c->scratch1.as<int>(), n_samples, 0, n_samples, (const RansacState*)nullptr, (float4*)nullptr, c->scratch2.as<double>(),
+           ok_d, sub_d, solver);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(H_out, c->scratch2.p, sizeof(double) * 9 * (size_t)n_samples, cudaMemcpyDeviceToHost, c->stream));
     if (ok_out) CU(cudaMemcpyAsync(ok_out, ok_d, (size_t)n_samples, cudaMemcpyDeviceToHost, c->stream));
@@ -532,12 +555,15 @@ int b2r_sample_cv(b2r_ctx* c, const float* src, const float* dst, int32_t n, int
     int rc = upload_f32_points(c, src, dst, n, c->scratch0);
     if (rc) return rc;
     CU(c->scratch1.reserve(sizeof(int) * 4 * (size_t)n_iters));
-    CU(c->scratch2.reserve(sizeof(int)));
-    LAUNCH(c, k_cv_sample_h, 1, 32, 0, c->scratch0.as<PointH>(), n, n_iters, c->scratch1.as<int>(), c->scratch2.as<int>(), 1);
+    CU(c->scratch2.reserve(sizeof(RansacState)));
+    LAUNCH(c, k_state_init, 1, 32, 0, c->scratch2.as<RansacState>(), (int)n_iters, 1);
+    LAUNCH(c, k_cv_sample_h, 1, 32, 0, c->scratch0.as<PointH>(), n, n_iters, 0, n_iters, c->scratch1.as<int>(),
+           c->scratch2.as<RansacState>(), 1);
     CU(cudaGetLastError());
-    int gen = 0;
-    CU(cudaMemcpyAsync(&gen, c->scratch2.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    RansacState st_h;
+    CU(cudaMemcpyAsync(&st_h, c->scratch2.p, sizeof(RansacState), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    const int gen = st_h.gen;
     CU(cudaMemcpyAsync(idx_out, c->scratch1.p, sizeof(int) * 4 * (size_t)gen, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (n_generated_out) *n_generated_out = gen;

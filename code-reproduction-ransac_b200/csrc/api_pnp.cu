@@ -13,14 +13,14 @@ struct b2r_p_problem {
     DevBuf Kq;                // [Q][4] fx, fy, cx, cy
     DevBuf samples;           // [Q][H][5] int32
     DevBuf mx, mf;            // [Q][H][12] fp64 / fp32 models
-    DevBuf counts, ngen, keys, sel;
+    DevBuf counts, state, keys, sel;   // state: [Q] RansacState + one int32 "not done" counter
     DevBuf rmask, pose, info_i, info_d, inliers, ninl;
     int H_last = 0;
     float stage_ms[5] = {0, 0, 0, 0, 0};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     void release() {
         raw_obj.release(); raw_img.release(); px.release(); pf.release(); centre.release(); Kq.release();
-        samples.release(); mx.release(); mf.release(); counts.release(); ngen.release(); keys.release(); sel.release();
+        samples.release(); mx.release(); mf.release(); counts.release(); state.release(); keys.release(); sel.release();
         rmask.release(); pose.release(); info_i.release(); info_d.release(); inliers.release(); ninl.release();
         for (auto& e : ev)
             if (e) cudaEventDestroy(e), e = nullptr;
@@ -86,7 +86,7 @@ static int p_reserve(b2r_p_problem* pr, int Q, int n, int H, bool exact) {
     if (exact) CU(pr->mx.reserve(sizeof(double) * 12 * (size_t)Q * H));
     else CU(pr->mf.reserve(sizeof(float) * 12 * (size_t)Q * H));
     CU(pr->counts.reserve(sizeof(int) * (size_t)Q * H));
-    CU(pr->ngen.reserve(sizeof(int) * (size_t)Q));
+    CU(pr->state.reserve(sizeof(RansacState) * (size_t)Q + 64));
     CU(pr->keys.reserve(sizeof(unsigned long long) * (size_t)Q));
     CU(pr->sel.reserve(sizeof(HSelect) * (size_t)Q));
     CU(pr->rmask.reserve((size_t)Q * n));
@@ -107,74 +107,110 @@ static int pick_tile(b2r_ctx* c, long long hyp_blocks, int n, int Q, int max_til
     return tile;
 }
 
+static int zero_counts(b2r_ctx* c, int* counts, int Q, int H, int H_stride, int begin) {
+    if (begin == 0 && H == H_stride) CU(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)Q * H, c->stream));
+    else CU(cudaMemset2DAsync(counts + begin, sizeof(int) * (size_t)H_stride, 0, sizeof(int) * (size_t)H, (size_t)Q, c->stream));
+    return B2R_OK;
+}
+
+// score hypotheses [begin, begin+H) of every problem; mx/counts are [Q][H_stride] arrays
 static int score_p_exact(b2r_ctx* c, const double* mx, int H, const PointPX* px, size_t stride, int n, const double* Kq,
-                         float thr_sq, int* counts, int Q) {
-    CU(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)Q * H, c->stream));
+                         float thr_sq, int* counts, int Q, int H_stride = 0, int begin = 0) {
+    if (H_stride == 0) H_stride = H;
+    int rc = zero_counts(c, counts, Q, H, H_stride, begin);
+    if (rc) return rc;
     const bool two = (long long)H * Q > 1024LL * c->sm_count;
     const int per_cta = K3P_THREADS * (two ? 2 : 1);
     const long long hb = (H + per_cta - 1) / per_cta;
     const int tile = pick_tile(c, hb, n, Q, 1024);
     dim3 grid((unsigned)hb, (unsigned)((n + tile - 1) / tile), (unsigned)Q);
     const size_t smem = 128 + (size_t)tile * 32;
-    if (two) LAUNCH(c, (k3_score_p_exact<2>), grid, K3P_THREADS, smem, mx, H, px, stride, n, Kq, thr_sq, counts, tile);
-    else LAUNCH(c, (k3_score_p_exact<1>), grid, K3P_THREADS, smem, mx, H, px, stride, n, Kq, thr_sq, counts, tile);
+    const double* m0 = mx + 12 * (size_t)begin;
+    if (two) LAUNCH(c, (k3_score_p_exact<2>), grid, K3P_THREADS, smem, m0, H, H_stride, px, stride, n, Kq, thr_sq, counts + begin, tile);
+    else LAUNCH(c, (k3_score_p_exact<1>), grid, K3P_THREADS, smem, m0, H, H_stride, px, stride, n, Kq, thr_sq, counts + begin, tile);
     CU(cudaGetLastError());
     return B2R_OK;
 }
 
 static int score_p_fast(b2r_ctx* c, const float4* mf, int H, const PointPF* pf, size_t stride, int n, float thr_sq, int* counts,
-                        int Q) {
-    CU(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)Q * H, c->stream));
+                        int Q, int H_stride = 0, int begin = 0) {
+    if (H_stride == 0) H_stride = H;
+    int rc = zero_counts(c, counts, Q, H, H_stride, begin);
+    if (rc) return rc;
     const bool big = (long long)H * Q > 2048LL * c->sm_count;
     const int per_cta = K3_THREADS * 2 * (big ? 2 : 1);
     const long long hb = (H + per_cta - 1) / per_cta;
     const int tile = pick_tile(c, hb, n, Q, 1024);
     dim3 grid((unsigned)hb, (unsigned)((n + tile - 1) / tile), (unsigned)Q);
     const size_t smem = 128 + (size_t)tile * 32;
-    if (big) LAUNCH(c, (k3_score_p_fast<2>), grid, K3_THREADS, smem, mf, H, pf, stride, n, thr_sq, counts, tile);
-    else LAUNCH(c, (k3_score_p_fast<1>), grid, K3_THREADS, smem, mf, H, pf, stride, n, thr_sq, counts, tile);
+    const float4* m0 = mf + 3 * (size_t)begin;
+    if (big) LAUNCH(c, (k3_score_p_fast<2>), grid, K3_THREADS, smem, m0, H, H_stride, pf, stride, n, thr_sq, counts + begin, tile);
+    else LAUNCH(c, (k3_score_p_fast<1>), grid, K3_THREADS, smem, m0, H, H_stride, pf, stride, n, thr_sq, counts + begin, tile);
     CU(cudaGetLastError());
     return B2R_OK;
 }
 
-// stage 1: sample + solve + score (+ per-problem argmax key for PHILOX)
+// stage 1: sample + solve + score (+ per-problem argmax key for PHILOX).  The replay path runs OpenCV's sequential loop in
+// growing chunks of iterations (256, 512, ...) and stops once every problem of the batch has reached its iteration bound.
 static int p_run_score(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p) {
     const int Q = pr->Q, n = pr->n;
     int H = p->max_iters > 1 ? p->max_iters : 1;
-    if (n == PNP_MP) H = 1;  // OpenCV solves the only possible subset once (niters = 1)
+    if (n == PNP_MP) H = 1;  // OpenCV solves the only possible subset once
     const bool exact = p->arith == B2R_ARITH_EXACT;
     int rc = p_reserve(pr, Q, n, H, exact);
     if (rc) return rc;
     pr->H_last = H;
     const float thr_sq = (float)(p->thr * p->thr);
     const bool philox = p->sampler == B2R_SAMPLER_PHILOX;
+    const size_t cstride = pr->P == 1 ? 0 : 3;
+    double* mx = exact ? pr->mx.as<double>() : nullptr;
+    float4* mf = exact ? nullptr : pr->mf.as<float4>();
     CU(cudaEventRecord(pr->ev[0], c->stream));
-    if (!philox)
-        LAUNCH(c, k_cv_sample_p, (unsigned)((Q + 31) / 32), 32, 0, n, H, pr->samples.as<int>(), pr->ngen.as<int>(), Q);
-    {
-        dim3 grid((unsigned)((H + 63) / 64), (unsigned)Q);
-        LAUNCH(c, k_epnp_solve_p, grid, 64, 0, pr->px.as<PointPX>(), pr->pts_stride(), n, H, pr->Kq.as<double>(),
-               pr->centre.as<double>(), (size_t)(pr->P == 1 ? 0 : 3), philox ? 1 : 0, (long long)p->hyp_begin, p->seed,
-               pr->samples.as<int>(), exact ? pr->mx.as<double>() : (double*)nullptr, exact ? (float4*)nullptr : pr->mf.as<float4>(),
-               (double*)nullptr, (uint8_t*)nullptr);
-    }
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(pr->ev[1], c->stream));
-    if (exact)
-        rc = score_p_exact(c, pr->mx.as<double>(), H, pr->px.as<PointPX>(), pr->pts_stride(), n, pr->Kq.as<double>(), thr_sq,
-                           pr->counts.as<int>(), Q);
-    else
-        rc = score_p_fast(c, pr->mf.as<float4>(), H, pr->pf.as<PointPF>(), pr->pts_stride(), n, thr_sq, pr->counts.as<int>(), Q);
-    if (rc) return rc;
-    CU(cudaEventRecord(pr->ev[2], c->stream));
     if (philox) {
+        dim3 grid((unsigned)((H + 63) / 64), (unsigned)Q);
+        LAUNCH(c, k_epnp_solve_p, grid, 64, 0, pr->px.as<PointPX>(), pr->pts_stride(), n, H, 0, H, (const RansacState*)nullptr,
+               pr->Kq.as<double>(), pr->centre.as<double>(), cstride, 1, (long long)p->hyp_begin, p->seed, pr->samples.as<int>(), mx,
+               mf, (double*)nullptr, (uint8_t*)nullptr);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(pr->ev[1], c->stream));
+        if (exact) rc = score_p_exact(c, mx, H, pr->px.as<PointPX>(), pr->pts_stride(), n, pr->Kq.as<double>(), thr_sq, pr->counts.as<int>(), Q);
+        else rc = score_p_fast(c, mf, H, pr->pf.as<PointPF>(), pr->pts_stride(), n, thr_sq, pr->counts.as<int>(), Q);
+        if (rc) return rc;
+        CU(cudaEventRecord(pr->ev[2], c->stream));
         CU(cudaMemsetAsync(pr->keys.p, 0, sizeof(unsigned long long) * Q, c->stream));
         int gx = (H + 255) / 256;
         if (gx > 4 * c->sm_count) gx = 4 * c->sm_count;
         LAUNCH(c, k_argmax_key, dim3((unsigned)gx, (unsigned)Q), 256, 0, pr->counts.as<int>(), H, (unsigned long long)p->hyp_begin,
                pr->keys.as<unsigned long long>());
         CU(cudaGetLastError());
+        return B2R_OK;
     }
+    RansacState* st = pr->state.as<RansacState>();
+    int* not_done = reinterpret_cast<int*>(st + Q);
+    LAUNCH(c, k_state_init, (unsigned)((Q + 127) / 128), 128, 0, st, n == PNP_MP ? 1 : (int)p->max_iters, Q);
+    for (int begin = 0, len = 256; begin < H; begin += len, len *= 2) {
+        if (len > H - begin) len = H - begin;
+        CU(cudaMemsetAsync(not_done, 0, sizeof(int), c->stream));
+        LAUNCH(c, k_cv_sample_p, (unsigned)((Q + 31) / 32), 32, 0, n, H, begin, len, pr->samples.as<int>(), st, Q);
+        dim3 grid((unsigned)((len + 63) / 64), (unsigned)Q);
+        LAUNCH(c, k_epnp_solve_p, grid, 64, 0, pr->px.as<PointPX>(), pr->pts_stride(), n, H, begin, len, (const RansacState*)st,
+               pr->Kq.as<double>(), pr->centre.as<double>(), cstride, 0, 0LL, (uint64_t)0, pr->samples.as<int>(), mx, mf,
+               (double*)nullptr, (uint8_t*)nullptr);
+        CU(cudaGetLastError());
+        if (exact) rc = score_p_exact(c, mx, len, pr->px.as<PointPX>(), pr->pts_stride(), n, pr->Kq.as<double>(), thr_sq, pr->counts.as<int>(), Q, H, begin);
+        else rc = score_p_fast(c, mf, len, pr->pf.as<PointPF>(), pr->pts_stride(), n, thr_sq, pr->counts.as<int>(), Q, H, begin);
+        if (rc) return rc;
+        LAUNCH(c, k_select_cv_chunk, (unsigned)((Q + 127) / 128), 128, 0, pr->counts.as<int>(), H, begin, len, n, p->confidence, PNP_MP,
+               st, pr->sel.as<HSelect>(), Q, not_done);
+        CU(cudaGetLastError());
+        if (begin + len >= H) break;
+        int nd = 0;
+        CU(cudaMemcpyAsync(&nd, not_done, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (nd == 0) break;
+    }
+    CU(cudaEventRecord(pr->ev[1], c->stream));  // replay path: the whole loop is accounted to stage 0
+    CU(cudaEventRecord(pr->ev[2], c->stream));
     return B2R_OK;
 }
 
@@ -221,10 +257,7 @@ static int p_run_finish(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p, co
             LAUNCH(c, k_select_from_keys, (unsigned)((Q + 127) / 128), 128, 0, pr->keys.as<unsigned long long>(),
                    (unsigned long long)p->hyp_begin, H, PNP_MP, pr->sel.as<HSelect>(), Q);
         }
-    } else {
-        LAUNCH(c, k_select_cv, (unsigned)((Q + 127) / 128), 128, 0, pr->counts.as<int>(), pr->ngen.as<int>(), H, n, p->max_iters,
-               p->confidence, PNP_MP, pr->sel.as<HSelect>(), Q);
-    }
+    }   // CV_REPLAY: p_run_score's last k_select_cv_chunk already left the selection in pr->sel
     CU(cudaGetLastError());
     CU(cudaEventRecord(pr->ev[3], c->stream));
     const int csize = n >= 32768 ? 8 : (n >= 8192 ? 2 : 1);
@@ -508,9 +541,9 @@ int b2r_pnp_minimal_models(b2r_ctx* c, const double* obj, const double* img, int
     CU(cudaMemcpyAsync(c->scratch1.p, idx, sizeof(int) * PNP_MP * (size_t)n_samples, cudaMemcpyHostToDevice, c->stream));
     double* mx = c->scratch2.as<double>();
     double* rt = mx + 12 * (size_t)n_samples;
-    LAUNCH(c, k_epnp_solve_p, dim3((unsigned)((n_samples + 63) / 64), 1), 64, 0, pr->px.as<PointPX>(), (size_t)0, n, n_samples,
-           pr->Kq.as<double>(), pr->centre.as<double>(), (size_t)0, 0, 0LL, (uint64_t)0, c->scratch1.as<int>(), mx, (float4*)nullptr, rt,
-           c->scratch3.as<uint8_t>());
+    LAUNCH(c, k_epnp_solve_p, dim3((unsigned)((n_samples + 63) / 64), 1), 64, 0, pr->px.as<PointPX>(), (size_t)0, n, n_samples, 0,
+           n_samples, (const RansacState*)nullptr, pr->Kq.as<double>(), pr->centre.as<double>(), (size_t)0, 0, 0LL, (uint64_t)0,
+           c->scratch1.as<int>(), mx, (float4*)nullptr, rt, c->scratch3.as<uint8_t>());
     CU(cudaGetLastError());
     std::vector<double> h(18 * (size_t)n_samples);
     CU(cudaMemcpyAsync(h.data(), mx, sizeof(double) * 18 * (size_t)n_samples, cudaMemcpyDeviceToHost, c->stream));
@@ -528,8 +561,9 @@ int b2r_sample_cv_p(b2r_ctx* c, int32_t n, int32_t n_iters, int32_t* idx_out) {
     if (!c || !idx_out || n < 5 || n_iters < 1) return fail(B2R_ERR_ARG, "bad argument (need n >= 5)%s%s");
     CU(cudaSetDevice(c->device));
     CU(c->scratch1.reserve(sizeof(int) * PNP_MP * (size_t)n_iters));
-    CU(c->scratch2.reserve(sizeof(int)));
-    LAUNCH(c, k_cv_sample_p, 1, 32, 0, (int)n, (int)n_iters, c->scratch1.as<int>(), c->scratch2.as<int>(), 1);
+    CU(c->scratch2.reserve(sizeof(RansacState)));
+    LAUNCH(c, k_state_init, 1, 32, 0, c->scratch2.as<RansacState>(), (int)n_iters, 1);
+    LAUNCH(c, k_cv_sample_p, 1, 32, 0, (int)n, (int)n_iters, 0, (int)n_iters, c->scratch1.as<int>(), c->scratch2.as<RansacState>(), 1);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(idx_out, c->scratch1.p, sizeof(int) * PNP_MP * (size_t)n_iters, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

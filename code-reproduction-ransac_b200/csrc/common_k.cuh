@@ -29,29 +29,62 @@ __device__ __forceinline__ int ransac_update_num_iters(double p, double ep, int 
     return denom >= 0 || -num >= maxIters * (-denom) ? maxIters : __double2int_rn(num / denom);
 }
 
-// OpenCV's sequential rule applied to the counts of a scored superset: walk the iterations
-// in order, take a hypothesis when its count beats max(best, modelPoints-1), shrink niters, stop at niters.
-static __global__ void k_select_cv(const int* __restrict__ counts, const int* __restrict__ n_generated, int H, int n,
-                            int max_iters, double confidence, int model_points, HSelect* __restrict__ sel, int Q) {
+// Running state of OpenCV's sequential RANSAC loop, one per problem.  The replay path scores the
+// iterations in growing chunks (128, 256, 512, ... for the homography; 256, ... for PnP): after each chunk the rule below
+// is advanced over the chunk's counts, and chunks that start beyond the current iteration bound are never generated,
+// solved or scored — the reference typically stops after tens of iterations out of maxIters = 2000 / 5000.
+struct RansacState {
+    unsigned long long rng;  // cv::RNG state after the last generated subset
+    int niters;              // current iteration bound (shrinks through RANSACUpdateNumIters)
+    int max_good;            // best inlier count so far
+    int best;                // iteration that produced it, -1 = none
+    int it;                  // iterations consumed
+    int gen;                 // iterations for which a subset exists (getSubset can give up: the loop then ends there)
+    int done;                // the loop has ended
+};
+
+static __global__ void k_state_init(RansacState* __restrict__ st, int max_iters, int Q) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= Q) return;
-    const int* C = counts + (size_t)q * H;
-    const int gen = n_generated[q];
-    int niters = max(max_iters, 1), maxGood = 0, best = -1, it = 0;
-    for (; it < niters && it < gen; ++it) {
-        const int good = C[it];
-        if (good > max(maxGood, model_points - 1)) {
-            best = it;
-            maxGood = good;
-            niters = ransac_update_num_iters(confidence, (double)(n - good) / n, model_points, niters);
+    RansacState s;
+    s.rng = 0xffffffffffffffffull;  // OpenCV re-seeds cv::RNG with 2^64-1 inside every call
+    s.niters = max(max_iters, 1);
+    s.max_good = 0; s.best = -1; s.it = 0; s.gen = 0; s.done = 0;
+    st[q] = s;
+}
+
+// Advance the rule over iterations [begin, begin+len): take a hypothesis when its count beats max(best, modelPoints-1),
+// shrink niters, stop at niters.  counts: [Q][H_stride].  *not_done is incremented for every problem that needs the next chunk.
+static __global__ void k_select_cv_chunk(const int* __restrict__ counts, int H_stride, int begin, int len, int n, double confidence,
+                                         int model_points, RansacState* __restrict__ st, HSelect* __restrict__ sel, int Q,
+                                         int* __restrict__ not_done) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    RansacState s = st[q];
+    if (!s.done) {
+        const int* C = counts + (size_t)q * H_stride;
+        const int end = min(begin + len, s.gen);
+        int it = max(begin, s.it);
+        for (; it < s.niters && it < end; ++it) {
+            const int good = C[it];
+            if (good > max(s.max_good, model_points - 1)) {
+                s.best = it;
+                s.max_good = good;
+                s.niters = ransac_update_num_iters(confidence, (double)(n - good) / n, model_points, s.niters);
+            }
         }
+        s.it = it;
+        // ended: bound reached, getSubset gave up inside this chunk, or this was the last chunk
+        s.done = (it >= s.niters || s.gen < begin + len || begin + len >= H_stride) ? 1 : 0;
+        st[q] = s;
+        if (!s.done) atomicAdd(not_done, 1);
     }
-    HSelect s;
-    s.best = best;
-    s.best_count = maxGood;
-    s.iters_run = it;
-    s.pad = 0;
-    sel[q] = s;
+    HSelect o;
+    o.best = s.best;
+    o.best_count = s.max_good;
+    o.iters_run = s.it;
+    o.pad = 0;
+    sel[q] = o;
 }
 
 // Fixed-H rule: the lowest-id hypothesis with the maximum count; key = count << 32 | (0xFFFFFFFF - id).

@@ -91,17 +91,21 @@ k_philox_sample_solve_h(const PointH* __restrict__ pts, int n, int H, long long 
 }
 
 // ---- K1 (replay of cv::RNG): one thread per problem, sequential ------------------------------------------
-// samples : [Q][n_iters][4]; n_generated[q] = iterations for which a subset was produced
-__global__ void k_cv_sample_h(const PointH* __restrict__ pts, int n, int n_iters, int* __restrict__ samples,
-                              int* __restrict__ n_generated, int Q) {
+// Generates the subsets of iterations [begin, begin+len) (clipped to the problem's current iteration bound),
+// continuing the RNG stream stored in the problem's state.  samples : [Q][H_stride][4]
+__global__ void k_cv_sample_h(const PointH* __restrict__ pts, int n, int H_stride, int begin, int len,
+                              int* __restrict__ samples, RansacState* __restrict__ state, int Q) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= Q) return;
+    RansacState st = state[q];
+    if (st.done || begin >= st.niters || st.gen < begin) return;
     const PointH* P = pts + (size_t)q * n;
-    int* S = samples + (size_t)q * n_iters * 4;
+    int* S = samples + (size_t)q * H_stride * 4;
     CvRng rng;
-    rng.state = 0xffffffffffffffffull;
-    int it = 0;
-    for (; it < n_iters; ++it) {
+    rng.state = st.rng;
+    const int end = min(begin + len, st.niters);
+    int it = begin;
+    for (; it < end; ++it) {
         int idx[4];
         float ms1[8], ms2[8];
         bool found = false;
@@ -125,21 +129,25 @@ __global__ void k_cv_sample_h(const PointH* __restrict__ pts, int n, int n_iters
         if (!found) break;
         reinterpret_cast<int4*>(S)[it] = make_int4(idx[0], idx[1], idx[2], idx[3]);
     }
-    n_generated[q] = it;
+    st.rng = rng.state;
+    st.gen = it;
+    state[q] = st;
 }
 
 // ---- K2: batched 4-point solves from stored samples -------------------------------------------------------
-// H64 (optional): [Q][H][9] fp64 models, ok (optional): [Q][H] flags, subset_ok (optional): checkSubset result
+// Solves iterations [begin, begin+len) of every problem (those below state[q].gen when a state is given).
+// H64 (optional): [Q][H_stride][9] fp64 models, ok (optional): flags, subset_ok (optional): checkSubset result
 __global__ void __launch_bounds__(128)
-k_solve_h4(const PointH* __restrict__ pts, int n, const int* __restrict__ samples, int H, const int* __restrict__ n_valid,
-           float4* __restrict__ models, double* __restrict__ H64, uint8_t* __restrict__ ok_out,
-           uint8_t* __restrict__ subset_ok, int fast_solver) {
+k_solve_h4(const PointH* __restrict__ pts, int n, const int* __restrict__ samples, int H_stride, int begin, int len,
+           const RansacState* __restrict__ state, float4* __restrict__ models, double* __restrict__ H64,
+           uint8_t* __restrict__ ok_out, uint8_t* __restrict__ subset_ok, int fast_solver) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int q = blockIdx.y;
-    if (g >= H) return;
-    const size_t slot = (size_t)q * H + g;
+    if (g >= len) return;
+    const int it = begin + g;
+    const size_t slot = (size_t)q * H_stride + it;
     const int4 s = reinterpret_cast<const int4*>(samples)[slot];
-    const bool have = (n_valid == nullptr || g < n_valid[q]) && s.x >= 0;
+    const bool have = (state == nullptr || it < state[q].gen) && s.x >= 0;
     double Hm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     bool ok = false;
     if (have) {
@@ -442,7 +450,22 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                 for (int i = 0; i < 81; ++i) Ap[i] = sh.A[i];
                 for (int i = 0; i < 9; ++i) Ap[i * 9 + i] += sh.lambda * sh.D[i];
                 double dd[9], L[81];
-                if (sh.lambda > 0 && cholesky<9>(Ap, L)) cholesky_solve<9>(L, sh.v, dd);
+                bool solved = false;
+                if (sh.lambda > 0) {
+                    solved = cholesky<9>(Ap, L);
+                } else if (fast_solver) {
+                    // throughput mode: the null direction is known (n = x/|x|, J n = 0, hence n.v = 0), so the
+                    // minimum-norm solution is that of the SPD system (A + s n n^T) d = v
+                    double nn = 0, tr = 0;
+                    for (int i = 0; i < 9; ++i) { nn += sh.x[i] * sh.x[i]; tr += sh.A[i * 9 + i]; }
+                    const double sg = tr / (9 * nn);
+                    for (int i = 0; i < 9; ++i)
+                        for (int j = 0; j < 9; ++j) Ap[i * 9 + j] += sg * sh.x[i] * sh.x[j];
+                    solved = cholesky<9>(Ap, L);
+                    if (!solved)
+                        for (int i = 0; i < 81; ++i) Ap[i] = sh.A[i];
+                }
+                if (solved) cholesky_solve<9>(L, sh.v, dd);
                 else solve_sym_eig<9>(Ap, sh.v, dd, nullptr);
                 for (int i = 0; i < 9; ++i) { sh.d[i] = dd[i]; sh.xd[i] = sh.x[i] - dd[i]; }
             }
@@ -467,7 +490,24 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     nu = fmin(fmax(nu, 2.), 10.);
                     if (sh.lambda == 0) {
                         double diag[9], maxval = DBL_EPSILON;
-                        solve_sym_eig<9>(sh.A, nullptr, nullptr, diag);
+                        bool have = false;
+                        if (fast_solver) {  // diag of the pseudo-inverse = diag((A + s n n^T)^-1) - n_i^2 / s
+                            double Ar[81], L[81], nn = 0, tr = 0;
+                            for (int i = 0; i < 9; ++i) { nn += sh.x[i] * sh.x[i]; tr += sh.A[i * 9 + i]; }
+                            const double sg = tr / (9 * nn);
+                            for (int i = 0; i < 9; ++i)
+                                for (int j = 0; j < 9; ++j) Ar[i * 9 + j] = sh.A[i * 9 + j] + sg * sh.x[i] * sh.x[j];
+                            if (cholesky<9>(Ar, L)) {
+                                have = true;
+                                for (int j = 0; j < 9; ++j) {
+                                    double e[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, y[9];
+                                    e[j] = 1;
+                                    cholesky_solve<9>(L, e, y);
+                                    diag[j] = y[j] - sh.x[j] * sh.x[j] / (nn * sg);
+                                }
+                            }
+                        }
+                        if (!have) solve_sym_eig<9>(sh.A, nullptr, nullptr, diag);
                         for (int i = 0; i < 9; ++i) maxval = fmax(maxval, fabs(diag[i]));
                         sh.lambda = sh.lc = 1. / maxval;
                         nu *= 0.5;

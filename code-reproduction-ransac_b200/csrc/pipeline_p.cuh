@@ -57,14 +57,19 @@ __global__ void k_pack_points_p(const double* __restrict__ obj, const double* __
 // ---- K1: samplers --------------------------------------------------------------------------------------------
 // Replay of the subsets RANSACPointSetRegistrator::getSubset draws for a callback without checkSubset
 // (SURVEY.md A.3): cv::RNG(2^64-1), `next() % n` per slot, duplicates re-drawn one at a time.  The stream depends
-// on n only; one thread per problem writes samples[q][it][0..4].
-__global__ void k_cv_sample_p(int n, int n_iters, int* __restrict__ samples, int* __restrict__ n_generated, int Q) {
+// on n only; one thread per problem continues it over iterations [begin, begin+len) (clipped to the problem's current
+// iteration bound) and writes samples[q][it][0..4].
+__global__ void k_cv_sample_p(int n, int H_stride, int begin, int len, int* __restrict__ samples, RansacState* __restrict__ state,
+                              int Q) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= Q) return;
-    int* S = samples + (size_t)q * n_iters * PNP_MP;
+    RansacState st = state[q];
+    if (st.done || begin >= st.niters || st.gen < begin) return;
+    int* S = samples + (size_t)q * H_stride * PNP_MP;
     CvRng rng;
-    rng.state = 0xffffffffffffffffull;
-    for (int it = 0; it < n_iters; ++it) {
+    rng.state = st.rng;
+    const int end = min(begin + len, st.niters);
+    for (int it = begin; it < end; ++it) {
         int idx[PNP_MP];
         if (n > PNP_MP) {
             for (int i = 0; i < PNP_MP; ++i) {
@@ -82,7 +87,9 @@ __global__ void k_cv_sample_p(int n, int n_iters, int* __restrict__ samples, int
         }
         for (int i = 0; i < PNP_MP; ++i) S[it * PNP_MP + i] = idx[i];
     }
-    n_generated[q] = n_iters;
+    st.rng = rng.state;
+    st.gen = end;
+    state[q] = st;
 }
 
 // 5 distinct indices in [0, n) from two Philox blocks (same no-rejection scheme as distinct4)
@@ -133,19 +140,22 @@ __device__ __forceinline__ void store_fast_model(float4* __restrict__ mf, size_t
     mf[3 * slot + 2] = r2;
 }
 
-// One thread per (problem, hypothesis).  sampler_philox != 0: draw the sample from the hypothesis id first.
+// One thread per (problem, hypothesis) for hypotheses [begin, begin+len) of every problem ([Q][H] arrays).
+// sampler_philox != 0: draw the sample from the hypothesis id first.  state (replay path): iterations at or beyond
+// state[q].gen are not solved (their model is NaN).
 //   samples : [Q][H][5] (read in replay mode, written in Philox mode)
 //   mx      : [Q][H][12] fp64  R(rvec) | tvec   (what cv::projectPoints evaluates), NaN = no model      (optional)
 //   mf      : [Q][H][3] float4 rows of the fast model                                                     (optional)
 //   rt      : [Q][H][6] fp64 rvec | tvec, zeros when there is no model                                    (optional)
 __global__ void __launch_bounds__(64)
-k_epnp_solve_p(const PointPX* __restrict__ pts, size_t pts_q_stride, int n, int H, const double* __restrict__ Kq,
+k_epnp_solve_p(const PointPX* __restrict__ pts, size_t pts_q_stride, int n, int H, int begin, int len,
+               const RansacState* __restrict__ state, const double* __restrict__ Kq,
                const double* __restrict__ centre, size_t centre_q_stride, int sampler_philox, long long hyp_begin,
                uint64_t seed, int* __restrict__ samples, double* __restrict__ mx, float4* __restrict__ mf,
                double* __restrict__ rt, uint8_t* __restrict__ ok_out) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int q = blockIdx.y;
-    if (g >= H) return;
+    if ((int)(blockIdx.x * blockDim.x + threadIdx.x) >= len) return;
+    const int g = begin + blockIdx.x * blockDim.x + threadIdx.x;
     const size_t slot = (size_t)q * H + g;
     const PointPX* P = pts + (size_t)q * pts_q_stride;
     int idx[PNP_MP];
@@ -159,9 +169,12 @@ k_epnp_solve_p(const PointPX* __restrict__ pts, size_t pts_q_stride, int n, int 
         for (int i = 0; i < PNP_MP; ++i) idx[i] = samples[slot * PNP_MP + i];
     }
     double obj5[15], img5[10], rvec[3], tvec[3], R[9];
-    gather5(P, idx, obj5, img5);
     const double* K4 = Kq + (size_t)q * 4;
-    const bool ok = pnp_minimal_model(obj5, img5, K4[0], K4[1], K4[2], K4[3], rvec, tvec);
+    bool ok = state == nullptr || g < state[q].gen;
+    if (ok) {
+        gather5(P, idx, obj5, img5);
+        ok = pnp_minimal_model(obj5, img5, K4[0], K4[1], K4[2], K4[3], rvec, tvec);
+    }
     if (ok) rodrigues_vec2mat(rvec, R);
     if (mx) {
         const double qn = __longlong_as_double(0x7ff8000000000000ll);

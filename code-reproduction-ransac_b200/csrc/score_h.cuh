@@ -115,17 +115,17 @@ struct HEval {
     }
 };
 
-// models : [Q][H][8] fp32 (h0..h7, h8 == 1 implied), 32-byte aligned rows
+// models : [Q][H_stride][8] fp32 (h0..h7, h8 == 1 implied), 32-byte aligned rows; the first H of each problem are scored
 // pts    : [Q][N] PointH
-// counts : [Q][H] int32, must be zeroed by the caller; each CTA adds its tile's inlier counts
+// counts : [Q][H_stride] int32, must be zeroed by the caller; each CTA adds its tile's inlier counts
 // grid   : x = ceil(H / (K3_THREADS*2*NPAIR)), y = ceil(N / tile_pts), z = Q; dynamic smem = 128 + tile_pts*16
 template <int NPAIR, bool EXACT>
 __global__ void __launch_bounds__(K3_THREADS, 2)
-k3_score_h(const float4* __restrict__ models, int H, const PointH* __restrict__ pts, int N, float thr,
+k3_score_h(const float4* __restrict__ models, int H, int H_stride, const PointH* __restrict__ pts, int N, float thr,
            int* __restrict__ counts, int tile_pts) {
-    models += (size_t)blockIdx.z * H * 2;
+    models += (size_t)blockIdx.z * H_stride * 2;
     pts += (size_t)blockIdx.z * N;
-    counts += (size_t)blockIdx.z * H;
+    counts += (size_t)blockIdx.z * H_stride;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     const float4* tile = reinterpret_cast<const float4*>(smem_raw + 128);

@@ -50,18 +50,18 @@ __device__ __forceinline__ bool p_inlier_exact(const double* R, const double* t,
 
 constexpr int K3P_THREADS = 256;
 
-// models : [Q][H][12] fp64 = R (row-major 9) | t (3); NaN rows = no model
+// models : [Q][H_stride][12] fp64 = R (row-major 9) | t (3); NaN rows = no model; the first H of each problem are scored
 // pts    : [N] PointPX (pts_q_stride = 0: the Q problems share the points, e.g. the intrinsics grid of testpro-K.py) or [Q][N]
 // Kq     : [Q][4] fp64 = fx, fy, cx, cy
 // counts : [Q][H] int32, zeroed by the caller
 // grid   : x = ceil(H / (K3P_THREADS*NH)), y = ceil(N / tile_pts), z = Q; dynamic smem = 128 + tile_pts*32
 template <int NH>
 __global__ void __launch_bounds__(K3P_THREADS)
-k3_score_p_exact(const double* __restrict__ models, int H, const PointPX* __restrict__ pts, size_t pts_q_stride, int N,
-                 const double* __restrict__ Kq, float thr, int* __restrict__ counts, int tile_pts) {
-    models += (size_t)blockIdx.z * H * 12;
+k3_score_p_exact(const double* __restrict__ models, int H, int H_stride, const PointPX* __restrict__ pts, size_t pts_q_stride,
+                 int N, const double* __restrict__ Kq, float thr, int* __restrict__ counts, int tile_pts) {
+    models += (size_t)blockIdx.z * H_stride * 12;
     pts += (size_t)blockIdx.z * pts_q_stride;
-    counts += (size_t)blockIdx.z * H;
+    counts += (size_t)blockIdx.z * H_stride;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     const PointPX* tile = reinterpret_cast<const PointPX*>(smem_raw + 128);
@@ -114,11 +114,11 @@ k3_score_p_exact(const double* __restrict__ models, int H, const PointPX* __rest
 // pts    : PointPF, same sharing rule as above
 template <int NPAIR>
 __global__ void __launch_bounds__(K3_THREADS, 2)
-k3_score_p_fast(const float4* __restrict__ models, int H, const PointPF* __restrict__ pts, size_t pts_q_stride, int N,
-                float thr, int* __restrict__ counts, int tile_pts) {
-    models += (size_t)blockIdx.z * H * 3;
+k3_score_p_fast(const float4* __restrict__ models, int H, int H_stride, const PointPF* __restrict__ pts, size_t pts_q_stride,
+                int N, float thr, int* __restrict__ counts, int tile_pts) {
+    models += (size_t)blockIdx.z * H_stride * 3;
     pts += (size_t)blockIdx.z * pts_q_stride;
-    counts += (size_t)blockIdx.z * H;
+    counts += (size_t)blockIdx.z * H_stride;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     const PointPF* tile = reinterpret_cast<const PointPF*>(smem_raw + 128);

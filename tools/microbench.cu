@@ -152,7 +152,7 @@ static void run_k3(const char* name, const float4* d_models, int H, const PointH
     for (int r = 0; r < reps + 2; ++r) {
         CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * H));
         CK(cudaEventRecord(e0));
-        k3_score_h<NPAIR, EXACT><<<grid, K3_THREADS, smem>>>(d_models, H, d_pts, N, thr, d_counts, tile);
+        k3_score_h<NPAIR, EXACT><<<grid, K3_THREADS, smem>>>(d_models, H, H, d_pts, N, thr, d_counts, tile);
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         CK(cudaGetLastError());

@@ -97,7 +97,7 @@ int main(int argc, char** argv) {
         cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); float best = 1e30f;
         for (int r = 0; r < 6; ++r) {
             CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * H)); CK(cudaEventRecord(e0));
-            k3_score_h<2, false><<<grid, K3_THREADS, smem>>>(d_models, H, d_pts, N, thr, d_counts, tile);
+            k3_score_h<2, false><<<grid, K3_THREADS, smem>>>(d_models, H, H, d_pts, N, thr, d_counts, tile);
             CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (r >= 2) best = fminf(best, ms);
         }
         CK(cudaMemcpy(ref.data(), d_counts, sizeof(int) * H, cudaMemcpyDeviceToHost));
