@@ -56,6 +56,8 @@ SIGNATURES = {
                                       c_u8_p, C.POINTER(HInfo)]),
     "b2r_find_homography_batch": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_int32, C.c_int32,
                                             C.POINTER(HParams), c_double_p, c_u8_p, C.POINTER(HInfo)]),
+    "b2r_camera_sweep": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, c_double_p, C.c_int32, C.POINTER(HParams),
+                                   c_double_p, c_double_p, c_double_p, c_u8_p, C.POINTER(HInfo), c_i32_p]),
     "b2r_h_problem_upload": (C.c_void_p, [C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_int32, C.c_int32]),
     "b2r_h_problem_reupload": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_int32, C.c_int32]),
     "b2r_h_problem_free": (None, [C.c_void_p, C.c_void_p]),

@@ -305,6 +305,21 @@ class Context:
     def upload(self, src, dst, dst_shared=None):
         return HomographyProblem(self, src, dst, dst_shared)
 
+    def camera_sweep(self, pos3d, pixels, cams, thr, max_iters=2000, confidence=0.995, **kw):
+        """find_homographies + arg-min (main_v1.py:254-297, :863-866) fused on the device: projection of the landmarks per
+        candidate camera, RANSAC, err1/err2, arg-min.  Returns dict(scores (Q,2), M (Q,3,3), H (Q,3,3), mask (Q,n), infos, best)."""
+        pos3d, pixels, cams = _f64(pos3d, 3), _f64(pixels, 2), _f64(cams, 3)
+        n, Q = len(pos3d), len(cams)
+        p = make_params(thr, max_iters, confidence, **kw)
+        scores, M, H = np.zeros((Q, 2)), np.zeros((Q, 3, 3)), np.zeros((Q, 3, 3))
+        mask = np.zeros((Q, n), dtype=np.uint8)
+        info = (HInfo * Q)()
+        best = C.c_int32(0)
+        self._check(self._L.b2r_camera_sweep(self._c, _ptr(pos3d, C.c_double), _ptr(pixels, C.c_double), n, _ptr(cams, C.c_double), Q,
+                                             C.byref(p), _ptr(scores, C.c_double), _ptr(M, C.c_double), _ptr(H, C.c_double),
+                                             _ptr(mask, C.c_uint8), info, C.byref(best)))
+        return dict(scores=scores, M=M, H=H, mask=mask, infos=[_info_dict(i) for i in info], best=int(best.value))
+
     # ---- cv2.solvePnPRansac / solvePnPRefineLM ----------------------------------------------------------
     def solve_pnp_ransac(self, obj, img, K, iterations_count=100, reprojection_error=8.0, confidence=0.99, **kw):
         """cv2.solvePnPRansac(obj, img, K, zeros, iterationsCount=..., reprojectionError=..., confidence=...) on the GPU

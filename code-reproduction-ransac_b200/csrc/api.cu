@@ -2,7 +2,7 @@
 // arithmetic step of the hot path runs in the kernels of pipeline_h.cuh / score_h.cuh.  There is no CPU
 // fallback: each entry point fails with B2R_ERR_CUDA when no device is usable.
 #include "host_common.h"
-#include "pipeline_h.cuh"
+#include "sweep.cuh"
 
 using namespace b2r;
 
@@ -29,12 +29,13 @@ struct b2r_h_problem {
     DevBuf mask;      // [Q][n] u8
     DevBuf rmask;     // [Q][n] u8
     DevBuf info;      // [Q][12] int32
+    DevBuf sweep;     // camera sweep: pos3d, pixels, cams, pos2 [Q][n][2], scores [Q][2], M [Q][9], best
     int H_last = 0;
     float stage_ms[5] = {0, 0, 0, 0, 0};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     void release() {
         pts.release(); samples.release(); models.release(); counts.release(); state.release(); keys.release();
-        sel.release(); H.release(); mask.release(); rmask.release(); info.release();
+        sel.release(); H.release(); mask.release(); rmask.release(); info.release(); sweep.release();
         for (auto& e : ev)
             if (e) cudaEventDestroy(e), e = nullptr;
     }
@@ -491,6 +492,50 @@ int b2r_find_homography(b2r_ctx* c, const double* src, const double* dst, int32_
     if (rc) return rc;
     if (info_out) *info_out = info;
     return info.status;
+}
+
+
+// ---- the camera-location sweep (find_homographies + arg-min), fused --------------------------------------------------
+int b2r_camera_sweep(b2r_ctx* c, const double* pos3d, const double* pixels, int32_t n, const double* cams, int32_t Q,
+                     const b2r_h_params* p, double* scores_out, double* M_out, double* H_out, uint8_t* mask_out,
+                     b2r_h_info* info_out, int32_t* best_out) {
+    if (!c || !pos3d || !pixels || !cams || !scores_out) return fail(B2R_ERR_ARG, "null argument%s%s");
+    if (Q < 1) return fail(B2R_ERR_ARG, "Q must be >= 1%s%s");
+    if (n < 4) return fail(B2R_ERR_ARG, "findHomography needs at least 4 point pairs (cv2 raises cv2.error)%s%s");
+    int rc = check_params(p);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    if (!c->cached) c->cached = new b2r_h_problem();
+    b2r_h_problem* pr = c->cached;
+    const size_t total = (size_t)Q * n;
+    CU(pr->pts.reserve(sizeof(PointH) * total));
+    // layout of the sweep buffer (doubles): pos3d 3n | pixels 2n | cams 3Q | pos2 2Qn | scores 2Q | M 9Q | best (int)
+    const size_t o_pix = 3 * (size_t)n, o_cam = o_pix + 2 * (size_t)n, o_pos2 = o_cam + 3 * (size_t)Q, o_sc = o_pos2 + 2 * total,
+                 o_M = o_sc + 2 * (size_t)Q, o_best = o_M + 9 * (size_t)Q;
+    CU(pr->sweep.reserve(sizeof(double) * (o_best + 1)));
+    double* sw = pr->sweep.as<double>();
+    CU(cudaMemcpyAsync(sw, pos3d, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(sw + o_pix, pixels, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(sw + o_cam, cams, sizeof(double) * 3 * Q, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_sweep_prologue, (unsigned)((total + 255) / 256), 256, 0, sw, sw + o_pix, sw + o_cam, Q, n, sw + o_pos2,
+           pr->pts.as<PointH>());
+    CU(cudaGetLastError());
+    pr->Q = Q;
+    pr->n = n;
+    if ((rc = run_score(c, pr, p))) return rc;
+    if ((rc = run_finish(c, pr, p, nullptr))) return rc;
+    LAUNCH(c, k_sweep_epilogue, (unsigned)Q, 128, 0, pr->H.as<double>(), pr->mask.as<uint8_t>(), pr->info.as<int>(), sw + o_pos2,
+           sw + o_pix, n, p->thr, sw + o_sc, sw + o_M);
+    LAUNCH(c, k_sweep_argmin, 1, 256, 0, sw + o_sc, Q, reinterpret_cast<int*>(sw + o_best));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(scores_out, sw + o_sc, sizeof(double) * 2 * Q, cudaMemcpyDeviceToHost, c->stream));
+    if (M_out) CU(cudaMemcpyAsync(M_out, sw + o_M, sizeof(double) * 9 * Q, cudaMemcpyDeviceToHost, c->stream));
+    int best = 0;
+    CU(cudaMemcpyAsync(&best, sw + o_best, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    rc = fetch(c, pr, H_out, mask_out, info_out);   // synchronises the stream
+    if (rc) return rc;
+    if (best_out) *best_out = best;
+    return B2R_OK;
 }
 
 // ---- building blocks ------------------------------------------------------------------------------------------------

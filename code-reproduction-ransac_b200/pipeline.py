@@ -62,9 +62,12 @@ def find_homography(recs, pixels, pos3ds, symbols, camera_location, im=None, sho
 
 
 def find_homographies(recs, camera_locations, im=None, show=False, ransacbound=75.0, output=None, ctx=None,
-                      return_details=False, **ransac_kw):
+                      return_details=False, fused=True, **ransac_kw):
     """The camera-location sweep, main_v1.py:254-297: returns num_matches (Q, 2) = [err1, err2] per candidate and,
-    when `output` is given and show is False, writes the reference's `*_location.csv` (main_v1.py:286-292)."""
+    when `output` is given and show is False, writes the reference's `*_location.csv` (main_v1.py:286-292).
+
+    fused=True (default): ONE device call (b2r_camera_sweep) does the per-candidate projection, the RANSAC, the scores
+    and the arg-min.  fused=False: projection and scores in NumPy around the batched RANSAC call (same results)."""
     ctx = ctx or api.default_context()
     pixels = np.array([r["pixel"] for r in recs], dtype=np.float64)
     pos3ds = np.array([r["pos3d"] for r in recs], dtype=np.float64)
@@ -72,17 +75,31 @@ def find_homographies(recs, camera_locations, im=None, show=False, ransacbound=7
     loc3ds = np.array([cl["pos3d"] for cl in camera_locations], dtype=np.float64)
     Q = loc3ds.shape[0]
     good = (pixels[:, 0] != 0) | (pixels[:, 1] != 0)
-    pos2 = candidate_pos2(pos3ds[None, good, :], loc3ds[:, None, :])          # (Q, n, 2)
-    H, ok, mask, infos = ctx.find_homography_batch(pos2, pixels[good], ransacbound, **ransac_kw)
+    grid_code_min = 0                                                           # main_v1.py:275
     num_matches = np.zeros((Q, 2))
     Ms = np.zeros((Q, 3, 3))
-    grid_code_min = 0                                                           # main_v1.py:275
-    for i in range(Q):
-        if grids[i] >= grid_code_min:
-            if not ok[i]:
-                raise np.linalg.LinAlgError(f"findHomography returned no model for candidate {i} "
-                                            "(the reference fails at main_v1.py:314)")
-            Ms[i], num_matches[i, 0], num_matches[i, 1] = _score(H[i], mask[i], pos2[i], pixels[good], ransacbound)
+    if fused:
+        res = ctx.camera_sweep(pos3ds[good], pixels[good], loc3ds, ransacbound, **ransac_kw)
+        H, mask, infos = res["H"], res["mask"], res["infos"]
+        ok = np.array([i["status"] == api.OK for i in infos])
+        pos2 = None
+        for i in range(Q):
+            if grids[i] >= grid_code_min:
+                if not ok[i]:
+                    raise np.linalg.LinAlgError(f"findHomography returned no model for candidate {i} "
+                                                "(the reference fails at main_v1.py:314)")
+                Ms[i], num_matches[i] = res["M"][i], res["scores"][i]
+        best = res["best"]
+    else:
+        pos2 = candidate_pos2(pos3ds[None, good, :], loc3ds[:, None, :])          # (Q, n, 2)
+        H, ok, mask, infos = ctx.find_homography_batch(pos2, pixels[good], ransacbound, **ransac_kw)
+        for i in range(Q):
+            if grids[i] >= grid_code_min:
+                if not ok[i]:
+                    raise np.linalg.LinAlgError(f"findHomography returned no model for candidate {i} "
+                                                "(the reference fails at main_v1.py:314)")
+                Ms[i], num_matches[i, 0], num_matches[i, 1] = _score(H[i], mask[i], pos2[i], pixels[good], ransacbound)
+        best = best_location(num_matches)
     if show is False and output:
         scores = [[i + 1, num_matches[i, 0], num_matches[i, 1], grids[i], loc3ds[i][0], loc3ds[i][1], loc3ds[i][2]]
                   for i in range(Q)]
@@ -91,7 +108,9 @@ def find_homographies(recs, camera_locations, im=None, show=False, ransacbound=7
             w.writerow(["location_id", "min_score", "max_score", "grid_code", "Z", "X", "Y"])
             w.writerows(scores)
     if return_details:
-        return num_matches, dict(H=H, M=Ms, mask=mask, infos=infos, pos2=pos2)
+        if pos2 is None:
+            pos2 = candidate_pos2(pos3ds[None, good, :], loc3ds[:, None, :])
+        return num_matches, dict(H=H, M=Ms, mask=mask, infos=infos, pos2=pos2, best=best)
     return num_matches
 
 

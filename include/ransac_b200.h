@@ -109,6 +109,16 @@ int b2r_find_homography_batch(b2r_ctx* ctx, const double* src_host, const double
                               int32_t Q, int32_t n, const b2r_h_params* params, double* H_out, uint8_t* mask_out,
                               b2r_h_info* info_out);
 
+/* ---- find_homographies + arg-min (main_v1.py:254-297, :863-866), fused on the device ---------------------------------- */
+/* pos3d_host (n,3), pixels_host (n,2): the landmarks with a non-zero pixel (main_v1.py:308 drops the others), cams_host (Q,3):
+ * candidate camera positions; all float64.  Per candidate the device computes the reference's projection pos2
+ * (main_v1.py:304-311), runs cv2.findHomography(pos2, pixels, RANSAC, params->thr), and scores it (main_v1.py:314, 327-348,
+ * 419).  scores_out (Q,2) = err1, err2 (0,0 for a candidate without model — the reference fails there, see info_out).
+ * M_out (Q,9) = inv(H), H_out (Q,9), mask_out (Q,n), info_out (Q) may be NULL.  *best_out = argmin(err2 | 0 -> 1e6). */
+int b2r_camera_sweep(b2r_ctx* ctx, const double* pos3d_host, const double* pixels_host, int32_t n, const double* cams_host,
+                     int32_t Q, const b2r_h_params* params, double* scores_out, double* M_out, double* H_out,
+                     uint8_t* mask_out, b2r_h_info* info_out, int32_t* best_out);
+
 /* ---- device-resident form: the points already live in HBM -------------------------------------------- */
 /* Uploads and packs Q problems once (fp32 quantisation as cv2 does); returns a handle. */
 typedef struct b2r_h_problem b2r_h_problem;

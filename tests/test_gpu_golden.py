@@ -49,6 +49,24 @@ def test_camera_location_sweep_on_repo_data(ctx, oracle, gold):
     assert abs(nm[180, 1] - s["err2"][180]) < 1e-6 * s["err2"][180]
 
 
+def test_fused_sweep_equals_host_side_sweep(ctx, gold):
+    """b2r_camera_sweep (projection, RANSAC, err1/err2, arg-min on the device) against the NumPy prologue/epilogue around
+    the batched call: same masks and H bit for bit, scores to 1e-8 relative (3x3 inverses of the ill-conditioned H by
+    adjugate vs LAPACK's LU; the north star asks for 1e-4 px), same arg-min."""
+    s = gold["fixture_a_sweep"]
+    pos3d, pixels, loc3ds = np.array(s["pos3d"]), np.array(s["pixels"]), np.array(s["loc3ds"])
+    recs = [dict(symbol=str(i), name="", pixel=pixels[i], pos3d=pos3d[i]) for i in range(len(pixels))]
+    recs.append(dict(symbol="x", name="not annotated", pixel=np.zeros(2), pos3d=pos3d[0] + 1.0))      # dropped, main_v1.py:308
+    locs = [dict(grid_code=g, pos3d=loc3ds[i]) for i, g in enumerate(s["grids"])]
+    nm_f, det_f = pipeline.find_homographies(recs, locs, None, False, s["thr"], None, ctx=ctx, return_details=True, fused=True)
+    nm_h, det_h = pipeline.find_homographies(recs, locs, None, False, s["thr"], None, ctx=ctx, return_details=True, fused=False)
+    np.testing.assert_array_equal(det_f["mask"], det_h["mask"])
+    np.testing.assert_array_equal(det_f["H"], det_h["H"])
+    np.testing.assert_allclose(nm_f, nm_h, rtol=1e-8)
+    np.testing.assert_allclose(det_f["M"], det_h["M"], rtol=1e-7, atol=1e-10)
+    assert det_f["best"] == det_h["best"] == pipeline.best_location(nm_f) == 180
+
+
 def test_debug_log_ransac_stage(ctx, gold):
     """The reference's recorded run: logged (legacy) masks and logged matrices M, plus what cv2 4.13 returns."""
     for b in gold["debug_log"]:
