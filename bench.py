@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--arith", default="fast", choices=["fast", "exact"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (PnP model, other configs, latencies)")
     return ap.parse_args()
 
 
@@ -305,6 +306,9 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _, _ = reference_throughput(src, dst, THR_PX, args.cpu_seconds, 1)
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        extra = extras(ctx, args, rank, world, device, src, dst)
 
     if rank == 0:
         out = {
@@ -316,9 +320,98 @@ def run_b200(args):
             "gpu_launches": int(launches_t.item()), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
             "stage_ms": stage_mean, "result": {"inliers": info_res[0]["n_inliers"], "best_count": info_res[0]["best_count"]},
         }
+        out.update(extra)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def extras(ctx, args, rank, world, device, src, dst):
+    """Secondary measurements reported next to the headline (rank 0, one GPU): the PnP model on the same workload shape,
+    BASELINE configs[1] and configs[4], and "ms to best pose" on the reference's own data next to cv2 on the host."""
+    import ransac_b200
+    from ransac_b200 import pipeline, synth
+    out = {}
+    N, H = args.points, args.hyps_per_gpu
+    rng = np.random.default_rng(1898 + 20)
+    # ---- PnP model (cv2.solvePnPRansac path), same shape ------------------------------------------------------------------
+    P, px, _ = synth.pnp_set(N, args.outliers, rng)
+    pp = ctx.upload_pnp(P, px, synth.K_1898)
+    pnp = {}
+    for name, arith in (("fast", ransac_b200.ARITH_FAST), ("exact", ransac_b200.ARITH_EXACT)):
+        par = ransac_b200.make_p_params(8.0, H, 0.99, sampler=ransac_b200.SAMPLER_PHILOX, seed=5, arith=arith)
+        best = None
+        for _ in range(4):
+            pp.run(par)
+            pp.fetch(want_inliers=False)
+            ms = pp.stage_ms()
+            best = ms if best is None or ms["total"] < best["total"] else best
+        pnp[name] = {"k3_evals_per_s": float(N) * H / (best["score"] * 1e-3), "step_evals_per_s": float(N) * H / (best["total"] * 1e-3),
+                     "stage_ms": best}
+    pnp["fast"]["k3_tflops_at_26_flop_per_eval"] = pnp["fast"]["k3_evals_per_s"] * 26.0 / 1e12
+    pp.free()
+    out["pnp_model"] = pnp
+    # ---- other BASELINE configs (homography model, fast arithmetic, Philox) -----------------------------------------------------
+    other = {}
+    for cfg, Q in ((1, 1), (4, 4096)):
+        c = synth.CONFIGS[cfg]
+        s1, d1, _ = synth.homography_set(c["n_points"], c["outliers"], np.random.default_rng(1898 + cfg))
+        if Q > 1:   # Q independent problems: fresh outliers/noise per problem would cost minutes of host time; jitter the pixels instead
+            s1 = np.broadcast_to(s1, (Q,) + s1.shape).copy()
+            d1 = np.broadcast_to(d1, (Q,) + d1.shape) + np.random.default_rng(7).normal(0, 0.3, (Q,) + d1.shape)
+        prob = ctx.upload(s1, d1)
+        par = ransac_b200.make_params(THR_PX, c["hypotheses"], sampler=ransac_b200.SAMPLER_PHILOX, seed=3, arith=ransac_b200.ARITH_FAST,
+                                      solver=ransac_b200.SOLVER_FAST)
+        best = None
+        for _ in range(4):
+            prob.run(par)
+            prob.fetch(want_mask=False)
+            ms = prob.stage_ms()
+            best = ms if best is None or ms["total"] < best["total"] else best
+        ev = float(c["n_points"]) * c["hypotheses"] * Q
+        other[f"configs[{cfg}]"] = {"problems": Q, "points": c["n_points"], "hypotheses": c["hypotheses"],
+                                    "step_evals_per_s": ev / (best["total"] * 1e-3), "k3_evals_per_s": ev / (best["score"] * 1e-3),
+                                    "stage_ms": best}
+        prob.free()
+    out["other_configs"] = other
+    # ---- ms to best pose on the reference's own data (golden inputs), parity mode --------------------------------------------------
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "cv2_golden.json")) as f:
+            g = json.load(f)["fixture_a_sweep"]
+        pos3d, pixels, loc3ds = np.array(g["pos3d"]), np.array(g["pixels"]), np.array(g["loc3ds"])
+
+        def med(fn, reps=15):
+            fn(); fn()
+            ts = []
+            for _ in range(reps):
+                t = time.perf_counter(); fn(); ts.append(time.perf_counter() - t)
+            return 1e3 * float(np.median(ts))
+        lat = {"sweep_458_candidates_ms": med(lambda: ctx.camera_sweep(pos3d, pixels, loc3ds, g["thr"])),
+               "find_homography_12pts_ms": med(lambda: ctx.find_homography(pipeline.candidate_pos2(pos3d, loc3ds[180]), pixels, g["thr"])),
+               "solve_pnp_ransac_12pts_ms": med(lambda: ctx.solve_pnp_ransac(pos3d, pixels, synth.K_1898, 5000, 30.0, 0.99)),
+               "estimate_camera_pose_12pts_ms": med(lambda: pipeline.estimate_camera_pose(pos3d, pixels, synth.K_1898, ctx=ctx)),
+               "what": "wall clock per call through the host API incl. H2D/D2H, CV_REPLAY sampler + exact arithmetic (bit-exact "
+                       "inlier sets): main_v1.py:254-297 sweep, :312, :497-502, :468-512"}
+        try:
+            import cv2
+            cv2.setNumThreads(1)
+            dist0 = np.zeros((4, 1))
+            pos2 = pipeline.candidate_pos2(pos3d[None], loc3ds[:, None, :])
+
+            def cv_sweep():
+                for q in range(len(loc3ds)):
+                    cv2.findHomography(pos2[q], pixels, cv2.RANSAC, g["thr"])
+            lat["cv2_host"] = {"sweep_458_candidates_ms": med(cv_sweep, 3),
+                               "find_homography_12pts_ms": med(lambda: cv2.findHomography(pos2[180], pixels, cv2.RANSAC, g["thr"])),
+                               "solve_pnp_ransac_12pts_ms": med(lambda: cv2.solvePnPRansac(pos3d, pixels, synth.K_1898, dist0, iterationsCount=5000,
+                                                                                            reprojectionError=30.0, confidence=0.99), 5),
+                               "what": "the cv2 calls alone on one host core (the reference adds its Python loop on top)"}
+        except ImportError:
+            lat["cv2_host"] = None
+        out["ms_to_best_pose"] = lat
+    except OSError:
+        out["ms_to_best_pose"] = None
+    return out
 
 
 def measured_peaks():

@@ -13,7 +13,7 @@ from ._lib import HInfo, HParams, PInfo, PParams
 SAMPLER_CV_REPLAY, SAMPLER_PHILOX = 0, 1
 ARITH_EXACT, ARITH_FAST = 0, 1
 MASK_CV413, MASK_LEGACY = 0, 1
-SOLVER_EXACT, SOLVER_FAST = 0, 1
+SOLVER_EXACT, SOLVER_FAST, SOLVER_EXACT_WARP = 0, 1, 2
 OK, NO_MODEL = 0, 1
 
 

@@ -148,6 +148,16 @@ static int check_params(const b2r_h_params* p) {
     return B2R_OK;
 }
 
+// opt in to the 171 KB of dynamic shared memory of k_solve_h4_smem (once per process and device)
+static int k2s_prepare(b2r_ctx* c) {
+    static thread_local int done_device = -1;
+    if (done_device != c->device) {
+        CU(cudaFuncSetAttribute(k_solve_h4_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2S_SMEM));
+        done_device = c->device;
+    }
+    return B2R_OK;
+}
+
 template <int NPAIR>
 static int launch_k3(b2r_ctx* c, const float4* models, int H, int H_stride, const PointH* pts, int n, float thr_sq, int* counts,
                      int Q, int arith) {
@@ -246,11 +256,22 @@ static int run_score(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p) {
         for (int begin = 0, len = 128; begin < H; begin += len, len *= 2) {
             if (len > H - begin) len = H - begin;
             CU(cudaMemsetAsync(not_done, 0, sizeof(int), c->stream));
-            LAUNCH(c, k_cv_sample_h, (unsigned)((Q + 31) / 32), 32, 0, pr->pts.as<PointH>(), n, H, begin, len,
-                   pr->samples.as<int>(), st, Q);
-            dim3 grid((unsigned)((len + 127) / 128), (unsigned)Q);
-            LAUNCH(c, k_solve_h4, grid, 128, 0, pr->pts.as<PointH>(), n, pr->samples.as<int>(), H, begin, len,
-                   (const RansacState*)st, pr->models.as<float4>(), (double*)nullptr, (uint8_t*)nullptr, (uint8_t*)nullptr, p->solver);
+            LAUNCH(c, k_cv_sample_h, (unsigned)Q, 32, 0, pr->pts.as<PointH>(), n, H, begin, len, pr->samples.as<int>(), st, Q);
+            if (p->solver == B2R_SOLVER_EXACT && (long long)Q * len <= 4LL * c->sm_count) {
+                // a handful of solves: one warp each (latency)
+                dim3 grid((unsigned)((len + 7) / 8), (unsigned)Q);
+                LAUNCH(c, k_solve_h4_warp, grid, 256, 0, pr->pts.as<PointH>(), n, pr->samples.as<int>(), H, begin, len,
+                       (const RansacState*)st, pr->models.as<float4>(), (double*)nullptr, (uint8_t*)nullptr, (uint8_t*)nullptr);
+            } else if (p->solver == B2R_SOLVER_EXACT) {
+                if ((rc = k2s_prepare(c))) return rc;
+                dim3 grid((unsigned)((len + K2S_THREADS - 1) / K2S_THREADS), (unsigned)Q);
+                LAUNCH(c, k_solve_h4_smem, grid, K2S_THREADS, K2S_SMEM, pr->pts.as<PointH>(), n, pr->samples.as<int>(), H, begin, len,
+                       (const RansacState*)st, pr->models.as<float4>(), (double*)nullptr, (uint8_t*)nullptr, (uint8_t*)nullptr);
+            } else {
+                dim3 grid((unsigned)((len + 127) / 128), (unsigned)Q);
+                LAUNCH(c, k_solve_h4, grid, 128, 0, pr->pts.as<PointH>(), n, pr->samples.as<int>(), H, begin, len,
+                       (const RansacState*)st, pr->models.as<float4>(), (double*)nullptr, (uint8_t*)nullptr, (uint8_t*)nullptr, p->solver);
+            }
             CU(cudaGetLastError());
             rc = score_models(c, pr->models.as<float4>(), len, pr->pts.as<PointH>(), n, thr_sq, pr->counts.as<int>(), Q, p->arith, H,
                               begin);
@@ -582,9 +603,19 @@ int b2r_solve_h4(b2r_ctx* c, const float* src, const float* dst, int32_t n, cons
     CU(cudaMemcpyAsync(c->scratch1.p, idx, sizeof(int) * 4 * (size_t)n_samples, cudaMemcpyHostToDevice, c->stream));
     uint8_t* ok_d = c->scratch3.as<uint8_t>();
     uint8_t* sub_d = ok_d + n_samples;
-    LAUNCH(c, k_solve_h4, dim3((unsigned)((n_samples + 127) / 128), 1), 128, 0, c->scratch0.as<PointH>(), n,
-           c->scratch1.as<int>(), n_samples, 0, n_samples, (const RansacState*)nullptr, (float4*)nullptr, c->scratch2.as<double>(),
-           ok_d, sub_d, solver);
+    if (solver == B2R_SOLVER_EXACT_WARP) {
+        LAUNCH(c, k_solve_h4_warp, dim3((unsigned)((n_samples + 7) / 8), 1), 256, 0, c->scratch0.as<PointH>(), n,
+               c->scratch1.as<int>(), n_samples, 0, n_samples, (const RansacState*)nullptr, (float4*)nullptr, c->scratch2.as<double>(),
+               ok_d, sub_d);
+    } else if (solver == B2R_SOLVER_EXACT) {
+        if ((rc = k2s_prepare(c))) return rc;
+        LAUNCH(c, k_solve_h4_smem, dim3((unsigned)((n_samples + K2S_THREADS - 1) / K2S_THREADS), 1), K2S_THREADS, K2S_SMEM,
+               c->scratch0.as<PointH>(), n, c->scratch1.as<int>(), n_samples, 0, n_samples, (const RansacState*)nullptr,
+               (float4*)nullptr, c->scratch2.as<double>(), ok_d, sub_d);
+    } else
+        LAUNCH(c, k_solve_h4, dim3((unsigned)((n_samples + 127) / 128), 1), 128, 0, c->scratch0.as<PointH>(), n,
+               c->scratch1.as<int>(), n_samples, 0, n_samples, (const RansacState*)nullptr, (float4*)nullptr, c->scratch2.as<double>(),
+               ok_d, sub_d, solver);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(H_out, c->scratch2.p, sizeof(double) * 9 * (size_t)n_samples, cudaMemcpyDeviceToHost, c->stream));
     if (ok_out) CU(cudaMemcpyAsync(ok_out, ok_d, (size_t)n_samples, cudaMemcpyDeviceToHost, c->stream));

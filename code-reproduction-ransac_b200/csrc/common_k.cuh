@@ -202,6 +202,35 @@ __device__ void solve_sym_eig(const double* A, const double* b, double* x, doubl
     }
 }
 
+// solve_sym_eig executed by ONE WARP through the warp-cooperative Jacobi (jacobi_eig_warp): same arithmetic, ~10x
+// less latency.  A_src, b, x, inv_diag live in shared memory; x / inv_diag may be null.
+template <int N>
+__device__ void solve_sym_eig_warp(JacobiWarp9& jw, const double* A_src, const double* b, double* x, double* inv_diag) {
+    const int lane = threadIdx.x & 31;
+    for (int e = lane; e < N * N; e += 32) jw.A[e] = A_src[e];
+    __syncwarp();
+    jacobi_eig_warp<N>(jw.A, jw.W, jw.V, jw.indR, jw.indC);
+    double thr = 0;
+    for (int i = 0; i < N; ++i) thr += fabs(jw.W[i]);
+    thr *= DBL_EPSILON * 2;
+    if (lane < N) {
+        double xj = 0, dj = 0;
+        for (int i = 0; i < N; ++i) {
+            if (fabs(jw.W[i]) <= thr) continue;
+            if (x) {
+                double s = 0;
+                for (int j = 0; j < N; ++j) s += jw.V[i * N + j] * b[j];
+                s /= jw.W[i];
+                xj += s * jw.V[i * N + lane];
+            }
+            if (inv_diag) dj += jw.V[i * N + lane] * jw.V[i * N + lane] / jw.W[i];
+        }
+        if (x) x[lane] = xj;
+        if (inv_diag) inv_diag[lane] = dj;
+    }
+    __syncwarp();
+}
+
 // Cholesky factor of a symmetric positive definite N x N matrix (lower triangle in L); false when a pivot is not
 // safely positive — callers then fall back to the Jacobi eigen-decomposition, which is what OpenCV always uses.
 template <int N>

@@ -90,16 +90,28 @@ k_philox_sample_solve_h(const PointH* __restrict__ pts, int n, int H, long long 
     }
 }
 
-// ---- K1 (replay of cv::RNG): one thread per problem, sequential ------------------------------------------
+// ---- K1 (replay of cv::RNG): sequential per problem, one WARP per problem ---------------------------------------
 // Generates the subsets of iterations [begin, begin+len) (clipped to the problem's current iteration bound),
 // continuing the RNG stream stored in the problem's state.  samples : [Q][H_stride][4]
-__global__ void k_cv_sample_h(const PointH* __restrict__ pts, int n, int H_stride, int begin, int len,
-                              int* __restrict__ samples, RansacState* __restrict__ state, int Q) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+// The stream is sequential and data-dependent (duplicate draws and rejected subsets consume RNG outputs), so one lane
+// walks it; a problem gets a warp of its own because 32 problems sharing a warp would all pay for the unluckiest one's
+// rejections at every iteration.  The other lanes stage the points in shared memory when they fit (n <= 2048).
+constexpr int K1_SMEM_PTS = 2048;
+__global__ void __launch_bounds__(32)
+k_cv_sample_h(const PointH* __restrict__ pts, int n, int H_stride, int begin, int len,
+              int* __restrict__ samples, RansacState* __restrict__ state, int Q) {
+    __shared__ PointH sp[K1_SMEM_PTS];
+    const int q = blockIdx.x;
     if (q >= Q) return;
     RansacState st = state[q];
     if (st.done || begin >= st.niters || st.gen < begin) return;
     const PointH* P = pts + (size_t)q * n;
+    if (n <= K1_SMEM_PTS) {
+        for (int i = threadIdx.x; i < n; i += 32) sp[i] = P[i];
+        __syncwarp();
+        P = sp;
+    }
+    if (threadIdx.x != 0) return;
     int* S = samples + (size_t)q * H_stride * 4;
     CvRng rng;
     rng.state = st.rng;
@@ -120,7 +132,11 @@ __global__ void k_cv_sample_h(const PointH* __restrict__ pts, int n, int H_strid
                 } while (dup);
                 idx[i] = idx_i;
             }
-            gather4(P, idx, ms1, ms2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 v = *reinterpret_cast<const float4*>(P + idx[k]);
+                ms1[2 * k] = v.x; ms1[2 * k + 1] = v.y; ms2[2 * k] = -v.z; ms2[2 * k + 1] = -v.w;
+            }
             if (h_check_subset4(ms1, ms2)) {
                 found = true;
                 break;
@@ -163,6 +179,74 @@ k_solve_h4(const PointH* __restrict__ pts, int n, const int* __restrict__ sample
     if (H64)
         for (int i = 0; i < 9; ++i) H64[slot * 9 + i] = ok ? Hm[i] : 0.0;
     if (ok_out) ok_out[slot] = ok ? 1 : 0;
+}
+
+// K2, exact solver, thread per solve with the 9x9 matrices in SHARED memory ([element][thread] layout, conflict-free for
+// any per-thread pivot sequence).  One warp per CTA: 32 x 171 doubles = 43 KB of dynamic shared memory, five CTAs per SM.
+// Bit-identical to k_solve_h4; ~8x its throughput (its per-thread local arrays overflow the L1).
+constexpr int K2S_THREADS = 32;
+constexpr size_t K2S_SMEM = sizeof(double) * 171 * K2S_THREADS;
+__global__ void __launch_bounds__(K2S_THREADS)
+k_solve_h4_smem(const PointH* __restrict__ pts, int n, const int* __restrict__ samples, int H_stride, int begin, int len,
+                const RansacState* __restrict__ state, float4* __restrict__ models, double* __restrict__ H64,
+                uint8_t* __restrict__ ok_out, uint8_t* __restrict__ subset_ok) {
+    extern __shared__ __align__(16) double k2s_ws[];
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.y;
+    if (g >= len) return;
+    const int it = begin + g;
+    const size_t slot = (size_t)q * H_stride + it;
+    const int4 s = reinterpret_cast<const int4*>(samples)[slot];
+    const bool have = (state == nullptr || it < state[q].gen) && s.x >= 0;
+    double Hm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    bool ok = false;
+    if (have) {
+        const int idx[4] = {s.x, s.y, s.z, s.w};
+        float ms1[8], ms2[8];
+        gather4(pts + (size_t)q * n, idx, ms1, ms2);
+        if (subset_ok) subset_ok[slot] = h_check_subset4(ms1, ms2) ? 1 : 0;
+        ok = h_solve4_strided<K2S_THREADS>(k2s_ws + threadIdx.x, ms1, ms2, Hm) > 0;
+    } else if (subset_ok) {
+        subset_ok[slot] = 0;
+    }
+    if (models) store_model(models, slot, Hm, ok);
+    if (H64)
+        for (int i = 0; i < 9; ++i) H64[slot * 9 + i] = ok ? Hm[i] : 0.0;
+    if (ok_out) ok_out[slot] = ok ? 1 : 0;
+}
+
+// K2, exact solver, one WARP per 4-point solve (shared-memory matrices, warp-cooperative Jacobi): bit-identical to the
+// thread-per-solve kernel above and several times faster, because 81 + 81 doubles per thread in local memory do not fit
+// the L1 once a few warps are resident.  Same arguments as k_solve_h4.
+__global__ void __launch_bounds__(256)
+k_solve_h4_warp(const PointH* __restrict__ pts, int n, const int* __restrict__ samples, int H_stride, int begin, int len,
+                const RansacState* __restrict__ state, float4* __restrict__ models, double* __restrict__ H64,
+                uint8_t* __restrict__ ok_out, uint8_t* __restrict__ subset_ok) {
+    __shared__ JacobiWarp9 jw[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * 8 + warp;
+    const int q = blockIdx.y;
+    if (g >= len) return;
+    const int it = begin + g;
+    const size_t slot = (size_t)q * H_stride + it;
+    const int4 s = reinterpret_cast<const int4*>(samples)[slot];
+    const bool have = (state == nullptr || it < state[q].gen) && s.x >= 0;
+    double Hm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    bool ok = false, sub = false;
+    if (have) {
+        const int idx[4] = {s.x, s.y, s.z, s.w};
+        float ms1[8], ms2[8];
+        gather4(pts + (size_t)q * n, idx, ms1, ms2);
+        if (subset_ok) sub = h_check_subset4(ms1, ms2);
+        ok = h_solve4_warp(jw[warp], ms1, ms2, Hm) > 0;
+    }
+    if (lane == 0) {
+        if (subset_ok) subset_ok[slot] = sub ? 1 : 0;
+        if (models) store_model(models, slot, Hm, ok);
+        if (H64)
+            for (int i = 0; i < 9; ++i) H64[slot * 9 + i] = ok ? Hm[i] : 0.0;
+        if (ok_out) ok_out[slot] = ok ? 1 : 0;
+    }
 }
 
 // ---- K4 finalize -----------------------------------------------------------------------------------------------
@@ -209,9 +293,11 @@ struct HFinalizeShared {
     double H[9];          // current model (fp64)
     double x[9], xd[9];   // LM parameter vectors (all nine entries of H, as OpenCV 4.13 refines them)
     double A[81], v[9], D[9], d[9];
-    double S, lambda, lc, rmax;
+    double Ap[81], diag[9];
+    double S, Sd, lambda, lc, rmax, nu;
     float Hf[8];
-    int flag, k, lm_iters, proceed;
+    float ms1[8], ms2[8];
+    int flag, k, lm_iters, proceed, use_eig, need_diag;
 };
 
 // K4.  One cluster per problem (blockIdx.x / cluster size = problem).
@@ -228,6 +314,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
              int* __restrict__ info, const uint8_t* __restrict__ ext_mask, const double* __restrict__ ext_H) {
     __shared__ HFinalizeShared sh;
     __shared__ ClusterRed R;
+    __shared__ JacobiWarp9 jw;   // workspace of the warp-cooperative eigen-solver (warp 0)
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned csize = cluster.num_blocks(), crank = cluster.block_rank();
     const int q = blockIdx.x / csize, tid = threadIdx.x;
@@ -250,7 +337,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
         return;
     }
     const int4 smp = ext_mask ? make_int4(-1, -1, -1, -1) : reinterpret_cast<const int4*>(samples)[(size_t)q * Hs + s.best];
-    if (tid == 0) {
+    if (tid < 32) {  // warp 0: the winning minimal model (every lane computes / receives the same values)
         double Hm[9];
         if (ext_mask) {
             for (int i = 0; i < 9; ++i) Hm[i] = ext_H[(size_t)q * 9 + i];
@@ -258,11 +345,13 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
             const int idx[4] = {smp.x, smp.y, smp.z, smp.w};
             float ms1[8], ms2[8];
             gather4(P, idx, ms1, ms2);
-            if (fast_solver) h_solve4_fast(ms1, ms2, Hm); else h_solve4(ms1, ms2, Hm);
+            if (fast_solver) h_solve4_fast(ms1, ms2, Hm); else h_solve4_warp(jw, ms1, ms2, Hm);
         }
-        for (int i = 0; i < 9; ++i) sh.H[i] = Hm[i];
-        for (int i = 0; i < 8; ++i) sh.Hf[i] = (float)Hm[i];
-        sh.lm_iters = 0;
+        if (tid == 0) {
+            for (int i = 0; i < 9; ++i) sh.H[i] = Hm[i];
+            for (int i = 0; i < 8; ++i) sh.Hf[i] = (float)Hm[i];
+            sh.lm_iters = 0;
+        }
     }
     __syncthreads();
 
@@ -333,28 +422,39 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     }
                 }
             cluster_reduce<THREADS, 24, false>(R, L);
-            if (tid == 0) {
-                double LtL[81];
-                for (int j = 0; j < 81; ++j) LtL[j] = 0;
+            if (tid < 32) {  // warp 0
                 // index of (a,b), a<=b, in the packed symmetric 3x3: (0,0)=0 (0,1)=1 (0,2)=2 (1,1)=3 (1,2)=4 (2,2)=5
                 const int sym[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
-                for (int a = 0; a < 3; ++a)
-                    for (int b = 0; b < 3; ++b) {
-                        const int e = sym[a][b];
-                        if (b >= a) {
-                            LtL[a * 9 + b] = R.out[e];
-                            LtL[(3 + a) * 9 + 3 + b] = R.out[e];
-                            LtL[(6 + a) * 9 + 6 + b] = R.out[18 + e];
+                double* LtL = jw.A;
+                for (int j = tid; j < 81; j += 32) LtL[j] = 0;
+                __syncwarp();
+                if (tid == 0)
+                    for (int a = 0; a < 3; ++a)
+                        for (int b = 0; b < 3; ++b) {
+                            const int e = sym[a][b];
+                            if (b >= a) {
+                                LtL[a * 9 + b] = R.out[e];
+                                LtL[(3 + a) * 9 + 3 + b] = R.out[e];
+                                LtL[(6 + a) * 9 + 6 + b] = R.out[18 + e];
+                            }
+                            LtL[a * 9 + 6 + b] = -R.out[6 + e];
+                            LtL[(3 + a) * 9 + 6 + b] = -R.out[12 + e];
                         }
-                        LtL[a * 9 + 6 + b] = -R.out[6 + e];
-                        LtL[(3 + a) * 9 + 6 + b] = -R.out[12 + e];
-                    }
+                __syncwarp();
                 double Hm[9], vec[9];
-                if (fast_solver && smallest_eigvec9(LtL, vec))
-                    h_from_eigvec(vec, nm, Hm);
-                else
-                    h_from_LtL(LtL, nm, Hm);
-                for (int i = 0; i < 9; ++i) sh.H[i] = Hm[i];
+                bool done = false;
+                if (fast_solver) {
+                    if (tid == 0) sh.flag = smallest_eigvec9(LtL, sh.diag) ? 1 : 0;
+                    __syncwarp();
+                    if (sh.flag) {
+                        for (int i = 0; i < 9; ++i) vec[i] = sh.diag[i];
+                        h_from_eigvec(vec, nm, Hm);
+                        done = true;
+                    }
+                }
+                if (!done) h_from_LtL_warp(jw, nm, Hm);
+                if (tid == 0)
+                    for (int i = 0; i < 9; ++i) sh.H[i] = Hm[i];
             }
             __syncthreads();
         }
@@ -446,7 +546,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
             if (tid == 0) {
                 // J^T J is singular along h itself (the projection is scale-invariant): with lambda == 0 only the
                 // eigen-decomposition solve with OpenCV's cut-off is meaningful; with lambda > 0 the matrix is SPD
-                double Ap[81];
+                double* Ap = sh.Ap;
                 for (int i = 0; i < 81; ++i) Ap[i] = sh.A[i];
                 for (int i = 0; i < 9; ++i) Ap[i * 9 + i] += sh.lambda * sh.D[i];
                 double dd[9], L[81];
@@ -465,14 +565,23 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     if (!solved)
                         for (int i = 0; i < 81; ++i) Ap[i] = sh.A[i];
                 }
-                if (solved) cholesky_solve<9>(L, sh.v, dd);
-                else solve_sym_eig<9>(Ap, sh.v, dd, nullptr);
-                for (int i = 0; i < 9; ++i) { sh.d[i] = dd[i]; sh.xd[i] = sh.x[i] - dd[i]; }
+                if (solved) {
+                    cholesky_solve<9>(L, sh.v, dd);
+                    for (int i = 0; i < 9; ++i) sh.d[i] = dd[i];
+                }
+                sh.use_eig = solved ? 0 : 1;
             }
+            __syncthreads();
+            if (sh.use_eig && tid < 32) solve_sym_eig_warp<9>(jw, sh.Ap, sh.v, sh.d, nullptr);   // cv::solve(..., DECOMP_EIG)
+            __syncthreads();
+            if (tid == 0)
+                for (int i = 0; i < 9; ++i) sh.xd[i] = sh.x[i] - sh.d[i];
             __syncthreads();
             const double2 ed = eval(sh.xd, false);
             if (tid == 0) {
                 const double Sd = ed.x, S = sh.S;
+                sh.Sd = Sd;
+                sh.need_diag = 0;
                 double dS = 0;
                 for (int i = 0; i < 9; ++i) {
                     double t = 0;
@@ -488,8 +597,8 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     for (int i = 0; i < 9; ++i) t += sh.d[i] * sh.v[i];
                     double nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1) + 2;
                     nu = fmin(fmax(nu, 2.), 10.);
+                    sh.nu = nu;
                     if (sh.lambda == 0) {
-                        double diag[9], maxval = DBL_EPSILON;
                         bool have = false;
                         if (fast_solver) {  // diag of the pseudo-inverse = diag((A + s n n^T)^-1) - n_i^2 / s
                             double Ar[81], L[81], nn = 0, tr = 0;
@@ -503,20 +612,29 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                                     double e[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, y[9];
                                     e[j] = 1;
                                     cholesky_solve<9>(L, e, y);
-                                    diag[j] = y[j] - sh.x[j] * sh.x[j] / (nn * sg);
+                                    sh.diag[j] = y[j] - sh.x[j] * sh.x[j] / (nn * sg);
                                 }
                             }
                         }
-                        if (!have) solve_sym_eig<9>(sh.A, nullptr, nullptr, diag);
-                        for (int i = 0; i < 9; ++i) maxval = fmax(maxval, fabs(diag[i]));
-                        sh.lambda = sh.lc = 1. / maxval;
-                        nu *= 0.5;
+                        sh.need_diag = have ? 1 : 2;   // 2: take it from the eigen-decomposition
+                    } else {
+                        sh.lambda *= nu;
                     }
-                    sh.lambda *= nu;
                 }
-                sh.flag = Sd < S;
+            }
+            __syncthreads();
+            if (sh.need_diag == 2 && tid < 32) solve_sym_eig_warp<9>(jw, sh.A, nullptr, nullptr, sh.diag);
+            __syncthreads();
+            if (tid == 0) {
+                if (sh.need_diag) {
+                    double maxval = DBL_EPSILON;
+                    for (int i = 0; i < 9; ++i) maxval = fmax(maxval, fabs(sh.diag[i]));
+                    sh.lambda = sh.lc = 1. / maxval;
+                    sh.lambda *= sh.nu * 0.5;
+                }
+                sh.flag = sh.Sd < sh.S;
                 if (sh.flag) {
-                    sh.S = Sd;
+                    sh.S = sh.Sd;
                     for (int i = 0; i < 9; ++i) sh.x[i] = sh.xd[i];
                 }
             }

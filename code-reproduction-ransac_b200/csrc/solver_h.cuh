@@ -131,6 +131,247 @@ __device__ void jacobi_eig(double* A, double* W, double* V) {
     }
 }
 
+// ---- the same eigen-solver on strided storage ------------------------------------------------------------------------
+// Element e of A / V / W lives at base[e * STRIDE]: with STRIDE = threads per CTA and base = shared-memory column of the
+// calling thread, a warp's accesses hit 32 different banks whatever element each lane works on (every solve follows its
+// own pivot sequence), while per-thread local arrays of 171 doubles would overflow the L1 as soon as a few warps are
+// resident.  Operation for operation identical to jacobi_eig<N>.
+template <int N, int STRIDE>
+__device__ void jacobi_eig_strided(double* A, double* W, double* V) {
+    signed char indR[N], indC[N];
+    int i, k, l, m;
+#define AA(r, c) A[((r) * N + (c)) * STRIDE]
+#define VV(r, c) V[((r) * N + (c)) * STRIDE]
+#define WW(r) W[(r) * STRIDE]
+    for (i = 0; i < N * N; i++) V[i * STRIDE] = 0;
+    for (i = 0; i < N; i++) VV(i, i) = 1;
+    for (k = 0; k < N; k++) {
+        WW(k) = AA(k, k);
+        if (k < N - 1) {
+            double mv = fabs(AA(k, k + 1));
+            m = k + 1;
+            for (i = k + 2; i < N; i++) {
+                double val = fabs(AA(k, i));
+                if (mv < val) mv = val, m = i;
+            }
+            indR[k] = (signed char)m;
+        }
+        if (k > 0) {
+            double mv = fabs(AA(0, k));
+            m = 0;
+            for (i = 1; i < k; i++) {
+                double val = fabs(AA(i, k));
+                if (mv < val) mv = val, m = i;
+            }
+            indC[k] = (signed char)m;
+        }
+    }
+    for (int it = 0; it < N * N * 30; it++) {
+        double mv = fabs(AA(0, indR[0]));
+        k = 0;
+        for (i = 1; i < N - 1; i++) {
+            double val = fabs(AA(i, indR[i]));
+            if (mv < val) mv = val, k = i;
+        }
+        l = indR[k];
+        for (i = 1; i < N; i++) {
+            double val = fabs(AA(indC[i], i));
+            if (mv < val) mv = val, k = indC[i], l = i;
+        }
+        double p = AA(k, l);
+        if (fabs(p) <= DBL_EPSILON) break;
+        double y = (WW(l) - WW(k)) * 0.5;
+        double t = fabs(y) + cv_hypot(p, y);
+        double s = cv_hypot(p, t);
+        double c = t / s;
+        s = p / s;
+        t = (p / t) * p;
+        if (y < 0) s = -s, t = -t;
+        AA(k, l) = 0;
+        WW(k) -= t;
+        WW(l) += t;
+#define B2R_ROTS(v0, v1)             \
+    {                                \
+        double a0 = (v0), b0 = (v1); \
+        (v0) = a0 * c - b0 * s;      \
+        (v1) = a0 * s + b0 * c;      \
+    }
+        for (i = 0; i < k; i++) B2R_ROTS(AA(i, k), AA(i, l));
+        for (i = k + 1; i < l; i++) B2R_ROTS(AA(k, i), AA(i, l));
+        for (i = l + 1; i < N; i++) B2R_ROTS(AA(k, i), AA(l, i));
+        for (i = 0; i < N; i++) B2R_ROTS(VV(k, i), VV(l, i));
+#undef B2R_ROTS
+        for (int j = 0; j < 2; j++) {
+            int idx = j == 0 ? k : l;
+            if (idx < N - 1) {
+                mv = fabs(AA(idx, idx + 1));
+                m = idx + 1;
+                for (i = idx + 2; i < N; i++) {
+                    double val = fabs(AA(idx, i));
+                    if (mv < val) mv = val, m = i;
+                }
+                indR[idx] = (signed char)m;
+            }
+            if (idx > 0) {
+                mv = fabs(AA(0, idx));
+                m = 0;
+                for (i = 1; i < idx; i++) {
+                    double val = fabs(AA(i, idx));
+                    if (mv < val) mv = val, m = i;
+                }
+                indC[idx] = (signed char)m;
+            }
+        }
+    }
+    for (k = 0; k < N - 1; k++) {
+        m = k;
+        for (i = k + 1; i < N; i++)
+            if (WW(m) < WW(i)) m = i;
+        if (k != m) {
+            double tmp = WW(m);
+            WW(m) = WW(k);
+            WW(k) = tmp;
+            for (i = 0; i < N; i++) {
+                tmp = VV(m, i);
+                VV(m, i) = VV(k, i);
+                VV(k, i) = tmp;
+            }
+        }
+    }
+#undef AA
+#undef VV
+#undef WW
+}
+
+// ---- warp-cooperative form of the same eigen-solver ---------------------------------------------------------------
+// One solve per WARP, matrices in shared memory.  Pivot choice and the rotation parameters are computed redundantly by
+// every lane (broadcast reads, no divergence); lane i then rotates the element pairs of index i — in the serial code
+// those pairs are disjoint for different i, so every element goes through exactly the same IEEE operations and the
+// result is bit-identical to jacobi_eig<N>.  A single thread walking 9x9 matrices in local memory takes ~0.3 ms per
+// decomposition (the finalize kernel runs a dozen of them back to back); this form takes ~30 us.
+struct JacobiWarp9 {
+    double A[81], V[81], W[9];
+    int indR[9], indC[9];
+};
+
+template <int N>
+__device__ void jacobi_eig_warp(double* A, double* W, double* V, int* indR, int* indC) {
+    const int lane = threadIdx.x & 31;
+    for (int e = lane; e < N * N; e += 32) V[e] = (e / N == e % N) ? 1. : 0.;
+    if (lane < N) {
+        const int k = lane;
+        W[k] = A[k * N + k];
+        if (k < N - 1) {
+            double mv = fabs(A[k * N + k + 1]);
+            int m = k + 1;
+            for (int i = k + 2; i < N; i++) {
+                const double val = fabs(A[k * N + i]);
+                if (mv < val) mv = val, m = i;
+            }
+            indR[k] = m;
+        }
+        if (k > 0) {
+            double mv = fabs(A[k]);
+            int m = 0;
+            for (int i = 1; i < k; i++) {
+                const double val = fabs(A[i * N + k]);
+                if (mv < val) mv = val, m = i;
+            }
+            indC[k] = m;
+        }
+    }
+    __syncwarp();
+    for (int it = 0; it < N * N * 30; it++) {
+        // pivot (every lane, same result)
+        double mv = fabs(A[indR[0]]);
+        int k = 0, l, i;
+        for (i = 1; i < N - 1; i++) {
+            const double val = fabs(A[i * N + indR[i]]);
+            if (mv < val) mv = val, k = i;
+        }
+        l = indR[k];
+        for (i = 1; i < N; i++) {
+            const double val = fabs(A[indC[i] * N + i]);
+            if (mv < val) mv = val, k = indC[i], l = i;
+        }
+        const double p = A[k * N + l];
+        if (fabs(p) <= DBL_EPSILON) break;
+        const double y = (W[l] - W[k]) * 0.5;
+        double t = fabs(y) + cv_hypot(p, y);
+        double s = cv_hypot(p, t);
+        const double c = t / s;
+        s = p / s;
+        t = (p / t) * p;
+        if (y < 0) s = -s, t = -t;
+        __syncwarp();  // all lanes have read A[k][l], W[k], W[l]
+        if (lane == 0) {
+            A[k * N + l] = 0;
+            W[k] -= t;
+            W[l] += t;
+        }
+        if (lane < N) {
+            i = lane;
+            double *p0 = nullptr, *p1 = nullptr;
+            if (i < k) { p0 = &A[i * N + k]; p1 = &A[i * N + l]; }
+            else if (i > k && i < l) { p0 = &A[k * N + i]; p1 = &A[i * N + l]; }
+            else if (i > l) { p0 = &A[k * N + i]; p1 = &A[l * N + i]; }
+            if (p0) {
+                const double a0 = *p0, b0 = *p1;
+                *p0 = a0 * c - b0 * s;
+                *p1 = a0 * s + b0 * c;
+            }
+            const double v0 = V[k * N + i], v1 = V[l * N + i];
+            V[k * N + i] = v0 * c - v1 * s;
+            V[l * N + i] = v0 * s + v1 * c;
+        }
+        __syncwarp();
+        if (lane < 4) {  // indR[k], indC[k], indR[l], indC[l]
+            const int idx = lane < 2 ? k : l;
+            if ((lane & 1) == 0) {
+                if (idx < N - 1) {
+                    double m2 = fabs(A[idx * N + idx + 1]);
+                    int m = idx + 1;
+                    for (i = idx + 2; i < N; i++) {
+                        const double val = fabs(A[idx * N + i]);
+                        if (m2 < val) m2 = val, m = i;
+                    }
+                    indR[idx] = m;
+                }
+            } else if (idx > 0) {
+                double m2 = fabs(A[idx]);
+                int m = 0;
+                for (i = 1; i < idx; i++) {
+                    const double val = fabs(A[i * N + idx]);
+                    if (m2 < val) m2 = val, m = i;
+                }
+                indC[idx] = m;
+            }
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    // eigenvalues descending, rows of V alongside
+    for (int k = 0; k < N - 1; k++) {
+        int m = k;
+        for (int i = k + 1; i < N; i++)
+            if (W[m] < W[i]) m = i;
+        __syncwarp();
+        if (k != m) {
+            if (lane == 0) {
+                const double tmp = W[m];
+                W[m] = W[k];
+                W[k] = tmp;
+            }
+            if (lane < N) {
+                const double tmp = V[m * N + lane];
+                V[m * N + lane] = V[k * N + lane];
+                V[k * N + lane] = tmp;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __device__ __forceinline__ void mat3_mul(const double* a, const double* b, double* o) {
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) {
@@ -208,6 +449,106 @@ static __device__ int h_solve4(const float* M, const float* m, double* H) {
     for (int i = 0; i < 81; i++) LtL[i] = 0;
     for (int i = 0; i < count; i++) h_accumulate_LtL(LtL, nm, M[2 * i], M[2 * i + 1], m[2 * i], m[2 * i + 1]);
     h_from_LtL(LtL, nm, H);
+    return 1;
+}
+
+// 4-point solve on strided (shared-memory) storage: ws = this thread's column of a [171][STRIDE] double workspace
+// (A 81 | V 81 | W 9).  Bit-identical to h_solve4.
+template <int STRIDE>
+__device__ __forceinline__ int h_solve4_strided(double* ws, const float* M, const float* m, double* H) {
+    HNorm nm = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int count = 4;
+    for (int i = 0; i < count; i++) {
+        nm.cmx += m[2 * i];
+        nm.cmy += m[2 * i + 1];
+        nm.cMx += M[2 * i];
+        nm.cMy += M[2 * i + 1];
+    }
+    nm.cmx /= count; nm.cmy /= count; nm.cMx /= count; nm.cMy /= count;
+    for (int i = 0; i < count; i++) {
+        nm.smx += fabs(m[2 * i] - nm.cmx);
+        nm.smy += fabs(m[2 * i + 1] - nm.cmy);
+        nm.sMx += fabs(M[2 * i] - nm.cMx);
+        nm.sMy += fabs(M[2 * i + 1] - nm.cMy);
+    }
+    if (fabs(nm.smx) < DBL_EPSILON || fabs(nm.smy) < DBL_EPSILON || fabs(nm.sMx) < DBL_EPSILON || fabs(nm.sMy) < DBL_EPSILON)
+        return 0;
+    nm.smx = count / nm.smx; nm.smy = count / nm.smy; nm.sMx = count / nm.sMx; nm.sMy = count / nm.sMy;
+    double* A = ws;
+    double* V = ws + 81 * STRIDE;
+    double* W = ws + 162 * STRIDE;
+    for (int e = 0; e < 81; e++) A[e * STRIDE] = 0;
+    for (int i = 0; i < count; i++) {
+        const double x = ((double)m[2 * i] - nm.cmx) * nm.smx, y = ((double)m[2 * i + 1] - nm.cmy) * nm.smy;
+        const double X = ((double)M[2 * i] - nm.cMx) * nm.sMx, Y = ((double)M[2 * i + 1] - nm.cMy) * nm.sMy;
+        const double Lx[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x};
+        const double Ly[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
+#pragma unroll
+        for (int j = 0; j < 9; j++)
+#pragma unroll
+            for (int k = j; k < 9; k++) A[(j * 9 + k) * STRIDE] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+    }
+    for (int j = 0; j < 9; j++)
+        for (int k = 0; k < j; k++) A[(j * 9 + k) * STRIDE] = A[(k * 9 + j) * STRIDE];
+    jacobi_eig_strided<9, STRIDE>(A, W, V);
+    double vec[9];
+    for (int i = 0; i < 9; ++i) vec[i] = V[(72 + i) * STRIDE];
+    h_from_eigvec(vec, nm, H);
+    return 1;
+}
+
+// Warp-cooperative 4-point / k-point solve.  M, m: the fp32 points (count of them, every lane passes the same pointers);
+// jw: the warp's shared-memory workspace.  Every lane returns the same flag and H.  Bit-identical to h_solve4.
+__device__ __forceinline__ void h_from_LtL_warp(JacobiWarp9& jw, const HNorm& nm, double* H) {
+    const int lane = threadIdx.x & 31;
+    for (int e = lane; e < 81; e += 32) {  // mirror the upper triangle down
+        const int j = e / 9, k = e % 9;
+        if (k < j) jw.A[e] = jw.A[k * 9 + j];
+    }
+    __syncwarp();
+    jacobi_eig_warp<9>(jw.A, jw.W, jw.V, jw.indR, jw.indC);
+    double vec[9];
+    for (int i = 0; i < 9; ++i) vec[i] = jw.V[72 + i];
+    h_from_eigvec(vec, nm, H);
+    __syncwarp();
+}
+
+__device__ __forceinline__ int h_solve4_warp(JacobiWarp9& jw, const float* M, const float* m, double* H) {
+    const int lane = threadIdx.x & 31;
+    HNorm nm = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int count = 4;
+    for (int i = 0; i < count; i++) {
+        nm.cmx += m[2 * i];
+        nm.cmy += m[2 * i + 1];
+        nm.cMx += M[2 * i];
+        nm.cMy += M[2 * i + 1];
+    }
+    nm.cmx /= count; nm.cmy /= count; nm.cMx /= count; nm.cMy /= count;
+    for (int i = 0; i < count; i++) {
+        nm.smx += fabs(m[2 * i] - nm.cmx);
+        nm.smy += fabs(m[2 * i + 1] - nm.cmy);
+        nm.sMx += fabs(M[2 * i] - nm.cMx);
+        nm.sMy += fabs(M[2 * i + 1] - nm.cMy);
+    }
+    if (fabs(nm.smx) < DBL_EPSILON || fabs(nm.smy) < DBL_EPSILON || fabs(nm.sMx) < DBL_EPSILON || fabs(nm.sMy) < DBL_EPSILON)
+        return 0;
+    nm.smx = count / nm.smx; nm.smy = count / nm.smy; nm.sMx = count / nm.sMx; nm.sMy = count / nm.sMy;
+    // entry (j,k), j <= k, of L^T L: the same per-point sums, in point order, as h_accumulate_LtL
+    for (int e = lane; e < 81; e += 32) {
+        const int j = e / 9, k = e % 9;
+        if (j > k) continue;
+        double acc = 0;
+        for (int i = 0; i < count; i++) {
+            const double x = ((double)m[2 * i] - nm.cmx) * nm.smx, y = ((double)m[2 * i + 1] - nm.cmy) * nm.smy;
+            const double X = ((double)M[2 * i] - nm.cMx) * nm.sMx, Y = ((double)M[2 * i + 1] - nm.cMy) * nm.sMy;
+            const double Lx[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x};
+            const double Ly[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
+            acc += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+        }
+        jw.A[e] = acc;
+    }
+    __syncwarp();
+    h_from_LtL_warp(jw, nm, H);
     return 1;
 }
 

@@ -70,3 +70,36 @@ def find_homography_sharded(ctx, src, dst, thr, total_hypotheses, seed=0, arith=
             prob.free()
     ok = infos[0]["status"] == api.OK
     return (H[0] if ok else None), mask[0].reshape(-1, 1), infos[0]
+
+
+# ---- PnP path (cv2.solvePnPRansac, main_v1.py:497): same sharding scheme ---------------------------------------------
+def run_sharded_pnp(problem, thr, hyp_begin, hyp_count, seed=0, arith=api.ARITH_EXACT, confidence=0.99, refine=True, group=None,
+                    device=None):
+    """Score this rank's hypothesis-id shard of a resident PnPProblem, MAX-reduce the packed keys, finish on every rank."""
+    p = api.make_p_params(thr, hyp_count, confidence, sampler=api.SAMPLER_PHILOX, seed=seed, arith=arith, refine=refine,
+                          hyp_begin=hyp_begin)
+    keys = problem.score_shard(p)
+    best = reduce_keys_max(keys, group=group, device=device)
+    problem.finish(p, best)
+    return best
+
+
+def solve_pnp_ransac_sharded(ctx, obj, img, K, thr, total_hypotheses, seed=0, arith=api.ARITH_EXACT, group=None, device=None,
+                             problem=None, **kw):
+    """End-to-end sharded cv2.solvePnPRansac: host points in, (ok, rvec, tvec, inliers, info) out on every rank."""
+    import torch.distributed as dist
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_available() and dist.is_initialized() else (0, 1)
+    begin, count = shard_range(total_hypotheses, rank, world)
+    prob = problem
+    if prob is None:
+        prob = ctx.upload_pnp(obj, img, K)
+    else:
+        prob.reupload(obj, img, K)
+    try:
+        run_sharded_pnp(prob, thr, begin, count, seed=seed, arith=arith, group=group, device=device, **kw)
+        rvec, tvec, inliers, infos = prob.fetch()
+    finally:
+        if problem is None:
+            prob.free()
+    ok = infos[0]["status"] == api.OK
+    return ok, rvec[0].reshape(3, 1), tvec[0].reshape(3, 1), (inliers[0].reshape(-1, 1) if ok else None), infos[0]

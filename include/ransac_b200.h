@@ -50,6 +50,8 @@ extern "C" {
 /* minimal solver */
 #define B2R_SOLVER_EXACT 0 /* OpenCV's normalised DLT + Jacobi eigen-solver, fp64, bit-identical models */
 #define B2R_SOLVER_FAST 1  /* closed-form 4-point solve in registers (fp64), ~1e-12 relative agreement   */
+#define B2R_SOLVER_EXACT_WARP 2 /* b2r_solve_h4 only: the exact solver's one-warp-per-solve kernel (same bits; the
+                                   pipeline picks it by itself for small batches, where latency matters)  */
 /* which mask cv2.findHomography returns */
 #define B2R_MASK_CV413 0  /* OpenCV 4.13: mask re-derived from the refined H   */
 #define B2R_MASK_LEGACY 1 /* older OpenCV (the reference's debug.log): RANSAC-stage mask */

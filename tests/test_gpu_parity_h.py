@@ -46,7 +46,11 @@ def test_solver_bit_exact_and_check_subset(ctx, oracle, n, seed):
     sq, dq = _quant(s), _quant(d)
     rng = np.random.default_rng(seed)
     idx = np.stack([rng.choice(n, 4, replace=False) for _ in range(400)]).astype(np.int32)
-    H, ok, sub = ctx.solve_h4(sq, dq, idx)
+    H, ok, sub = ctx.solve_h4(sq, dq, idx)                                        # thread per solve, shared-memory matrices
+    Hw, okw, subw = ctx.solve_h4(sq, dq, idx, solver=2)                           # B2R_SOLVER_EXACT_WARP: one warp per solve
+    np.testing.assert_array_equal(H, Hw)
+    np.testing.assert_array_equal(ok, okw)
+    np.testing.assert_array_equal(sub, subw)
     for k in range(len(idx)):
         Hr = oracle.h_run_kernel(sq[idx[k]], dq[idx[k]])
         assert ok[k] == (Hr is not None)
