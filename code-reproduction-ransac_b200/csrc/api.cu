@@ -160,9 +160,9 @@ static int k2s_prepare(b2r_ctx* c) {
 
 template <int NPAIR>
 static int launch_k3(b2r_ctx* c, const float4* models, int H, int H_stride, const PointH* pts, int n, float thr_sq, int* counts,
-                     int Q, int arith) {
-    // tile: as many points per CTA as keeps >= ~4 CTAs per SM slot in flight, capped by 2048 (32 KB)
-    int tile = 1024;
+                     int Q, int arith, int max_tile) {
+    // tile: as many points per CTA as keeps >= ~4 CTAs per SM slot in flight
+    int tile = max_tile;
     const long long hyp_blocks = (H + K3_THREADS * 2 * NPAIR - 1) / (K3_THREADS * 2 * NPAIR);
     while (tile > 128 && hyp_blocks * ((n + tile - 1) / tile) * Q < 8LL * c->sm_count) tile >>= 1;
     if (tile > n) tile = ((n + 7) / 8) * 8;
@@ -185,10 +185,12 @@ static int score_models(b2r_ctx* c, const float4* models, int H, const PointH* p
     } else {
         CU(cudaMemset2DAsync(counts + begin, sizeof(int) * (size_t)H_stride, 0, sizeof(int) * (size_t)H, (size_t)Q, c->stream));
     }
-    // few hypotheses per problem: 2 pairs per thread keeps more CTAs in flight; otherwise 4 pairs (fewer LDS per eval)
-    if ((long long)H * Q <= 2048LL * c->sm_count)
-        return launch_k3<2>(c, models + 2 * (size_t)begin, H, H_stride, pts, n, thr_sq, counts + begin, Q, arith);
-    return launch_k3<4>(c, models + 2 * (size_t)begin, H, H_stride, pts, n, thr_sq, counts + begin, Q, arith);
+    // measured on B200 at 100k x 100k (profiles/r01b_microbench_k3_variants.jsonl): fast arithmetic is fastest with 4
+    // hypothesis pairs per thread and 512-point tiles (2.57e12/s), exact arithmetic with 2 pairs (1.30e12/s); with few
+    // hypotheses 2 pairs per thread keep more CTAs in flight
+    if (arith == B2R_ARITH_FAST && (long long)H * Q >= 32768)
+        return launch_k3<4>(c, models + 2 * (size_t)begin, H, H_stride, pts, n, thr_sq, counts + begin, Q, arith, 512);
+    return launch_k3<2>(c, models + 2 * (size_t)begin, H, H_stride, pts, n, thr_sq, counts + begin, Q, arith, 1024);
 }
 
 static int problem_reserve(b2r_h_problem* pr, int Q, int n, int H) {

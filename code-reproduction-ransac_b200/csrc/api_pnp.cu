@@ -137,7 +137,7 @@ static int score_p_fast(b2r_ctx* c, const float4* mf, int H, const PointPF* pf, 
     if (H_stride == 0) H_stride = H;
     int rc = zero_counts(c, counts, Q, H, H_stride, begin);
     if (rc) return rc;
-    const bool big = (long long)H * Q > 2048LL * c->sm_count;
+    const bool big = (long long)H * Q >= 32768;   // 2 hypothesis pairs per thread once there are enough hypothesis blocks
     const int per_cta = K3_THREADS * 2 * (big ? 2 : 1);
     const long long hb = (H + per_cta - 1) / per_cta;
     const int tile = pick_tile(c, hb, n, Q, 1024);
