@@ -35,6 +35,10 @@ struct __align__(16) PointH {
 };
 
 constexpr int K3_THREADS = 256;
+#ifndef K3_UNROLL
+#define K3_UNROLL 8
+#endif
+constexpr int K3_POINT_UNROLL = K3_UNROLL;  // points per trip of the inner loop
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -163,7 +167,7 @@ k3_score_h(const float4* __restrict__ models, int H, int H_stride, const PointH*
 
     mbar_wait(bar, 0);
 
-#pragma unroll 2
+#pragma unroll K3_POINT_UNROLL
     for (int p = 0; p < np; ++p) {
         const float4 pt = tile[p];  // broadcast LDS.128
         const f2_t X = f2_dup(pt.x), Y = f2_dup(pt.y), nu = f2_dup(pt.z), nv = f2_dup(pt.w);
