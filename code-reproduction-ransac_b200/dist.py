@@ -103,3 +103,44 @@ def solve_pnp_ransac_sharded(ctx, obj, img, K, thr, total_hypotheses, seed=0, ar
             prob.free()
     ok = infos[0]["status"] == api.OK
     return ok, rvec[0].reshape(3, 1), tvec[0].reshape(3, 1), (inliers[0].reshape(-1, 1) if ok else None), infos[0]
+
+
+# ---- batched calls shard by PROBLEM: no exchange on the data path, one all-gather of the per-problem scores -----------
+def allgather_rows(local_rows, total, group=None, device=None):
+    """All ranks contribute their contiguous block of rows (shard_range order) of a (total, k) float64 table; every rank
+    gets the whole table.  NCCL on `device`, gloo on CPU.  (Q x (score, id), 64 KB at Q = 4096.)"""
+    import torch
+    import torch.distributed as dist
+    local_rows = np.ascontiguousarray(np.asarray(local_rows, dtype=np.float64))
+    k = local_rows.shape[1] if local_rows.ndim == 2 else 1
+    local_rows = local_rows.reshape(-1, k)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        assert len(local_rows) == total
+        return local_rows.copy()
+    world = dist.get_world_size(group)
+    counts = [shard_range(total, r, world)[1] for r in range(world)]
+    pad = max(counts)
+    buf = np.zeros((pad, k))
+    buf[:len(local_rows)] = local_rows
+    t = torch.from_numpy(buf)
+    if device is not None:
+        t = t.to(device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    return np.concatenate([o.cpu().numpy()[:c] for o, c in zip(out, counts)], axis=0)
+
+
+def camera_sweep_sharded(ctx, pos3d, pixels, cams, thr, group=None, device=None, **kw):
+    """find_homographies + arg-min (main_v1.py:254-297, :863-866) with the candidate cameras sharded over the ranks: each
+    rank runs the fused device sweep on its block of candidates; the (err1, err2) rows are all-gathered and every rank
+    takes the same arg-min.  Returns (scores (Q,2), best index)."""
+    import torch.distributed as dist
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_available() and dist.is_initialized() else (0, 1)
+    cams = np.asarray(cams, dtype=np.float64).reshape(-1, 3)
+    Q = len(cams)
+    begin, count = shard_range(Q, rank, world)
+    local = ctx.camera_sweep(pos3d, pixels, cams[begin:begin + count], thr, **kw)["scores"] if count > 0 else np.zeros((0, 2))
+    scores = allgather_rows(local, Q, group=group, device=device)
+    err2 = scores[:, 1].copy()
+    err2[err2 == 0] = 1000000                      # main_v1.py:865
+    return scores, int(np.argmin(err2))

@@ -113,6 +113,11 @@ best = rdist.reduce_keys_max(keys)
 assert int(best[0]) >> 32 == 50 and 0xFFFFFFFF - (int(best[0]) & 0xFFFFFFFF) == 7, best
 assert int(best[1]) >> 32 == 40 and 0xFFFFFFFF - (int(best[1]) & 0xFFFFFFFF) == 2, best
 assert rdist.shard_range(10, rank, 2) == ((0, 5) if rank == 0 else (5, 5))
+# problem-sharded batched calls: every rank contributes its block of per-problem scores, all get the whole table
+table = np.arange(7 * 2, dtype=np.float64).reshape(7, 2) * 1.5
+b, c = rdist.shard_range(7, rank, 2)
+got = rdist.allgather_rows(table[b:b + c], 7)
+assert np.array_equal(got, table), got
 dist.destroy_process_group()
 print("ok", rank)
 """
