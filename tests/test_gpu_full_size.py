@@ -85,3 +85,58 @@ def test_multi_query_batch_properties(ctx):
     np.testing.assert_array_equal(Hs[q], H[q])
     np.testing.assert_array_equal(ms[q], mask[q])
     prob.free()
+
+
+def reference_pnp_inliers(rvec, tvec, K, obj, img, thr):
+    """cv::projectPoints (zero distortion) + PnPRansacCallback::computeError restated with NumPy: float64 projection of
+    the float32-quantised points in OpenCV's operation order, rounded to float32, float32 squared distance."""
+    r = np.asarray(rvec, dtype=np.float64).reshape(3)
+    th = np.sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2])
+    c, s = np.cos(th), np.sin(th)
+    k = r * (1.0 / th)
+    rrt = np.outer(k, k)
+    rcr = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    R = c * np.eye(3) + (1.0 - c) * rrt + s * rcr
+    t = np.asarray(tvec, dtype=np.float64).reshape(3)
+    X, Y, Z = (obj[:, i].astype(np.float32).astype(np.float64) for i in range(3))
+    x = R[0, 0] * X + R[0, 1] * Y + R[0, 2] * Z + t[0]
+    y = R[1, 0] * X + R[1, 1] * Y + R[1, 2] * Z + t[1]
+    z = R[2, 0] * X + R[2, 1] * Y + R[2, 2] * Z + t[2]
+    iz = np.where(z != 0, 1.0 / np.where(z != 0, z, 1.0), 1.0)
+    pu = (x * iz * K[0, 0] + K[0, 2]).astype(np.float32)
+    pv = (y * iz * K[1, 1] + K[1, 2]).astype(np.float32)
+    dx, dy = img[:, 0].astype(np.float32) - pu, img[:, 1].astype(np.float32) - pv
+    return np.nonzero(dx * dx + dy * dy <= np.float32(thr * thr))[0].astype(np.int32)
+
+
+def test_pnp_large_problem_properties(ctx):
+    """The pose model at configs[2] size: 100k points x 100k Philox hypotheses.  The returned inlier list is exactly the
+    reference's projectPoints arithmetic applied to the winning minimal model (recomputed with NumPy float64/float32);
+    sharded = unsharded; fast arithmetic finds the same consensus up to threshold-borderline points."""
+    n, Htot, thr = 100_000, 100_000, 8.0
+    P, px, _ = synth.pnp_set(n, 0.5, np.random.default_rng(1898 + 22))
+    K = synth.K_1898
+    kw = dict(sampler=ransac_b200.SAMPLER_PHILOX, seed=77)
+    prob = ctx.upload_pnp(P, px, K)
+    prob.run(ransac_b200.make_p_params(thr, Htot, 0.99, arith=ransac_b200.ARITH_EXACT, **kw))
+    r0, t0, inl0, i0 = prob.fetch()
+    assert i0[0]["status"] == 0 and len(inl0[0]) > 0.4 * n
+    ref = reference_pnp_inliers(i0[0]["ransac_rvec"], i0[0]["ransac_tvec"], K, P, px, thr)
+    diff = np.setxor1d(ref, inl0[0])
+    assert len(diff) <= 2, len(diff)            # NumPy's cos/sin vs the device's: at most a borderline point or two
+    keys = [prob.score_shard(ransac_b200.make_p_params(thr, Htot // 4, 0.99, arith=ransac_b200.ARITH_EXACT, hyp_begin=r * (Htot // 4), **kw))
+            for r in range(4)]
+    best = np.maximum.reduce(keys)
+    assert int(best[0]) >> 32 == i0[0]["best_count"] and 0xFFFFFFFF - (int(best[0]) & 0xFFFFFFFF) == i0[0]["best_iter"]
+    prob.finish(ransac_b200.make_p_params(thr, Htot // 4, 0.99, arith=ransac_b200.ARITH_EXACT, hyp_begin=0, **kw), best)
+    r1, t1, inl1, i1 = prob.fetch()
+    np.testing.assert_array_equal(inl1[0], inl0[0])
+    np.testing.assert_array_equal(r1, r0)
+    np.testing.assert_array_equal(t1, t0)
+    prob.run(ransac_b200.make_p_params(thr, Htot, 0.99, arith=ransac_b200.ARITH_FAST, **kw))
+    rf, tf, inlf, i_f = prob.fetch()
+    assert abs(i_f[0]["best_count"] - i0[0]["best_count"]) <= 5
+    if i_f[0]["sample"] == i0[0]["sample"]:
+        np.testing.assert_array_equal(inlf[0], inl0[0])      # the returned list always comes from the exact arithmetic
+        assert np.abs(rf - r0).max() / np.abs(r0).max() < 1e-5
+    prob.free()
