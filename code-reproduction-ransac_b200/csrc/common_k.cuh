@@ -175,6 +175,46 @@ __device__ __forceinline__ void cluster_reduce(ClusterRed& R, double (&v)[NV]) {
     __syncthreads();
 }
 
+// Same reduction with the LAST NMAX of the NV values combined by max instead of + (one cluster barrier for a set of
+// sums plus a max-norm).
+template <int THREADS, int NV, int NMAX>
+__device__ __forceinline__ void cluster_reduce_tail_max(ClusterRed& R, double (&v)[NV]) {
+    static_assert(NV <= RED_MAX && NMAX <= NV, "too many values");
+    cg::cluster_group cluster = cg::this_cluster();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_down_sync(0xffffffffu, x, o);
+            x = i >= NV - NMAX ? fmax(x, y) : x + y;
+        }
+        if (lane == 0) R.warp[warp * NV + i] = x;
+    }
+    __syncthreads();
+    const int ph = R.phase;
+    if (threadIdx.x < NV) {
+        const bool is_max = (int)threadIdx.x >= NV - NMAX;
+        double s = R.warp[threadIdx.x];
+        for (int w = 1; w < THREADS / 32; ++w) s = is_max ? fmax(s, R.warp[w * NV + threadIdx.x]) : s + R.warp[w * NV + threadIdx.x];
+        R.part[ph][threadIdx.x] = s;
+    }
+    cluster.sync();
+    if (threadIdx.x < NV) {
+        const bool is_max = (int)threadIdx.x >= NV - NMAX;
+        const unsigned nb = cluster.num_blocks();
+        double s = 0;
+        for (unsigned r = 0; r < nb; ++r) {
+            const double* remote = cluster.map_shared_rank(&R.part[ph][0], r);
+            s = r == 0 ? remote[threadIdx.x] : (is_max ? fmax(s, remote[threadIdx.x]) : s + remote[threadIdx.x]);
+        }
+        R.out[threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) R.phase = ph ^ 1;
+    __syncthreads();
+}
+
 // x = solve(A, b), A symmetric n x n, through its Jacobi eigen-decomposition with OpenCV's
 // back-substitution threshold (cv::solve DECOMP_EIG); optionally the diagonal of A^-1.
 template <int N>

@@ -294,6 +294,7 @@ struct HFinalizeShared {
     double x[9], xd[9];   // LM parameter vectors (all nine entries of H, as OpenCV 4.13 refines them)
     double A[81], v[9], D[9], d[9];
     double Ap[81], diag[9];
+    double Ac[81], vc[9];  // J^T J and J^T r at the trial point (become A, v when the step is accepted)
     double S, Sd, lambda, lc, rmax, nu;
     float Hf[8];
     float ms1[8], ms2[8];
@@ -465,11 +466,12 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
         // Rows of J: Jx = [a, 0, -xi a], Jy = [0, a, -yi a] with a = (X, Y, 1) ww, so
         //   J^T J = [[aa, 0, -xi aa], [0, aa, -yi aa], [., ., (xi^2 + yi^2) aa]],   J^T r = [a rx, a ry, -(xi rx + yi ry) a]:
         // per-thread accumulators  S | aa (6) | xi aa (6) | yi aa (6) | (xi^2+yi^2) aa (6) | a rx (3) | a ry (3) | (xi rx + yi ry) a (3) = 34
-        auto eval = [&](const double* h, bool want_J) -> double2 {
-            double acc[34];
+        // One pass + ONE cluster reduction per evaluation: |r|^2, max |r_i| and the 33 sums of J^T J / J^T r together
+        // (the Jacobian terms of a rejected trial point are simply discarded).  Results: return value (S, rmax), sh.Ac, sh.vc.
+        auto eval = [&](const double* h) -> double2 {
+            double acc[35];
 #pragma unroll
-            for (int j = 0; j < 34; ++j) acc[j] = 0;
-            double rmax[1] = {0};
+            for (int j = 0; j < 35; ++j) acc[j] = 0;
             for (int i = gtid; i < n; i += gstride)
                 if (rmask[i]) {
                     const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
@@ -480,62 +482,59 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     const double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
                     const double rx = xi - (double)(-p.z), ry = yi - (double)(-p.w);
                     acc[0] += rx * rx + ry * ry;
-                    rmax[0] = fmax(rmax[0], fmax(fabs(rx), fabs(ry)));
-                    if (want_J) {
-                        const double a[3] = {Mx * ww, My * ww, ww};
-                        const double aa[6] = {a[0] * a[0], a[0] * a[1], a[0] * a[2], a[1] * a[1], a[1] * a[2], a[2] * a[2]};
-                        const double r2 = xi * xi + yi * yi, rr = xi * rx + yi * ry;
+                    acc[34] = fmax(acc[34], fmax(fabs(rx), fabs(ry)));
+                    const double a[3] = {Mx * ww, My * ww, ww};
+                    const double aa[6] = {a[0] * a[0], a[0] * a[1], a[0] * a[2], a[1] * a[1], a[1] * a[2], a[2] * a[2]};
+                    const double r2 = xi * xi + yi * yi, rr = xi * rx + yi * ry;
 #pragma unroll
-                        for (int u = 0; u < 6; ++u) {
-                            acc[1 + u] += aa[u];
-                            acc[7 + u] += xi * aa[u];
-                            acc[13 + u] += yi * aa[u];
-                            acc[19 + u] += r2 * aa[u];
-                        }
+                    for (int u = 0; u < 6; ++u) {
+                        acc[1 + u] += aa[u];
+                        acc[7 + u] += xi * aa[u];
+                        acc[13 + u] += yi * aa[u];
+                        acc[19 + u] += r2 * aa[u];
+                    }
 #pragma unroll
-                        for (int u = 0; u < 3; ++u) {
-                            acc[25 + u] += a[u] * rx;
-                            acc[28 + u] += a[u] * ry;
-                            acc[31 + u] += a[u] * rr;
-                        }
+                    for (int u = 0; u < 3; ++u) {
+                        acc[25 + u] += a[u] * rx;
+                        acc[28 + u] += a[u] * ry;
+                        acc[31 + u] += a[u] * rr;
                     }
                 }
-            if (want_J) {
-                cluster_reduce<THREADS, 34, false>(R, acc);
-            } else {
-                double a1[1] = {acc[0]};
-                cluster_reduce<THREADS, 1, false>(R, a1);
-            }
-            const double S = R.out[0];
-            if (want_J && tid == 0) {
+            cluster_reduce_tail_max<THREADS, 35, 1>(R, acc);
+            const double S = R.out[0], rmax = R.out[34];
+            if (tid == 0) {
                 const double* o = R.out;
                 const int sym[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
-                for (int j = 0; j < 81; ++j) sh.A[j] = 0;
+                for (int j = 0; j < 81; ++j) sh.Ac[j] = 0;
                 for (int u = 0; u < 3; ++u) {
                     for (int w = 0; w < 3; ++w) {
                         const int e = sym[u][w];
-                        sh.A[u * 9 + w] = o[1 + e];
-                        sh.A[(3 + u) * 9 + 3 + w] = o[1 + e];
-                        sh.A[u * 9 + 6 + w] = sh.A[(6 + w) * 9 + u] = -o[7 + e];
-                        sh.A[(3 + u) * 9 + 6 + w] = sh.A[(6 + w) * 9 + 3 + u] = -o[13 + e];
-                        sh.A[(6 + u) * 9 + 6 + w] = o[19 + e];
+                        sh.Ac[u * 9 + w] = o[1 + e];
+                        sh.Ac[(3 + u) * 9 + 3 + w] = o[1 + e];
+                        sh.Ac[u * 9 + 6 + w] = sh.Ac[(6 + w) * 9 + u] = -o[7 + e];
+                        sh.Ac[(3 + u) * 9 + 6 + w] = sh.Ac[(6 + w) * 9 + 3 + u] = -o[13 + e];
+                        sh.Ac[(6 + u) * 9 + 6 + w] = o[19 + e];
                     }
-                    sh.v[u] = o[25 + u];
-                    sh.v[3 + u] = o[28 + u];
-                    sh.v[6 + u] = -o[31 + u];
+                    sh.vc[u] = o[25 + u];
+                    sh.vc[3 + u] = o[28 + u];
+                    sh.vc[6 + u] = -o[31 + u];
                 }
             }
             __syncthreads();
-            cluster_reduce<THREADS, 1, true>(R, rmax);
-            return make_double2(S, R.out[0]);
+            return make_double2(S, rmax);
+        };
+        auto accept_candidate = [&]() {   // thread 0
+            for (int j = 0; j < 81; ++j) sh.A[j] = sh.Ac[j];
+            for (int j = 0; j < 9; ++j) sh.v[j] = sh.vc[j];
         };
 
         if (tid == 0)
             for (int i = 0; i < 9; ++i) sh.x[i] = sh.H[i];
         __syncthreads();
         {
-            const double2 e0 = eval(sh.x, true);
+            const double2 e0 = eval(sh.x);
             if (tid == 0) {
+                accept_candidate();
                 sh.S = e0.x; sh.rmax = e0.y;
                 for (int i = 0; i < 9; ++i) sh.D[i] = sh.A[i * 9 + i];
                 sh.lambda = 1; sh.lc = 0.75;
@@ -577,7 +576,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
             if (tid == 0)
                 for (int i = 0; i < 9; ++i) sh.xd[i] = sh.x[i] - sh.d[i];
             __syncthreads();
-            const double2 ed = eval(sh.xd, false);
+            const double2 ed = eval(sh.xd);
             if (tid == 0) {
                 const double Sd = ed.x, S = sh.S;
                 sh.Sd = Sd;
@@ -633,16 +632,14 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     sh.lambda *= sh.nu * 0.5;
                 }
                 sh.flag = sh.Sd < sh.S;
-                if (sh.flag) {
+                if (sh.flag) {   // accepted: the trial point's J^T J, J^T r and residual norms become current
                     sh.S = sh.Sd;
+                    sh.rmax = ed.y;
                     for (int i = 0; i < 9; ++i) sh.x[i] = sh.xd[i];
+                    accept_candidate();
                 }
             }
             __syncthreads();
-            if (sh.flag) {
-                const double2 e1 = eval(sh.x, true);
-                if (tid == 0) sh.rmax = e1.y;
-            }
             ++iter;
             if (tid == 0) {
                 double dmax = 0;
