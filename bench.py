@@ -127,9 +127,16 @@ def reference_throughput(src, dst, thr, seconds, threads):
     det = O.find_homography(src, dst, thr, details=True)[2]
     iters = det["iters"]
     call()  # warm
-    t_one = time.perf_counter()
-    call()
-    t_one = time.perf_counter() - t_one
+
+    def one_round():   # every thread makes one call: the per-call time UNDER the concurrency used below (the calls
+        ths = [threading.Thread(target=call) for _ in range(threads)]   # share memory bandwidth and caches)
+        t = time.perf_counter()
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        return time.perf_counter() - t
+    t_one = one_round()
     reps = max(1, int(seconds / max(t_one, 1e-4)))
     reps = min(reps, 2000)
 

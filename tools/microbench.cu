@@ -139,10 +139,11 @@ static void host_counts(const std::vector<float>& models, const std::vector<floa
     }
 }
 
+static int g_extra_smem = 0;
 template <int NPAIR, bool EXACT>
 static void run_k3(const char* name, const float4* d_models, int H, const PointH* d_pts, int N, float thr,
                    int* d_counts, int tile, int reps, std::vector<int>* result) {
-    size_t smem = 128 + (size_t)tile * 16;
+    size_t smem = 128 + (size_t)tile * 16 + (size_t)g_extra_smem;   // g_extra_smem: pad to force fewer resident CTAs per SM (occupancy probe)
     CK(cudaFuncSetAttribute(k3_score_h<NPAIR, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((H + K3_THREADS * 2 * NPAIR - 1) / (K3_THREADS * 2 * NPAIR), (N + tile - 1) / tile);
     cudaEvent_t e0, e1;
@@ -173,6 +174,7 @@ static void run_k3(const char* name, const float4* d_models, int H, const PointH
 }
 
 int main(int argc, char** argv) {
+    g_extra_smem = argc > 3 ? atoi(argv[3]) : 0;
     int H = argc > 1 ? atoi(argv[1]) : 100000;
     int N = argc > 2 ? atoi(argv[2]) : 100000;
     cudaDeviceProp prop;
