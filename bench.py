@@ -348,7 +348,8 @@ def extras(ctx, args, rank, world, device, src, dst):
     pp = ctx.upload_pnp(P, px, synth.K_1898)
     pnp = {}
     for name, arith in (("fast", ransac_b200.ARITH_FAST), ("exact", ransac_b200.ARITH_EXACT)):
-        par = ransac_b200.make_p_params(8.0, H, 0.99, sampler=ransac_b200.SAMPLER_PHILOX, seed=5, arith=arith)
+        par = ransac_b200.make_p_params(8.0, H, 0.99, sampler=ransac_b200.SAMPLER_PHILOX, seed=5, arith=arith,
+                                        solver=ransac_b200.SOLVER_FAST if name == "fast" else ransac_b200.SOLVER_EXACT)
         best = None
         for _ in range(4):
             pp.run(par)

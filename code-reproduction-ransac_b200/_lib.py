@@ -31,7 +31,7 @@ class PParams(C.Structure):
     """b2r_p_params"""
     _fields_ = [("thr", C.c_double), ("max_iters", C.c_int32), ("confidence", C.c_double), ("sampler", C.c_int32),
                 ("seed", C.c_uint64), ("arith", C.c_int32), ("refine", C.c_int32), ("hyp_begin", C.c_int64),
-                ("reserved", C.c_int32 * 2)]
+                ("solver", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PInfo(C.Structure):
@@ -97,7 +97,7 @@ SIGNATURES = {
     "b2r_score_p": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, C.c_int32, c_double_p, C.c_float,
                               C.c_int32, c_i32_p]),
     "b2r_pnp_minimal_models": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, c_double_p, c_i32_p, C.c_int32,
-                                         c_double_p, c_double_p, c_double_p, c_u8_p]),
+                                         C.c_int32, c_double_p, c_double_p, c_double_p, c_u8_p]),
     "b2r_sample_cv_p": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_i32_p]),
 }
 

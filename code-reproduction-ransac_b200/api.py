@@ -129,7 +129,7 @@ class HomographyProblem:
 
 
 def make_p_params(thr=8.0, max_iters=100, confidence=0.99, sampler=SAMPLER_CV_REPLAY, seed=0, arith=ARITH_EXACT,
-                  refine=True, hyp_begin=0):
+                  refine=True, hyp_begin=0, solver=SOLVER_EXACT):
     """b2r_p_params with cv2.solvePnPRansac's defaults (iterationsCount=100, reprojectionError=8.0, confidence=0.99)."""
     p = PParams()
     p.thr = float(thr)
@@ -140,6 +140,7 @@ def make_p_params(thr=8.0, max_iters=100, confidence=0.99, sampler=SAMPLER_CV_RE
     p.arith = int(arith)
     p.refine = 1 if refine else 0
     p.hyp_begin = int(hyp_begin)
+    p.solver = int(solver)
     return p
 
 
@@ -385,8 +386,9 @@ class Context:
                                         _ptr(Kd, C.c_double), C.c_float(np.float32(thr_sq)), int(arith), _ptr(counts, C.c_int32)))
         return counts
 
-    def pnp_minimal_models(self, obj, img, K, idx):
-        """K2 (PnP): EPnP models of the 5-point samples idx (m,5): (rvec (m,3), tvec (m,3), R (m,3,3), ok (m,))."""
+    def pnp_minimal_models(self, obj, img, K, idx, solver=SOLVER_EXACT):
+        """K2 (PnP): minimal models of the 5-point samples idx (m,5): (rvec (m,3), tvec (m,3), R (m,3,3), ok (m,)).
+        solver: SOLVER_EXACT = OpenCV's EPnP restated, SOLVER_FAST = the throughput path's 5-point solver."""
         o, im = _f64(obj, 3), _f64(img, 2)
         Kd = _K9(K)
         idx = np.ascontiguousarray(np.asarray(idx, dtype=np.int32).reshape(-1, 5))
@@ -394,7 +396,7 @@ class Context:
         rvec, tvec, R = np.zeros((m, 3)), np.zeros((m, 3)), np.zeros((m, 3, 3))
         ok = np.zeros(m, dtype=np.uint8)
         self._check(self._L.b2r_pnp_minimal_models(self._c, _ptr(o, C.c_double), _ptr(im, C.c_double), len(o), _ptr(Kd, C.c_double),
-                                                   _ptr(idx, C.c_int32), m, _ptr(rvec, C.c_double), _ptr(tvec, C.c_double),
+                                                   _ptr(idx, C.c_int32), m, int(solver), _ptr(rvec, C.c_double), _ptr(tvec, C.c_double),
                                                    _ptr(R, C.c_double), _ptr(ok, C.c_uint8)))
         return rvec, tvec, R, ok.astype(bool)
 

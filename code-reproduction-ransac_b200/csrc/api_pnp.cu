@@ -39,6 +39,7 @@ static int check_p_params(const b2r_p_params* p) {
     if (!(p->thr >= 0)) return fail(B2R_ERR_ARG, "reprojectionError must be >= 0%s%s");
     if (p->sampler != B2R_SAMPLER_CV_REPLAY && p->sampler != B2R_SAMPLER_PHILOX) return fail(B2R_ERR_ARG, "bad sampler%s%s");
     if (p->arith != B2R_ARITH_EXACT && p->arith != B2R_ARITH_FAST) return fail(B2R_ERR_ARG, "bad arith%s%s");
+    if (p->solver != B2R_SOLVER_EXACT && p->solver != B2R_SOLVER_FAST) return fail(B2R_ERR_ARG, "bad solver%s%s");
     if (p->max_iters > (1 << 30)) return fail(B2R_ERR_ARG, "iterationsCount too large%s%s");
     return B2R_OK;
 }
@@ -170,7 +171,7 @@ static int p_run_score(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p) {
         dim3 grid((unsigned)((H + 63) / 64), (unsigned)Q);
         LAUNCH(c, k_epnp_solve_p, grid, 64, 0, pr->px.as<PointPX>(), pr->pts_stride(), n, H, 0, H, (const RansacState*)nullptr,
                pr->Kq.as<double>(), pr->centre.as<double>(), cstride, 1, (long long)p->hyp_begin, p->seed, pr->samples.as<int>(), mx,
-               mf, (double*)nullptr, (uint8_t*)nullptr);
+               mf, (double*)nullptr, (uint8_t*)nullptr, (int)p->solver);
         CU(cudaGetLastError());
         CU(cudaEventRecord(pr->ev[1], c->stream));
         if (exact) rc = score_p_exact(c, mx, H, pr->px.as<PointPX>(), pr->pts_stride(), n, pr->Kq.as<double>(), thr_sq, pr->counts.as<int>(), Q);
@@ -195,7 +196,7 @@ static int p_run_score(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p) {
         dim3 grid((unsigned)((len + 63) / 64), (unsigned)Q);
         LAUNCH(c, k_epnp_solve_p, grid, 64, 0, pr->px.as<PointPX>(), pr->pts_stride(), n, H, begin, len, (const RansacState*)st,
                pr->Kq.as<double>(), pr->centre.as<double>(), cstride, 0, 0LL, (uint64_t)0, pr->samples.as<int>(), mx, mf,
-               (double*)nullptr, (uint8_t*)nullptr);
+               (double*)nullptr, (uint8_t*)nullptr, (int)p->solver);
         CU(cudaGetLastError());
         if (exact) rc = score_p_exact(c, mx, len, pr->px.as<PointPX>(), pr->pts_stride(), n, pr->Kq.as<double>(), thr_sq, pr->counts.as<int>(), Q, H, begin);
         else rc = score_p_fast(c, mf, len, pr->pf.as<PointPF>(), pr->pts_stride(), n, thr_sq, pr->counts.as<int>(), Q, H, begin);
@@ -266,13 +267,13 @@ static int p_run_finish(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p, co
         rc = launch_cluster(c, k_finalize_p<512>, Q, csize, 512, (const PointPX*)pr->px.as<PointPX>(), pr->pts_stride(),
                             (const double*)pr->raw_obj.as<double>(), (const double*)pr->raw_img.as<double>(), pr->pts_stride(), n,
                             (const int*)pr->samples.as<int>(), Hs, (const HSelect*)pr->sel.as<HSelect>(),
-                            (const double*)pr->Kq.as<double>(), thr_sq, (int)p->refine, (int)(n == PNP_MP), pr->rmask.as<uint8_t>(),
+                            (const double*)pr->Kq.as<double>(), thr_sq, (int)p->refine, (int)(n == PNP_MP), (int)p->solver, pr->rmask.as<uint8_t>(),
                             pr->pose.as<double>(), pr->info_i.as<int>(), pr->info_d.as<double>());
     else
         rc = launch_cluster(c, k_finalize_p<128>, Q, csize, 128, (const PointPX*)pr->px.as<PointPX>(), pr->pts_stride(),
                             (const double*)pr->raw_obj.as<double>(), (const double*)pr->raw_img.as<double>(), pr->pts_stride(), n,
                             (const int*)pr->samples.as<int>(), Hs, (const HSelect*)pr->sel.as<HSelect>(),
-                            (const double*)pr->Kq.as<double>(), thr_sq, (int)p->refine, (int)(n == PNP_MP), pr->rmask.as<uint8_t>(),
+                            (const double*)pr->Kq.as<double>(), thr_sq, (int)p->refine, (int)(n == PNP_MP), (int)p->solver, pr->rmask.as<uint8_t>(),
                             pr->pose.as<double>(), pr->info_i.as<int>(), pr->info_d.as<double>());
     if (rc) return rc;
     LAUNCH(c, k_compact_inliers, (unsigned)Q, 1024, 0, pr->rmask.as<uint8_t>(), n, pr->inliers.as<int>(), pr->ninl.as<int>());
@@ -527,7 +528,7 @@ int b2r_score_p(b2r_ctx* c, const double* models_Rt, int32_t n_models, const dou
 }
 
 int b2r_pnp_minimal_models(b2r_ctx* c, const double* obj, const double* img, int32_t n, const double* K, const int32_t* idx,
-                           int32_t n_samples, double* rvec_out, double* tvec_out, double* R_out, uint8_t* ok_out) {
+                           int32_t n_samples, int32_t solver, double* rvec_out, double* tvec_out, double* R_out, uint8_t* ok_out) {
     if (!c || !obj || !img || !K || !idx || n < 5 || n_samples < 1) return fail(B2R_ERR_ARG, "bad argument%s%s");
     for (size_t i = 0; i < (size_t)n_samples * PNP_MP; ++i)
         if (idx[i] < 0 || idx[i] >= n) return fail(B2R_ERR_ARG, "sample index out of range%s%s");
@@ -543,7 +544,7 @@ int b2r_pnp_minimal_models(b2r_ctx* c, const double* obj, const double* img, int
     double* rt = mx + 12 * (size_t)n_samples;
     LAUNCH(c, k_epnp_solve_p, dim3((unsigned)((n_samples + 63) / 64), 1), 64, 0, pr->px.as<PointPX>(), (size_t)0, n, n_samples, 0,
            n_samples, (const RansacState*)nullptr, pr->Kq.as<double>(), pr->centre.as<double>(), (size_t)0, 0, 0LL, (uint64_t)0,
-           c->scratch1.as<int>(), mx, (float4*)nullptr, rt, c->scratch3.as<uint8_t>());
+           c->scratch1.as<int>(), mx, (float4*)nullptr, rt, c->scratch3.as<uint8_t>(), (int)(solver == B2R_SOLVER_FAST));
     CU(cudaGetLastError());
     std::vector<double> h(18 * (size_t)n_samples);
     CU(cudaMemcpyAsync(h.data(), mx, sizeof(double) * 18 * (size_t)n_samples, cudaMemcpyDeviceToHost, c->stream));

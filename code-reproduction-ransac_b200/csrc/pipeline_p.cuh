@@ -147,12 +147,15 @@ __device__ __forceinline__ void store_fast_model(float4* __restrict__ mf, size_t
 //   mx      : [Q][H][12] fp64  R(rvec) | tvec   (what cv::projectPoints evaluates), NaN = no model      (optional)
 //   mf      : [Q][H][3] float4 rows of the fast model                                                     (optional)
 //   rt      : [Q][H][6] fp64 rvec | tvec, zeros when there is no model                                    (optional)
-__global__ void __launch_bounds__(64)
+#ifndef K2P_MIN_BLOCKS
+#define K2P_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(64, K2P_MIN_BLOCKS)
 k_epnp_solve_p(const PointPX* __restrict__ pts, size_t pts_q_stride, int n, int H, int begin, int len,
                const RansacState* __restrict__ state, const double* __restrict__ Kq,
                const double* __restrict__ centre, size_t centre_q_stride, int sampler_philox, long long hyp_begin,
                uint64_t seed, int* __restrict__ samples, double* __restrict__ mx, float4* __restrict__ mf,
-               double* __restrict__ rt, uint8_t* __restrict__ ok_out) {
+               double* __restrict__ rt, uint8_t* __restrict__ ok_out, int fast_solver) {
     const int q = blockIdx.y;
     if ((int)(blockIdx.x * blockDim.x + threadIdx.x) >= len) return;
     const int g = begin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -173,7 +176,8 @@ k_epnp_solve_p(const PointPX* __restrict__ pts, size_t pts_q_stride, int n, int 
     bool ok = state == nullptr || g < state[q].gen;
     if (ok) {
         gather5(P, idx, obj5, img5);
-        ok = pnp_minimal_model(obj5, img5, K4[0], K4[1], K4[2], K4[3], rvec, tvec);
+        ok = fast_solver ? pnp_minimal_model_fast(obj5, img5, K4[0], K4[1], K4[2], K4[3], rvec, tvec)
+                         : pnp_minimal_model(obj5, img5, K4[0], K4[1], K4[2], K4[3], rvec, tvec);
     }
     if (ok) rodrigues_vec2mat(rvec, R);
     if (mx) {
@@ -499,7 +503,7 @@ __global__ void __launch_bounds__(THREADS)
 k_finalize_p(const PointPX* __restrict__ pts, size_t pts_q_stride, const double* __restrict__ obj_raw,
              const double* __restrict__ img_raw, size_t raw_q_stride, int n, const int* __restrict__ samples, int Hs,
              const HSelect* __restrict__ sel, const double* __restrict__ Kq, float thr_sq, int refine, int all_inliers,
-             uint8_t* __restrict__ rmask_out, double* __restrict__ pose_out, int* __restrict__ info_i,
+             int fast_solver, uint8_t* __restrict__ rmask_out, double* __restrict__ pose_out, int* __restrict__ info_i,
              double* __restrict__ info_d) {
     __shared__ PnpLsqShared sh;
     __shared__ ClusterRed R;
@@ -525,7 +529,8 @@ k_finalize_p(const PointPX* __restrict__ pts, size_t pts_q_stride, const double*
             double obj5[15], img5[10];
             for (int i = 0; i < PNP_MP; ++i) smp[i] = samples[((size_t)q * Hs + s.best) * PNP_MP + i];
             gather5(P, smp, obj5, img5);
-            have_model = pnp_minimal_model(obj5, img5, K4[0], K4[1], K4[2], K4[3], model, model + 3) ? 1 : 0;
+            have_model = (fast_solver ? pnp_minimal_model_fast(obj5, img5, K4[0], K4[1], K4[2], K4[3], model, model + 3)
+                                      : pnp_minimal_model(obj5, img5, K4[0], K4[1], K4[2], K4[3], model, model + 3)) ? 1 : 0;
         }
     }
     __syncthreads();

@@ -183,7 +183,10 @@ typedef struct {
     int32_t refine;      /* 1: pose = LM (CvLevMarq, as solvePnP(ITERATIVE, useExtrinsicGuess)) on the inliers seeded
                             with the best RANSAC model, as cv2 does; 0: return the best RANSAC model                 */
     int64_t hyp_begin;   /* hypothesis-id shard of this rank (PHILOX only)                                            */
-    int32_t reserved[2];
+    int32_t solver;      /* B2R_SOLVER_EXACT: OpenCV's EPnP on the five points, restated operation for operation (the
+                            hypotheses cv2 scores); B2R_SOLVER_FAST: depth-parametrised 5-point solver + 3 Gauss-Newton
+                            steps, in registers (throughput path; its hypotheses are not OpenCV's)                      */
+    int32_t reserved;
 } b2r_p_params;
 
 typedef struct {
@@ -241,10 +244,10 @@ int b2r_p_problem_stage_ms(b2r_ctx* ctx, b2r_p_problem* prob, float ms_out[5]);
 int b2r_score_p(b2r_ctx* ctx, const double* models_Rt, int32_t n_models, const double* obj_host, const double* img_host,
                 int32_t n, const double* K, float thr_sq, int32_t arith, int32_t* counts_out);
 /* K2: EPnP minimal models of 5-point samples idx (n_samples,5).  Outputs (any may be NULL): rvec (n_samples,3), tvec
- * (n_samples,3), R = Rodrigues(rvec) (n_samples,9), ok (n_samples). */
+ * (n_samples,3), R = Rodrigues(rvec) (n_samples,9), ok (n_samples).  solver: B2R_SOLVER_EXACT / B2R_SOLVER_FAST. */
 int b2r_pnp_minimal_models(b2r_ctx* ctx, const double* obj_host, const double* img_host, int32_t n, const double* K,
-                           const int32_t* idx_host, int32_t n_samples, double* rvec_out, double* tvec_out, double* R_out,
-                           uint8_t* ok_out);
+                           const int32_t* idx_host, int32_t n_samples, int32_t solver, double* rvec_out, double* tvec_out,
+                           double* R_out, uint8_t* ok_out);
 /* K1: the first n_iters 5-point subsets OpenCV's RANSAC draws for n points.  idx_out (n_iters,5). */
 int b2r_sample_cv_p(b2r_ctx* ctx, int32_t n, int32_t n_iters, int32_t* idx_out);
 

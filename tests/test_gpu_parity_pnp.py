@@ -267,3 +267,32 @@ def test_philox_partition_invariance_and_fast_vs_exact(ctx):
     assert okf and abs(i_f["best_count"] - i0["best_count"]) <= 3
     if i_f["sample"] == i0["sample"]:
         assert relerr(rf, r0) < REL_POSE_TOL and relerr(tf, t0) < REL_POSE_TOL
+
+
+def test_fast_minimal_solver(ctx):
+    """B2R_SOLVER_FAST (depth-parametrised 5-point solver + Gauss-Newton, the throughput path): exact on noise-free
+    samples; in a Philox RANSAC on noisy data it finds the same consensus as the EPnP-based run up to a few points."""
+    R0, t0 = synth.look_at_pose()
+    rng = np.random.default_rng(80)
+    P, px, _ = synth.pnp_set(400, 0.0, rng, noise_px=0.0)
+    # local coordinates: OpenCV's float32 input quantisation moves raw UTM coordinates by up to 0.25 m (there is then no
+    # exact pose); relative to the corner of the landmark box it moves them by 3e-5 m
+    P = P - synth.BOX_LO
+    t0 = t0 + R0 @ synth.BOX_LO
+    idx = np.stack([rng.choice(400, 5, replace=False) for _ in range(500)]).astype(np.int32)
+    rvec, tvec, R, ok = ctx.pnp_minimal_models(P, px, K, idx, solver=ransac_b200.SOLVER_FAST)
+    assert ok.mean() > 0.99
+    errR = np.abs(R[ok] - R0).max(axis=(1, 2))
+    errt = np.abs(tvec[ok] - t0).max(axis=1) / np.abs(t0).max()
+    assert np.median(errR) < 1e-6 and np.median(errt) < 1e-6 and np.percentile(errR, 95) < 1e-4
+    P, px, _ = synth.pnp_set(5000, 0.5, rng)
+    kw = dict(sampler=ransac_b200.SAMPLER_PHILOX, seed=5, arith=ransac_b200.ARITH_FAST)
+    ok_e, r_e, t_e, inl_e, i_e = ctx.solve_pnp_ransac(P, px, K, 8192, 8.0, 0.99, solver=ransac_b200.SOLVER_EXACT, **kw)
+    ok_f, r_f, t_f, inl_f, i_f = ctx.solve_pnp_ransac(P, px, K, 8192, 8.0, 0.99, solver=ransac_b200.SOLVER_FAST, **kw)
+    assert ok_e and ok_f
+    assert abs(len(inl_f) - len(inl_e)) <= 0.02 * len(inl_e)
+    # both poses are early-stopped LM refinements (OpenCV's criterion fires after ~2 iterations on UTM-scale translations)
+    # of different minimal models on nearly the same inliers: compare the camera centres (the scene is ~600 m away)
+    o_e = -pipeline.rodrigues(r_e).T @ t_e.ravel()
+    o_f = -pipeline.rodrigues(r_f).T @ t_f.ravel()
+    assert np.linalg.norm(o_e - synth.CAMERA_ORIGIN) < 10.0 and np.linalg.norm(o_f - synth.CAMERA_ORIGIN) < 10.0

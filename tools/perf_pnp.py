@@ -14,7 +14,8 @@ P, px, _ = synth.pnp_set(N, 0.5, rng)
 ctx = ransac_b200.Context(0)
 prob = ctx.upload_pnp(P, px, synth.K_1898)
 for arith, name in ((ransac_b200.ARITH_FAST, "fast"), (ransac_b200.ARITH_EXACT, "exact")):
-    p = ransac_b200.make_p_params(8.0, H, 0.99, sampler=ransac_b200.SAMPLER_PHILOX, seed=3, arith=arith)
+    p = ransac_b200.make_p_params(8.0, H, 0.99, sampler=ransac_b200.SAMPLER_PHILOX, seed=3, arith=arith,
+                                  solver=ransac_b200.SOLVER_FAST if arith == ransac_b200.ARITH_FAST else ransac_b200.SOLVER_EXACT)
     best = None
     for rep in range(4):
         prob.run(p)
