@@ -13,6 +13,8 @@ struct b2r_p_problem {
     DevBuf Kq;                // [Q][4] fx, fy, cx, cy
     DevBuf samples;           // [Q][H][5] int32
     DevBuf mx, mf;            // [Q][H][12] fp64 / fp32 models
+    DevBuf rt;                // [Q][H][6] rvec | tvec of every hypothesis (replay path: the finalize kernel reads the winner's)
+    bool rt_valid = false;
     DevBuf counts, state, keys, sel;   // state: [Q] RansacState + one int32 "not done" counter
     DevBuf rmask, pose, info_i, info_d, inliers, ninl;
     int H_last = 0;
@@ -20,7 +22,7 @@ struct b2r_p_problem {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     void release() {
         raw_obj.release(); raw_img.release(); px.release(); pf.release(); centre.release(); Kq.release();
-        samples.release(); mx.release(); mf.release(); counts.release(); state.release(); keys.release(); sel.release();
+        samples.release(); mx.release(); mf.release(); rt.release(); counts.release(); state.release(); keys.release(); sel.release();
         rmask.release(); pose.release(); info_i.release(); info_d.release(); inliers.release(); ninl.release();
         for (auto& e : ev)
             if (e) cudaEventDestroy(e), e = nullptr;
@@ -167,6 +169,7 @@ static int p_run_score(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p) {
     double* mx = exact ? pr->mx.as<double>() : nullptr;
     float4* mf = exact ? nullptr : pr->mf.as<float4>();
     CU(cudaEventRecord(pr->ev[0], c->stream));
+    pr->rt_valid = false;
     if (philox) {
         dim3 grid((unsigned)((H + 63) / 64), (unsigned)Q);
         LAUNCH(c, k_epnp_solve_p, grid, 64, 0, pr->px.as<PointPX>(), pr->pts_stride(), n, H, 0, H, (const RansacState*)nullptr,
@@ -188,6 +191,8 @@ static int p_run_score(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p) {
     }
     RansacState* st = pr->state.as<RansacState>();
     int* not_done = reinterpret_cast<int*>(st + Q);
+    CU(pr->rt.reserve(sizeof(double) * 6 * (size_t)Q * H));
+    pr->rt_valid = true;
     LAUNCH(c, k_state_init, (unsigned)((Q + 127) / 128), 128, 0, st, n == PNP_MP ? 1 : (int)p->max_iters, Q);
     for (int begin = 0, len = 256; begin < H; begin += len, len *= 2) {
         if (len > H - begin) len = H - begin;
@@ -196,7 +201,7 @@ static int p_run_score(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p) {
         dim3 grid((unsigned)((len + 63) / 64), (unsigned)Q);
         LAUNCH(c, k_epnp_solve_p, grid, 64, 0, pr->px.as<PointPX>(), pr->pts_stride(), n, H, begin, len, (const RansacState*)st,
                pr->Kq.as<double>(), pr->centre.as<double>(), cstride, 0, 0LL, (uint64_t)0, pr->samples.as<int>(), mx, mf,
-               (double*)nullptr, (uint8_t*)nullptr, (int)p->solver);
+               pr->rt.as<double>(), (uint8_t*)nullptr, (int)p->solver);
         CU(cudaGetLastError());
         if (exact) rc = score_p_exact(c, mx, len, pr->px.as<PointPX>(), pr->pts_stride(), n, pr->Kq.as<double>(), thr_sq, pr->counts.as<int>(), Q, H, begin);
         else rc = score_p_fast(c, mf, len, pr->pf.as<PointPF>(), pr->pts_stride(), n, thr_sq, pr->counts.as<int>(), Q, H, begin);
@@ -267,13 +272,15 @@ static int p_run_finish(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p, co
         rc = launch_cluster(c, k_finalize_p<512>, Q, csize, 512, (const PointPX*)pr->px.as<PointPX>(), pr->pts_stride(),
                             (const double*)pr->raw_obj.as<double>(), (const double*)pr->raw_img.as<double>(), pr->pts_stride(), n,
                             (const int*)pr->samples.as<int>(), Hs, (const HSelect*)pr->sel.as<HSelect>(),
-                            (const double*)pr->Kq.as<double>(), thr_sq, (int)p->refine, (int)(n == PNP_MP), (int)p->solver, pr->rmask.as<uint8_t>(),
+                            (const double*)pr->Kq.as<double>(), thr_sq, (int)p->refine, (int)(n == PNP_MP), (int)p->solver,
+                            (const double*)(pr->rt_valid && !keys_host ? pr->rt.as<double>() : nullptr), pr->rmask.as<uint8_t>(),
                             pr->pose.as<double>(), pr->info_i.as<int>(), pr->info_d.as<double>());
     else
         rc = launch_cluster(c, k_finalize_p<128>, Q, csize, 128, (const PointPX*)pr->px.as<PointPX>(), pr->pts_stride(),
                             (const double*)pr->raw_obj.as<double>(), (const double*)pr->raw_img.as<double>(), pr->pts_stride(), n,
                             (const int*)pr->samples.as<int>(), Hs, (const HSelect*)pr->sel.as<HSelect>(),
-                            (const double*)pr->Kq.as<double>(), thr_sq, (int)p->refine, (int)(n == PNP_MP), (int)p->solver, pr->rmask.as<uint8_t>(),
+                            (const double*)pr->Kq.as<double>(), thr_sq, (int)p->refine, (int)(n == PNP_MP), (int)p->solver,
+                            (const double*)(pr->rt_valid && !keys_host ? pr->rt.as<double>() : nullptr), pr->rmask.as<uint8_t>(),
                             pr->pose.as<double>(), pr->info_i.as<int>(), pr->info_d.as<double>());
     if (rc) return rc;
     LAUNCH(c, k_compact_inliers, (unsigned)Q, 1024, 0, pr->rmask.as<uint8_t>(), n, pr->inliers.as<int>(), pr->ninl.as<int>());

@@ -244,9 +244,9 @@ struct PnpLsqShared {
     double pose[1][12];   // R | t of the pose being evaluated
     double dR[27];        // dR/dr_i, i = 0..2 (row-major 3x3 each)
     double p[6], prev[6], step[6], trial[6];
-    double A[36], g[6], D[6];
-    double S, Sd, lambda, lc, rmax;
-    int flag, iters, lg;
+    double A[36], g[6], D[6], Ap[36], diag[6];
+    double S, Sd, lambda, lc, rmax, nu;
+    int flag, iters, lg, need_diag;
 };
 
 __device__ __forceinline__ void pnp_residual(const double* Rt, const double* K4, double X, double Y, double Z, double u,
@@ -423,8 +423,8 @@ __device__ void pnp_refine_cvlevmarq(ClusterRed& R, PnpLsqShared& sh, const PnpP
 // cv2.solvePnPRefineLM (main_v1.py:508): the classic cv::LMSolver on the 6 pose parameters, max_iters (20) iterations,
 // eps FLT_EPSILON — the same driver as the homography refinement in pipeline_h.cuh, with cv::solve(DECOMP_EIG).
 template <int THREADS>
-__device__ void pnp_refine_lm(ClusterRed& R, PnpLsqShared& sh, const PnpPts& pts, const double* K4, int gtid, int gstride,
-                              int max_iters) {
+__device__ void pnp_refine_lm(ClusterRed& R, PnpLsqShared& sh, JacobiWarp9& jw, const PnpPts& pts, const double* K4, int gtid,
+                              int gstride, int max_iters) {
     double rmax;
     const double S0 = pnp_normal_eq<THREADS>(R, sh, sh.p, pts, K4, gtid, gstride, &rmax);
     if (threadIdx.x == 0) {
@@ -434,16 +434,20 @@ __device__ void pnp_refine_lm(ClusterRed& R, PnpLsqShared& sh, const PnpPts& pts
     __syncthreads();
     for (;;) {
         if (threadIdx.x == 0) {
-            double Ap[36], d[6];
-            for (int i = 0; i < 36; ++i) Ap[i] = sh.A[i];
-            for (int i = 0; i < 6; ++i) Ap[i * 6 + i] += sh.lambda * sh.D[i];
-            solve_sym_eig<6>(Ap, sh.g, d, nullptr);
-            for (int i = 0; i < 6; ++i) { sh.step[i] = d[i]; sh.trial[i] = sh.p[i] - d[i]; }
+            for (int i = 0; i < 36; ++i) sh.Ap[i] = sh.A[i];
+            for (int i = 0; i < 6; ++i) sh.Ap[i * 6 + i] += sh.lambda * sh.D[i];
         }
+        __syncthreads();
+        if (threadIdx.x < 32) solve_sym_eig_warp<6>(jw, sh.Ap, sh.g, sh.step, nullptr);   // cv::solve(..., DECOMP_EIG), warp 0
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int i = 0; i < 6; ++i) sh.trial[i] = sh.p[i] - sh.step[i];
         __syncthreads();
         const double Sd = pnp_cost<THREADS>(R, sh, sh.trial, pts, K4, gtid, gstride, nullptr);
         if (threadIdx.x == 0) {
             const double S = sh.S;
+            sh.Sd = Sd;
+            sh.need_diag = 0;
             double dS = 0;
             for (int i = 0; i < 6; ++i) {
                 double s = 0;
@@ -459,16 +463,22 @@ __device__ void pnp_refine_lm(ClusterRed& R, PnpLsqShared& sh, const PnpPts& pts
                 for (int i = 0; i < 6; ++i) t += sh.step[i] * sh.g[i];
                 double nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1) + 2;
                 nu = fmin(fmax(nu, 2.), 10.);
-                if (sh.lambda == 0) {
-                    double diag[6], maxval = DBL_EPSILON;
-                    solve_sym_eig<6>(sh.A, nullptr, nullptr, diag);
-                    for (int i = 0; i < 6; ++i) maxval = fmax(maxval, fabs(diag[i]));
-                    sh.lambda = sh.lc = 1. / maxval;
-                    nu *= 0.5;
-                }
-                sh.lambda *= nu;
+                sh.nu = nu;
+                if (sh.lambda == 0) sh.need_diag = 1;
+                else sh.lambda *= nu;
             }
-            sh.flag = Sd < S;
+        }
+        __syncthreads();
+        if (sh.need_diag && threadIdx.x < 32) solve_sym_eig_warp<6>(jw, sh.A, nullptr, nullptr, sh.diag);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (sh.need_diag) {
+                double maxval = DBL_EPSILON;
+                for (int i = 0; i < 6; ++i) maxval = fmax(maxval, fabs(sh.diag[i]));
+                sh.lambda = sh.lc = 1. / maxval;
+                sh.lambda *= sh.nu * 0.5;
+            }
+            sh.flag = sh.Sd < sh.S;
             if (sh.flag)
                 for (int i = 0; i < 6; ++i) sh.p[i] = sh.trial[i];
         }
@@ -492,6 +502,8 @@ __device__ void pnp_refine_lm(ClusterRed& R, PnpLsqShared& sh, const PnpPts& pts
 // ---- K4 finalize ------------------------------------------------------------------------------------------------
 // One thread-block cluster per problem.
 //   sel/samples : selection result and minimal samples ([Q][Hs][5], index sel.best)
+//   rt          : [Q][Hs][6] minimal models the solve kernel stored (replay path), or null: the winner's model is then
+//                 re-derived from its sample (hypothesis-sharded runs: the winner may come from another rank)
 //   all_inliers : n == 5 — OpenCV then returns solvePnP(EPNP) of the five points as it is: every point an inlier, no
 //                 threshold test, no refinement (probed against the binary)
 //   rmask       : [Q][n] RANSAC-stage inlier mask (what solvePnPRansac's `inliers` lists)
@@ -503,7 +515,7 @@ __global__ void __launch_bounds__(THREADS)
 k_finalize_p(const PointPX* __restrict__ pts, size_t pts_q_stride, const double* __restrict__ obj_raw,
              const double* __restrict__ img_raw, size_t raw_q_stride, int n, const int* __restrict__ samples, int Hs,
              const HSelect* __restrict__ sel, const double* __restrict__ Kq, float thr_sq, int refine, int all_inliers,
-             int fast_solver, uint8_t* __restrict__ rmask_out, double* __restrict__ pose_out, int* __restrict__ info_i,
+             int fast_solver, const double* __restrict__ rt, uint8_t* __restrict__ rmask_out, double* __restrict__ pose_out, int* __restrict__ info_i,
              double* __restrict__ info_d) {
     __shared__ PnpLsqShared sh;
     __shared__ ClusterRed R;
@@ -528,9 +540,15 @@ k_finalize_p(const PointPX* __restrict__ pts, size_t pts_q_stride, const double*
         if (s.best >= 0) {
             double obj5[15], img5[10];
             for (int i = 0; i < PNP_MP; ++i) smp[i] = samples[((size_t)q * Hs + s.best) * PNP_MP + i];
+            if (rt) {
+                const double* m = rt + ((size_t)q * Hs + s.best) * 6;
+                for (int i = 0; i < 6; ++i) model[i] = m[i];
+                have_model = 1;
+            } else {
             gather5(P, smp, obj5, img5);
             have_model = (fast_solver ? pnp_minimal_model_fast(obj5, img5, K4[0], K4[1], K4[2], K4[3], model, model + 3)
                                       : pnp_minimal_model(obj5, img5, K4[0], K4[1], K4[2], K4[3], model, model + 3)) ? 1 : 0;
+            }
         }
     }
     __syncthreads();
@@ -611,6 +629,7 @@ k_refine_lm_p(const double* __restrict__ obj, const double* __restrict__ img, in
               int max_iters, double* __restrict__ pose_io, int* __restrict__ iters_out) {
     __shared__ PnpLsqShared sh;
     __shared__ ClusterRed R;
+    __shared__ JacobiWarp9 jw;
     __shared__ double K4[4];
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned csize = cluster.num_blocks(), crank = cluster.block_rank();
@@ -621,7 +640,7 @@ k_refine_lm_p(const double* __restrict__ obj, const double* __restrict__ img, in
     __syncthreads();
     PnpPts ps;
     ps.px = nullptr; ps.mask = nullptr; ps.obj = obj; ps.img = img; ps.n = n;
-    pnp_refine_lm<THREADS>(R, sh, ps, K4, gtid, gstride, max_iters);
+    pnp_refine_lm<THREADS>(R, sh, jw, ps, K4, gtid, gstride, max_iters);
     __syncthreads();
     if (crank == 0 && tid < 6) pose_io[tid] = sh.p[tid];
     if (crank == 0 && tid == 0) iters_out[0] = sh.iters;
