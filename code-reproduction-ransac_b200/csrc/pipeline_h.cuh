@@ -308,7 +308,7 @@ struct HFinalizeShared {
 //   H_out      : [Q][9], mask_out : [Q][n], info : [Q] (b2r_h_info layout = 12 int32)
 //   ext_mask/ext_H : refine-only entry (b2r_refine_h): caller-supplied inlier mask and initial model
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 1)   // small problems come in batches: keep 4 CTAs per SM resident
 k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samples, int Hs,
              const HSelect* __restrict__ sel, float thr_sq, int mask_semantics, int refine, int fast_solver,
              double* __restrict__ H_out, uint8_t* __restrict__ mask_out, uint8_t* __restrict__ rmask_out,

@@ -511,7 +511,7 @@ __device__ void pnp_refine_lm(ClusterRed& R, PnpLsqShared& sh, JacobiWarp9& jw, 
 //   info_i      : [Q][12] int32, info_d : [Q][8] fp64 = RANSAC model rvec|tvec, mean inlier reprojection error of the
 //                 returned pose on the caller's un-quantised points (testpro-K.py:32-36, 80-82), final |r|^2
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 1)
 k_finalize_p(const PointPX* __restrict__ pts, size_t pts_q_stride, const double* __restrict__ obj_raw,
              const double* __restrict__ img_raw, size_t raw_q_stride, int n, const int* __restrict__ samples, int Hs,
              const HSelect* __restrict__ sel, const double* __restrict__ Kq, float thr_sq, int refine, int all_inliers,
