@@ -103,7 +103,7 @@ void b2r_ctx_destroy(b2r_ctx* c) {
     }
     b2r_p_problem_destroy(c->cached_p);
     c->in_a.release(); c->in_b.release(); c->scratch0.release(); c->scratch1.release(); c->scratch2.release();
-    c->scratch3.release(); c->pin_in.release(); c->pin_out.release();
+    c->scratch3.release(); c->gscratch.release(); c->pin_in.release(); c->pin_out.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -335,10 +335,31 @@ __global__ void k_resample_winner(const PointH* __restrict__ pts, int n, const u
     sel[q] = s;
 }
 
-// K4 launch: one thread-block cluster per problem (8 x 1024 threads for large n), one CTA for small problems.
+// K4 launch: one thread-block cluster per problem (8 x 1024 threads for large n), one CTA for small problems; a single
+// large problem runs on a cooperative grid over all SMs instead (reductions through global memory + grid barriers).
 static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samples, int Hs, const HSelect* sel, float thr_sq,
                            int mask_semantics, int refine, int solver, double* H_out, uint8_t* mask_out, uint8_t* rmask_out,
                            int* info, const uint8_t* ext_mask, const double* ext_H, int Q) {
+    if (Q == 1 && n >= 32768) {
+        constexpr int GT = 512;
+        static thread_local int coop_ctas[16] = {0};
+        int& ctas = coop_ctas[c->device & 15];
+        if (ctas == 0) {
+            int per_sm = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finalize_h<GT, true>, GT, 0));
+            ctas = per_sm >= 1 ? c->sm_count : -1;
+        }
+        if (ctas > 0) {
+            CU(c->gscratch.reserve(sizeof(double) * 2 * (size_t)ctas * RED_MAX));
+            double* gs = c->gscratch.as<double>();
+            void* args[] = {(void*)&pts, (void*)&n, (void*)&samples, (void*)&Hs, (void*)&sel, (void*)&thr_sq, (void*)&mask_semantics,
+                            (void*)&refine, (void*)&solver, (void*)&H_out, (void*)&mask_out, (void*)&rmask_out, (void*)&info,
+                            (void*)&ext_mask, (void*)&ext_H, (void*)&gs};
+            CU(cudaLaunchCooperativeKernel((const void*)k_finalize_h<GT, true>, dim3((unsigned)ctas), dim3(GT), args, 0, c->stream));
+            c->launches++;
+            return B2R_OK;
+        }
+    }
     const int threads = n >= 2048 ? 1024 : 128;
     const int csize = n >= 32768 ? 8 : (n >= 8192 ? 2 : 1);
     cudaLaunchConfig_t cfg = {};
@@ -353,12 +374,13 @@ static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samp
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    double* no_scratch = nullptr;
     if (threads == 1024)
-        CU(cudaLaunchKernelEx(&cfg, k_finalize_h<1024>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
-                              mask_out, rmask_out, info, ext_mask, ext_H));
+        CU(cudaLaunchKernelEx(&cfg, k_finalize_h<1024, false>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
+                              mask_out, rmask_out, info, ext_mask, ext_H, no_scratch));
     else
-        CU(cudaLaunchKernelEx(&cfg, k_finalize_h<128>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
-                              mask_out, rmask_out, info, ext_mask, ext_H));
+        CU(cudaLaunchKernelEx(&cfg, k_finalize_h<128, false>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
+                              mask_out, rmask_out, info, ext_mask, ext_H, no_scratch));
     c->launches++;
     return B2R_OK;
 }

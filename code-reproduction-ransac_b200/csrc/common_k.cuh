@@ -215,6 +215,48 @@ __device__ __forceinline__ void cluster_reduce_tail_max(ClusterRed& R, double (&
     __syncthreads();
 }
 
+// The same deterministic all-to-all reduction over a whole cooperative GRID (one big problem on all SMs): every CTA
+// publishes its partials in global memory, one grid barrier, every CTA sums all partials in CTA order.  gscratch holds
+// 2 x gridDim.x x RED_MAX doubles (double-buffered like ClusterRed::part).  The LAST NMAX values are combined by max.
+template <int THREADS, int NV, int NMAX>
+__device__ __forceinline__ void grid_reduce_tail_max(ClusterRed& R, double (&v)[NV], double* __restrict__ gscratch) {
+    static_assert(NV <= RED_MAX && NMAX <= NV, "too many values");
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_down_sync(0xffffffffu, x, o);
+            x = i >= NV - NMAX ? fmax(x, y) : x + y;
+        }
+        if (lane == 0) R.warp[warp * NV + i] = x;
+    }
+    __syncthreads();
+    const int ph = R.phase;
+    double* buf = gscratch + (size_t)ph * gridDim.x * RED_MAX;
+    if (threadIdx.x < NV) {
+        const bool is_max = (int)threadIdx.x >= NV - NMAX;
+        double s = R.warp[threadIdx.x];
+        for (int w = 1; w < THREADS / 32; ++w) s = is_max ? fmax(s, R.warp[w * NV + threadIdx.x]) : s + R.warp[w * NV + threadIdx.x];
+        buf[(size_t)blockIdx.x * RED_MAX + threadIdx.x] = s;
+    }
+    __threadfence();
+    grid.sync();
+    if (threadIdx.x < NV) {
+        const bool is_max = (int)threadIdx.x >= NV - NMAX;
+        double s = 0;
+        for (unsigned r = 0; r < gridDim.x; ++r) {
+            const double x = __ldcg(buf + (size_t)r * RED_MAX + threadIdx.x);
+            s = r == 0 ? x : (is_max ? fmax(s, x) : s + x);
+        }
+        R.out[threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) R.phase = ph ^ 1;
+    __syncthreads();
+}
+
 // x = solve(A, b), A symmetric n x n, through its Jacobi eigen-decomposition with OpenCV's
 // back-substitution threshold (cv::solve DECOMP_EIG); optionally the diagonal of A^-1.
 template <int N>

@@ -73,6 +73,7 @@ struct b2r_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     DevBuf in_a, in_b, scratch0, scratch1, scratch2, scratch3;  // staging for the host-pointer entry points
+    DevBuf gscratch;  // partial sums of the grid-wide finalize reductions (2 x CTAs x RED_MAX doubles)
     PinnedBuf pin_in, pin_out;
     b2r_h_problem* cached = nullptr;  // reusable problem storage of b2r_find_homography[_batch]
     b2r_p_problem* cached_p = nullptr;  // same for b2r_solve_pnp_ransac[_batch]

@@ -307,17 +307,26 @@ struct HFinalizeShared {
 //   rmask      : [Q][n] RANSAC-stage mask (output)
 //   H_out      : [Q][9], mask_out : [Q][n], info : [Q] (b2r_h_info layout = 12 int32)
 //   ext_mask/ext_H : refine-only entry (b2r_refine_h): caller-supplied inlier mask and initial model
-template <int THREADS>
+// GRID = true: ONE problem on a cooperative grid of gridDim.x CTAs (all SMs), reductions through gscratch + grid barriers
+// instead of distributed shared memory — a cluster is limited to 8 SMs, which made the passes over the points the bulk
+// of the finalize time of a large single problem.
+template <int THREADS, bool GRID = false>
 __global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 1)   // small problems come in batches: keep 4 CTAs per SM resident
 k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samples, int Hs,
              const HSelect* __restrict__ sel, float thr_sq, int mask_semantics, int refine, int fast_solver,
              double* __restrict__ H_out, uint8_t* __restrict__ mask_out, uint8_t* __restrict__ rmask_out,
-             int* __restrict__ info, const uint8_t* __restrict__ ext_mask, const double* __restrict__ ext_H) {
+             int* __restrict__ info, const uint8_t* __restrict__ ext_mask, const double* __restrict__ ext_H,
+             double* __restrict__ gscratch) {
     __shared__ HFinalizeShared sh;
     __shared__ ClusterRed R;
     __shared__ JacobiWarp9 jw;   // workspace of the warp-cooperative eigen-solver (warp 0)
     cg::cluster_group cluster = cg::this_cluster();
-    const unsigned csize = cluster.num_blocks(), crank = cluster.block_rank();
+    const unsigned csize = GRID ? gridDim.x : cluster.num_blocks(), crank = GRID ? blockIdx.x : cluster.block_rank();
+#define TEAM_REDUCE(NV, NMAX, arr)                                                        \
+    do {                                                                                  \
+        if (GRID) grid_reduce_tail_max<THREADS, NV, NMAX>(R, arr, gscratch);              \
+        else cluster_reduce_tail_max<THREADS, NV, NMAX>(R, arr);                          \
+    } while (0)
     const int q = blockIdx.x / csize, tid = threadIdx.x;
     const int gtid = crank * THREADS + tid, gstride = csize * THREADS;
     const bool writer = crank == 0;  // one CTA of the cluster writes the small outputs
@@ -371,7 +380,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
     }
     {
         double kv[1] = {(double)k_local};
-        cluster_reduce<THREADS, 1, false>(R, kv);
+        TEAM_REDUCE(1, 0, kv);
     }
     const int k = (int)R.out[0];
 
@@ -385,7 +394,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
                     c[0] += (double)(-p.z); c[1] += (double)(-p.w); c[2] += (double)p.x; c[3] += (double)p.y;
                 }
-            cluster_reduce<THREADS, 4, false>(R, c);
+            TEAM_REDUCE(4, 0, c);
             nm.cmx = R.out[0] / k; nm.cmy = R.out[1] / k; nm.cMx = R.out[2] / k; nm.cMy = R.out[3] / k;
             double a[4] = {0, 0, 0, 0};
             for (int i = gtid; i < n; i += gstride)
@@ -394,7 +403,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     a[0] += fabs((double)(-p.z) - nm.cmx); a[1] += fabs((double)(-p.w) - nm.cmy);
                     a[2] += fabs((double)p.x - nm.cMx); a[3] += fabs((double)p.y - nm.cMy);
                 }
-            cluster_reduce<THREADS, 4, false>(R, a);
+            TEAM_REDUCE(4, 0, a);
             nm.smx = R.out[0]; nm.smy = R.out[1]; nm.sMx = R.out[2]; nm.sMy = R.out[3];
         }
         const bool degenerate = fabs(nm.smx) < DBL_EPSILON || fabs(nm.smy) < DBL_EPSILON ||
@@ -422,7 +431,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                         L[18 + j] += r2 * pp[j];
                     }
                 }
-            cluster_reduce<THREADS, 24, false>(R, L);
+            TEAM_REDUCE(24, 0, L);
             if (tid < 32) {  // warp 0
                 // index of (a,b), a<=b, in the packed symmetric 3x3: (0,0)=0 (0,1)=1 (0,2)=2 (1,1)=3 (1,2)=4 (2,2)=5
                 const int sym[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
@@ -500,7 +509,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                         acc[31 + u] += a[u] * rr;
                     }
                 }
-            cluster_reduce_tail_max<THREADS, 35, 1>(R, acc);
+            TEAM_REDUCE(35, 1, acc);
             const double S = R.out[0], rmax = R.out[34];
             if (tid == 0) {
                 const double* o = R.out;
@@ -676,7 +685,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
     }
     {
         double kv[1] = {(double)n_inl};
-        cluster_reduce<THREADS, 1, false>(R, kv);
+        TEAM_REDUCE(1, 0, kv);
     }
     if (writer && tid < 9) H_out[(size_t)q * 9 + tid] = sh.H[tid];
     if (writer && tid == 0) {
@@ -684,7 +693,8 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
         inf[4] = smp.x; inf[5] = smp.y; inf[6] = smp.z; inf[7] = smp.w;
         inf[8] = (int)R.out[0]; inf[9] = sh.lm_iters; inf[10] = s.pad; inf[11] = 0;
     }
-    cluster.sync();  // no CTA may exit while a peer can still read its shared memory
+    if (!GRID) cluster.sync();  // no CTA may exit while a peer can still read its shared memory
+#undef TEAM_REDUCE
 }
 
 // ---- self tests / probes -----------------------------------------------------------------------------------------
