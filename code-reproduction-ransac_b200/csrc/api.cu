@@ -437,8 +437,8 @@ extern "C" {
 
 b2r_h_problem* b2r_h_problem_upload(b2r_ctx* c, const double* src, const double* dst, int32_t dst_shared, int32_t Q,
                                     int32_t n) {
-    if (!c || !src || !dst || Q < 1 || n < 4) {
-        fail(B2R_ERR_ARG, "b2r_h_problem_upload: need Q >= 1 and n >= 4 points (cv2.findHomography raises below 4)%s%s");
+    if (!c || !src || !dst || Q < 1 || Q > 65535 || n < 4) {
+        fail(B2R_ERR_ARG, "b2r_h_problem_upload: need 1 <= Q <= 65535 and n >= 4 points (cv2.findHomography raises below 4)%s%s");
         return nullptr;
     }
     if (cudaSetDevice(c->device) != cudaSuccess) {
@@ -458,7 +458,7 @@ b2r_h_problem* b2r_h_problem_upload(b2r_ctx* c, const double* src, const double*
 
 int b2r_h_problem_reupload(b2r_ctx* c, b2r_h_problem* pr, const double* src, const double* dst, int32_t dst_shared,
                            int32_t Q, int32_t n) {
-    if (!c || !pr || !src || !dst || Q < 1 || n < 4) return fail(B2R_ERR_ARG, "bad argument (need Q >= 1, n >= 4)%s%s");
+    if (!c || !pr || !src || !dst || Q < 1 || Q > 65535 || n < 4) return fail(B2R_ERR_ARG, "bad argument (need 1 <= Q <= 65535, n >= 4)%s%s");
     CU(cudaSetDevice(c->device));
     CU(pr->pts.reserve(sizeof(PointH) * (size_t)Q * n));
     return upload_points(c, pr, src, dst, dst_shared, Q, n);
@@ -516,7 +516,7 @@ int b2r_h_problem_stage_ms(b2r_ctx* c, b2r_h_problem* pr, float ms_out[5]) {
 int b2r_find_homography_batch(b2r_ctx* c, const double* src, const double* dst, int32_t dst_shared, int32_t Q, int32_t n,
                               const b2r_h_params* p, double* H_out, uint8_t* mask_out, b2r_h_info* info_out) {
     if (!c || !src || !dst || !H_out) return fail(B2R_ERR_ARG, "null argument%s%s");
-    if (Q < 1) return fail(B2R_ERR_ARG, "Q must be >= 1%s%s");
+    if (Q < 1 || Q > 65535) return fail(B2R_ERR_ARG, "Q must be in 1..65535 (one grid dimension per problem): split larger batches%s%s");
     if (n < 4) return fail(B2R_ERR_ARG, "findHomography needs at least 4 point pairs (cv2 raises cv2.error)%s%s");
     int rc = check_params(p);
     if (rc) return rc;
@@ -545,7 +545,7 @@ int b2r_camera_sweep(b2r_ctx* c, const double* pos3d, const double* pixels, int3
                      const b2r_h_params* p, double* scores_out, double* M_out, double* H_out, uint8_t* mask_out,
                      b2r_h_info* info_out, int32_t* best_out) {
     if (!c || !pos3d || !pixels || !cams || !scores_out) return fail(B2R_ERR_ARG, "null argument%s%s");
-    if (Q < 1) return fail(B2R_ERR_ARG, "Q must be >= 1%s%s");
+    if (Q < 1 || Q > 65535) return fail(B2R_ERR_ARG, "Q must be in 1..65535 (one grid dimension per problem): split larger batches%s%s");
     if (n < 4) return fail(B2R_ERR_ARG, "findHomography needs at least 4 point pairs (cv2 raises cv2.error)%s%s");
     int rc = check_params(p);
     if (rc) return rc;

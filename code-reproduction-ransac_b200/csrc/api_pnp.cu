@@ -324,7 +324,7 @@ static int p_fetch(b2r_ctx* c, b2r_p_problem* pr, double* rvec, double* tvec, in
 }
 
 static int check_pnp_shape(int Q, int n) {
-    if (Q < 1) return fail(B2R_ERR_ARG, "Q must be >= 1%s%s");
+    if (Q < 1 || Q > 65535) return fail(B2R_ERR_ARG, "Q must be in 1..65535 (one grid dimension per problem): split larger batches%s%s");
     if (n < 4) return fail(B2R_ERR_ARG, "solvePnPRansac needs at least 4 correspondences (cv2 raises cv2.error)%s%s");
     if (n == 4)
         return fail(B2R_ERR_ARG, "n == 4 takes OpenCV's P3P branch, which is not on the reference's path (12 points) and not "
