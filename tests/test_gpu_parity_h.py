@@ -165,3 +165,21 @@ def test_philox_partition_invariance_and_fast_vs_exact(ctx):
     Hf, mf, _ = ctx.find_homography(s, d, 3.0, max_iters=4096, arith=ransac_b200.ARITH_FAST, **kw)
     assert np.abs(Hf - H0).max() / np.abs(H0).max() < REL_H_TOL
     assert (mf != m0).sum() <= 2
+
+
+@pytest.mark.parametrize("n,seed", [(300, 60), (3000, 61), (40000, 62)])
+def test_refine_building_block(ctx, oracle, n, seed):
+    """K4's refinement alone (b2r_refine_h): refit on a given inlier set + the 9-parameter LM(10), against the oracle's
+    runKernel + LM on the same points.  n = 40000 takes the cooperative-grid form of the kernel, the others one CTA / a
+    cluster; the sums are reduced in a different order than on the CPU, hence a tolerance (1e-8) instead of equality."""
+    s, d = _problem(n, 0.4, seed)
+    sq, dq = _quant(s), _quant(d)
+    Hr, mr, det = oracle.find_homography(s, d, 3.0, details=True)
+    mask = det["ransac_mask"].astype(np.uint8)
+    H, iters = ctx.refine_h(sq, dq, mask, det["ransac_H"])
+    inl = mask.astype(bool)
+    H0 = oracle.h_run_kernel(sq[inl], dq[inl])
+    Href, it_ref = oracle.h_lm_refine(sq[inl], dq[inl], H0)
+    assert iters == it_ref
+    assert np.abs(H - Href).max() / np.abs(Href).max() < 1e-8
+    assert np.abs(H - Hr).max() / np.abs(Hr).max() < 1e-8          # = what the whole call returns
