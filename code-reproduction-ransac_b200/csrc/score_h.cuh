@@ -8,8 +8,8 @@
 // registers for the whole kernel.  A CTA stages one tile of points in shared memory with a single
 // 1-D TMA bulk copy (cp.async.bulk + mbarrier), then every warp walks the tile with broadcast
 // LDS.128 loads: no cross-lane traffic, counts stay in registers, one RED.ADD per hypothesis per
-// tile at the end.  Points are stored "pair-duplicated" (PointH below) so that a point can be
-// multiplied against two hypotheses with one FFMA2/FMUL2/FADD2.
+// tile at the end.  A point enters every FFMA2/FMUL2/FADD2 through the scalar-broadcast operand form, so one
+// instruction evaluates it against the two hypotheses of a pair.
 //
 // Arithmetic modes
 //   EXACT: the reference's un-fused fp32 sequence, operation for operation (A.5):

@@ -6,7 +6,7 @@
 // cyclic-by-max-pivot scheme), smallest eigenvector, de-normalise, scale by
 // 1/H[2][2].  The whole translation unit is compiled with -fmad=false and uses only IEEE
 // + - * / sqrt in fp64, in the reference's operation order, so the 4-point model is bit-identical
-// to the CPU result (tests/test_gpu_parity.py checks that against the oracle).
+// to the CPU result (tests/test_gpu_parity_h.py checks that against the oracle).
 #pragma once
 #include <cuda_runtime.h>
 #include <float.h>
