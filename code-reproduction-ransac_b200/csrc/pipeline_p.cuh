@@ -542,8 +542,12 @@ k_finalize_p(const PointPX* __restrict__ pts, size_t pts_q_stride, const double*
             for (int i = 0; i < PNP_MP; ++i) smp[i] = samples[((size_t)q * Hs + s.best) * PNP_MP + i];
             if (rt) {
                 const double* m = rt + ((size_t)q * Hs + s.best) * 6;
-                for (int i = 0; i < 6; ++i) model[i] = m[i];
-                have_model = 1;
+                bool any = false;
+                for (int i = 0; i < 6; ++i) {
+                    model[i] = m[i];
+                    any |= m[i] != 0;
+                }
+                have_model = any ? 1 : 0;   // the solve kernel stores zeros when the minimal solver produced no model
             } else {
             gather5(P, smp, obj5, img5);
             have_model = (fast_solver ? pnp_minimal_model_fast(obj5, img5, K4[0], K4[1], K4[2], K4[3], model, model + 3)
