@@ -256,12 +256,14 @@ static int run_score(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p) {
         int* not_done = reinterpret_cast<int*>(st + Q);
         LAUNCH(c, k_state_init, (unsigned)((Q + 127) / 128), 128, 0, st, p->max_iters, Q);
         // chunk boundaries 64, 128, 256, 512, ...: on the reference's data OpenCV stops after 13-173 iterations (median 24)
+        int active = Q;   // problems still iterating (from the "not done" counter of the previous chunk)
         for (int begin = 0, len = 64; begin < H; begin += len, len = begin) {
             if (len > H - begin) len = H - begin;
             CU(cudaMemsetAsync(not_done, 0, sizeof(int), c->stream));
             LAUNCH(c, k_cv_sample_h, (unsigned)Q, 32, 0, pr->pts.as<PointH>(), n, H, begin, len, pr->samples.as<int>(), st, Q);
-            if (p->solver == B2R_SOLVER_EXACT && (long long)Q * len <= 4LL * c->sm_count) {
-                // a handful of solves: one warp each (latency)
+            if (p->solver == B2R_SOLVER_EXACT && (long long)active * len <= 32LL * c->sm_count) {
+                // few solves (a single problem, or the stragglers of a batch: finished problems' warps exit at once):
+                // one warp each — 4x less latency than a thread each, and the redundant fp64 work does not matter
                 dim3 grid((unsigned)((len + 7) / 8), (unsigned)Q);
                 LAUNCH(c, k_solve_h4_warp, grid, 256, 0, pr->pts.as<PointH>(), n, pr->samples.as<int>(), H, begin, len,
                        (const RansacState*)st, pr->models.as<float4>(), (double*)nullptr, (uint8_t*)nullptr, (uint8_t*)nullptr);
@@ -287,6 +289,7 @@ static int run_score(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p) {
             CU(cudaMemcpyAsync(&nd, not_done, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
             if (nd == 0) break;
+            active = nd;
         }
     }
     CU(cudaEventRecord(pr->ev[1], c->stream));  // replay path: the whole loop is accounted to stage 0
