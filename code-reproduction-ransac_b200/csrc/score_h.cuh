@@ -85,10 +85,15 @@ struct HEval {
     __device__ __forceinline__ static f2_t err(const f2_t (&h)[8], f2_t X, f2_t Y, f2_t nu, f2_t nv, f2_t one) {
         if (EXACT) {
             // ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false (the scalar
-            // mul.rn.f32 / add.rn.f32 pair is never contracted).  So: products are packed (FMUL2), every sum that
-            // consumes a product directly is done with scalar __fadd_rn on the two halves, and only sums of sums
-            // are packed (FADD2).  tests/test_gpu_parity_h.py holds the counts to the un-fused CPU sequence.
-            const f2_t w = f2_add(f2_sum_of_products(f2_mul(h[6], X), f2_mul(h[7], Y)), one);
+            // mul.rn.f32 / add.rn.f32 pair is never contracted), which breaks bit-exactness.  Every product is therefore
+            // written as fma(a, b, +0): RN(a*b + 0) = RN(a*b) for every a, b (only the sign of an exact zero product can
+            // differ, which cannot reach the comparison: see below), the addend is the zero register (no register-file
+            // read), and ptxas does not contract an add into an FMA that already has an addend.  All sums are packed adds.
+            // Sign of zero: a product that is exactly -0 becomes +0; adding it to any non-zero value, squaring it, or
+            // taking 1/(.. + 1) gives the same bits either way, and dx = +-0 gives dx*dx = +0 in both cases.
+            // tests/test_gpu_parity_h.py holds the counts to the un-fused CPU sequence.
+            const f2_t zero = f2_dup(0.0f);
+            const f2_t w = f2_add(f2_add(f2_fma(h[6], X, zero), f2_fma(h[7], Y, zero)), one);
             float w0, w1;
             f2_unpack(w, w0, w1);
             f2_t ww;
@@ -100,11 +105,11 @@ struct HEval {
             } else {
                 ww = f2_pack(__frcp_rn(w0), __frcp_rn(w1));
             }
-            const f2_t sx = f2_add(f2_sum_of_products(f2_mul(h[0], X), f2_mul(h[1], Y)), h[2]);
-            const f2_t sy = f2_add(f2_sum_of_products(f2_mul(h[3], X), f2_mul(h[4], Y)), h[5]);
-            const f2_t dx = f2_sum_of_products(f2_mul(sx, ww), nu);
-            const f2_t dy = f2_sum_of_products(f2_mul(sy, ww), nv);
-            return f2_sum_of_products(f2_mul(dx, dx), f2_mul(dy, dy));
+            const f2_t sx = f2_add(f2_add(f2_fma(h[0], X, zero), f2_fma(h[1], Y, zero)), h[2]);
+            const f2_t sy = f2_add(f2_add(f2_fma(h[3], X, zero), f2_fma(h[4], Y, zero)), h[5]);
+            const f2_t dx = f2_add(f2_fma(sx, ww, zero), nu);
+            const f2_t dy = f2_add(f2_fma(sy, ww, zero), nv);
+            return f2_add(f2_fma(dx, dx, zero), f2_fma(dy, dy, zero));
         } else {
             f2_t w = f2_fma(h[6], X, f2_fma(h[7], Y, one));
             float w0, w1;
