@@ -97,7 +97,7 @@ struct HEval {
             float w0, w1;
             f2_unpack(w, w0, w1);
             f2_t ww;
-            if (__builtin_expect(rcp_rn_in_fast_range(w0) && rcp_rn_in_fast_range(w1), 1)) {
+            if (__builtin_expect(rcp_rn_fast_path_ok(w0) && rcp_rn_fast_path_ok(w1), 1)) {
                 // one Newton step on the MUFU seed: y + y*(1 - w*y), correctly rounded in the fast range
                 const float y0 = rcp_approx(w0), y1 = rcp_approx(w1);
                 const float e0 = __fmaf_rn(-w0, y0, 1.0f), e1 = __fmaf_rn(-w1, y1, 1.0f);
