@@ -103,6 +103,13 @@ class HomographyProblem:
         keys = np.ascontiguousarray(np.asarray(keys, dtype=np.uint64).reshape(self.Q))
         self.ctx._check(self.ctx._L.b2r_h_problem_finish(self.ctx._c, self._h, C.byref(params), _ptr(keys, C.c_uint64)))
 
+    def score_shard_dev(self, params, keys_dev_ptr):
+        """Stage 1 with the packed keys written to DEVICE memory (Q uint64 at `keys_dev_ptr`), asynchronous on the context's stream."""
+        self.ctx._check(self.ctx._L.b2r_h_problem_score_shard_dev(self.ctx._c, self._h, C.byref(params), C.c_void_p(int(keys_dev_ptr))))
+
+    def finish_dev(self, params, keys_dev_ptr):
+        self.ctx._check(self.ctx._L.b2r_h_problem_finish_dev(self.ctx._c, self._h, C.byref(params), C.c_void_p(int(keys_dev_ptr))))
+
     def fetch(self, want_mask=True):
         H = np.zeros((self.Q, 3, 3))
         mask = np.zeros((self.Q, self.n), dtype=np.uint8) if want_mask else None

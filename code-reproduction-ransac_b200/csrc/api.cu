@@ -400,14 +400,16 @@ static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samp
 }
 
 // stage 2: select + finalize.  keys_host != nullptr: use these (globally reduced) keys instead of the local ones.
-static int run_finish(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p, const uint64_t* keys_host) {
+static int run_finish(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p, const uint64_t* keys_host,
+                      const uint64_t* keys_dev = nullptr) {
     const int Q = pr->Q, n = pr->n, H = pr->H_last;
     const float thr_sq = (float)(p->thr * p->thr);
     if (n == 4) {
         LAUNCH(c, k_select_n4, (unsigned)((Q + 127) / 128), 128, 0, pr->sel.as<HSelect>(), pr->samples.as<int>(), Q);
     } else if (p->sampler == B2R_SAMPLER_PHILOX) {
-        if (keys_host) {
-            CU(cudaMemcpyAsync(pr->keys.p, keys_host, sizeof(uint64_t) * Q, cudaMemcpyHostToDevice, c->stream));
+        if (keys_host || keys_dev) {
+            if (keys_host) CU(cudaMemcpyAsync(pr->keys.p, keys_host, sizeof(uint64_t) * Q, cudaMemcpyHostToDevice, c->stream));
+            else CU(cudaMemcpyAsync(pr->keys.p, keys_dev, sizeof(uint64_t) * Q, cudaMemcpyDeviceToDevice, c->stream));
             LAUNCH(c, k_resample_winner, (unsigned)((Q + 127) / 128), 128, 0, pr->pts.as<PointH>(), n,
                    pr->keys.as<unsigned long long>(), p->seed, H, pr->samples.as<int>(), pr->sel.as<HSelect>(), H, Q);
         } else {
@@ -513,6 +515,26 @@ int b2r_h_problem_finish(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p, c
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
     return run_finish(c, pr, p, keys);
+}
+
+int b2r_h_problem_score_shard_dev(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p, uint64_t* keys_dev_out) {
+    if (!c || !pr || !keys_dev_out) return fail(B2R_ERR_ARG, "null argument%s%s");
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (p->sampler != B2R_SAMPLER_PHILOX) return fail(B2R_ERR_ARG, "hypothesis sharding needs the PHILOX sampler%s%s");
+    if (pr->n <= 4) return fail(B2R_ERR_ARG, "sharding needs n > 4%s%s");
+    CU(cudaSetDevice(c->device));
+    if ((rc = run_score(c, pr, p))) return rc;
+    CU(cudaMemcpyAsync(keys_dev_out, pr->keys.p, sizeof(uint64_t) * pr->Q, cudaMemcpyDeviceToDevice, c->stream));
+    return B2R_OK;
+}
+
+int b2r_h_problem_finish_dev(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p, const uint64_t* keys_dev) {
+    if (!c || !pr || !keys_dev) return fail(B2R_ERR_ARG, "null argument%s%s");
+    int rc = check_params(p);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    return run_finish(c, pr, p, nullptr, keys_dev);
 }
 
 int b2r_h_problem_fetch(b2r_ctx* c, b2r_h_problem* pr, double* H_out, uint8_t* mask_out, b2r_h_info* info_out) {

@@ -31,6 +31,18 @@ def reduce_keys_max(keys, group=None, device=None):
     return t.cpu().numpy().view(np.uint64)
 
 
+_KEYS = {}
+
+
+def _device_keys(Q, device):
+    """A cached int64 device tensor of Q packed keys (the all-reduce buffer)."""
+    import torch
+    k = (str(device), int(Q))
+    if k not in _KEYS:
+        _KEYS[k] = torch.zeros(int(Q), dtype=torch.int64, device=device)
+    return _KEYS[k]
+
+
 def shard_range(total, rank, world):
     """Contiguous split of `total` hypothesis ids: rank r gets [begin, begin+count)."""
     base, rem = divmod(int(total), int(world))
@@ -43,6 +55,18 @@ def run_sharded(problem, thr, hyp_begin, hyp_count, seed=0, arith=api.ARITH_EXAC
     """Score this rank's shard of a resident problem, reduce, finish.  Results stay on the device (problem.fetch())."""
     p = api.make_params(thr, hyp_count, confidence, sampler=api.SAMPLER_PHILOX, seed=seed, arith=arith,
                         mask_semantics=mask_semantics, refine=refine, hyp_begin=hyp_begin, solver=solver)
+    import torch.distributed as dist
+    if device is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 \
+            and dist.get_backend(group) == "nccl":
+        # keys never leave the GPU: score -> NCCL MAX all-reduce -> finish, all enqueued on the library's stream
+        import torch
+        stream = torch.cuda.ExternalStream(problem.ctx.stream, device=device)
+        with torch.cuda.stream(stream):
+            t = _device_keys(problem.Q, device)
+            problem.score_shard_dev(p, t.data_ptr())
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)     # keys < 2^63: int64 MAX == uint64 MAX
+            problem.finish_dev(p, t.data_ptr())
+        return None
     keys = problem.score_shard(p)
     best = reduce_keys_max(keys, group=group, device=device)
     problem.finish(p, best)

@@ -139,6 +139,10 @@ int b2r_h_problem_fetch(b2r_ctx* ctx, b2r_h_problem* prob, double* H_out, uint8_
  * (mask, refit, LM) identically on every rank. */
 int b2r_h_problem_score_shard(b2r_ctx* ctx, b2r_h_problem* prob, const b2r_h_params* params, uint64_t* keys_out);
 int b2r_h_problem_finish(b2r_ctx* ctx, b2r_h_problem* prob, const b2r_h_params* params, const uint64_t* keys);
+/* The same two stages with the keys staying in DEVICE memory (Q uint64 on the context's GPU), asynchronous on the context's
+ * stream: a collective library can reduce them in place (NCCL all-reduce enqueued on that stream) without a host round trip. */
+int b2r_h_problem_score_shard_dev(b2r_ctx* ctx, b2r_h_problem* prob, const b2r_h_params* params, uint64_t* keys_dev_out);
+int b2r_h_problem_finish_dev(b2r_ctx* ctx, b2r_h_problem* prob, const b2r_h_params* params, const uint64_t* keys_dev);
 /* Device time (ms, CUDA events on the context stream) of the stages of the last run:
  * [0] sample+solve, [1] scoring kernel, [2] select, [3] finalize (mask/refit/LM), [4] total. */
 int b2r_h_problem_stage_ms(b2r_ctx* ctx, b2r_h_problem* prob, float ms_out[5]);
