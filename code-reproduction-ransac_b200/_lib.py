@@ -95,6 +95,8 @@ SIGNATURES = {
     "b2r_p_problem_fetch": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, c_double_p, c_i32_p, c_i32_p, C.POINTER(PInfo)]),
     "b2r_p_problem_score_shard": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PParams), c_u64_p]),
     "b2r_p_problem_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PParams), c_u64_p]),
+    "b2r_p_problem_score_shard_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PParams), C.c_void_p]),
+    "b2r_p_problem_finish_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PParams), C.c_void_p]),
     "b2r_p_problem_stage_ms": (C.c_int, [C.c_void_p, C.c_void_p, c_float_p]),
     "b2r_score_p": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, C.c_int32, c_double_p, C.c_float,
                               C.c_int32, c_i32_p]),

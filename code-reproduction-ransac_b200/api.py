@@ -210,6 +210,12 @@ class PnPProblem:
         keys = np.ascontiguousarray(np.asarray(keys, dtype=np.uint64).reshape(self.Q))
         self.ctx._check(self.ctx._L.b2r_p_problem_finish(self.ctx._c, self._h, C.byref(params), _ptr(keys, C.c_uint64)))
 
+    def score_shard_dev(self, params, keys_dev_ptr):
+        self.ctx._check(self.ctx._L.b2r_p_problem_score_shard_dev(self.ctx._c, self._h, C.byref(params), C.c_void_p(int(keys_dev_ptr))))
+
+    def finish_dev(self, params, keys_dev_ptr):
+        self.ctx._check(self.ctx._L.b2r_p_problem_finish_dev(self.ctx._c, self._h, C.byref(params), C.c_void_p(int(keys_dev_ptr))))
+
     def fetch(self, want_inliers=True):
         """(rvec (Q,3), tvec (Q,3), inliers list of int32 arrays or None, infos)"""
         rvec, tvec = np.zeros((self.Q, 3)), np.zeros((self.Q, 3))

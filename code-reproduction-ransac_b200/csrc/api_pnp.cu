@@ -248,15 +248,17 @@ static int launch_cluster(b2r_ctx* c, Kern kern, int n_clusters, int csize, int 
     return B2R_OK;
 }
 
-static int p_run_finish(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p, const uint64_t* keys_host) {
+static int p_run_finish(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p, const uint64_t* keys_host,
+                        const uint64_t* keys_dev = nullptr) {
     const int Q = pr->Q, n = pr->n, H = pr->H_last;
     const float thr_sq = (float)(p->thr * p->thr);
     int Hs = H;
     if (n == PNP_MP) {
         LAUNCH(c, k_select_single, (unsigned)((Q + 127) / 128), 128, 0, pr->sel.as<HSelect>(), Q);
     } else if (p->sampler == B2R_SAMPLER_PHILOX) {
-        if (keys_host) {
-            CU(cudaMemcpyAsync(pr->keys.p, keys_host, sizeof(uint64_t) * Q, cudaMemcpyHostToDevice, c->stream));
+        if (keys_host || keys_dev) {
+            if (keys_host) CU(cudaMemcpyAsync(pr->keys.p, keys_host, sizeof(uint64_t) * Q, cudaMemcpyHostToDevice, c->stream));
+            else CU(cudaMemcpyAsync(pr->keys.p, keys_dev, sizeof(uint64_t) * Q, cudaMemcpyDeviceToDevice, c->stream));
             LAUNCH(c, k_resample_winner_p, (unsigned)((Q + 127) / 128), 128, 0, n, pr->keys.as<unsigned long long>(), p->seed, H,
                    pr->samples.as<int>(), pr->sel.as<HSelect>(), H, Q);
         } else {
@@ -273,14 +275,14 @@ static int p_run_finish(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p, co
                             (const double*)pr->raw_obj.as<double>(), (const double*)pr->raw_img.as<double>(), pr->pts_stride(), n,
                             (const int*)pr->samples.as<int>(), Hs, (const HSelect*)pr->sel.as<HSelect>(),
                             (const double*)pr->Kq.as<double>(), thr_sq, (int)p->refine, (int)(n == PNP_MP), (int)p->solver,
-                            (const double*)(pr->rt_valid && !keys_host ? pr->rt.as<double>() : nullptr), pr->rmask.as<uint8_t>(),
+                            (const double*)(pr->rt_valid && !keys_host && !keys_dev ? pr->rt.as<double>() : nullptr), pr->rmask.as<uint8_t>(),
                             pr->pose.as<double>(), pr->info_i.as<int>(), pr->info_d.as<double>());
     else
         rc = launch_cluster(c, k_finalize_p<128>, Q, csize, 128, (const PointPX*)pr->px.as<PointPX>(), pr->pts_stride(),
                             (const double*)pr->raw_obj.as<double>(), (const double*)pr->raw_img.as<double>(), pr->pts_stride(), n,
                             (const int*)pr->samples.as<int>(), Hs, (const HSelect*)pr->sel.as<HSelect>(),
                             (const double*)pr->Kq.as<double>(), thr_sq, (int)p->refine, (int)(n == PNP_MP), (int)p->solver,
-                            (const double*)(pr->rt_valid && !keys_host ? pr->rt.as<double>() : nullptr), pr->rmask.as<uint8_t>(),
+                            (const double*)(pr->rt_valid && !keys_host && !keys_dev ? pr->rt.as<double>() : nullptr), pr->rmask.as<uint8_t>(),
                             pr->pose.as<double>(), pr->info_i.as<int>(), pr->info_d.as<double>());
     if (rc) return rc;
     LAUNCH(c, k_compact_inliers, (unsigned)Q, 1024, 0, pr->rmask.as<uint8_t>(), n, pr->inliers.as<int>(), pr->ninl.as<int>());
@@ -419,6 +421,26 @@ int b2r_p_problem_finish(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p, c
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
     return p_run_finish(c, pr, p, keys);
+}
+
+int b2r_p_problem_score_shard_dev(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p, uint64_t* keys_dev_out) {
+    if (!c || !pr || !keys_dev_out) return fail(B2R_ERR_ARG, "null argument%s%s");
+    int rc = check_p_params(p);
+    if (rc) return rc;
+    if (p->sampler != B2R_SAMPLER_PHILOX) return fail(B2R_ERR_ARG, "hypothesis sharding needs the PHILOX sampler%s%s");
+    if (pr->n <= PNP_MP) return fail(B2R_ERR_ARG, "sharding needs n > 5%s%s");
+    CU(cudaSetDevice(c->device));
+    if ((rc = p_run_score(c, pr, p))) return rc;
+    CU(cudaMemcpyAsync(keys_dev_out, pr->keys.p, sizeof(uint64_t) * pr->Q, cudaMemcpyDeviceToDevice, c->stream));
+    return B2R_OK;
+}
+
+int b2r_p_problem_finish_dev(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p, const uint64_t* keys_dev) {
+    if (!c || !pr || !keys_dev) return fail(B2R_ERR_ARG, "null argument%s%s");
+    int rc = check_p_params(p);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    return p_run_finish(c, pr, p, nullptr, keys_dev);
 }
 
 int b2r_p_problem_fetch(b2r_ctx* c, b2r_p_problem* pr, double* rvec_out, double* tvec_out, int32_t* inliers_out,

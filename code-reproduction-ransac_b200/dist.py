@@ -98,10 +98,21 @@ def find_homography_sharded(ctx, src, dst, thr, total_hypotheses, seed=0, arith=
 
 # ---- PnP path (cv2.solvePnPRansac, main_v1.py:497): same sharding scheme ---------------------------------------------
 def run_sharded_pnp(problem, thr, hyp_begin, hyp_count, seed=0, arith=api.ARITH_EXACT, confidence=0.99, refine=True, group=None,
-                    device=None):
+                    device=None, solver=api.SOLVER_EXACT):
     """Score this rank's hypothesis-id shard of a resident PnPProblem, MAX-reduce the packed keys, finish on every rank."""
     p = api.make_p_params(thr, hyp_count, confidence, sampler=api.SAMPLER_PHILOX, seed=seed, arith=arith, refine=refine,
-                          hyp_begin=hyp_begin)
+                          hyp_begin=hyp_begin, solver=solver)
+    import torch.distributed as dist
+    if device is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 \
+            and dist.get_backend(group) == "nccl":
+        import torch
+        stream = torch.cuda.ExternalStream(problem.ctx.stream, device=device)
+        with torch.cuda.stream(stream):
+            t = _device_keys(problem.Q, device)
+            problem.score_shard_dev(p, t.data_ptr())
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            problem.finish_dev(p, t.data_ptr())
+        return None
     keys = problem.score_shard(p)
     best = reduce_keys_max(keys, group=group, device=device)
     problem.finish(p, best)

@@ -240,6 +240,9 @@ int b2r_p_problem_fetch(b2r_ctx* ctx, b2r_p_problem* prob, double* rvec_out, dou
                         int32_t* n_inliers_out, b2r_p_info* info_out);
 int b2r_p_problem_score_shard(b2r_ctx* ctx, b2r_p_problem* prob, const b2r_p_params* params, uint64_t* keys_out);
 int b2r_p_problem_finish(b2r_ctx* ctx, b2r_p_problem* prob, const b2r_p_params* params, const uint64_t* keys);
+/* device-resident keys, asynchronous on the context's stream (see b2r_h_problem_score_shard_dev) */
+int b2r_p_problem_score_shard_dev(b2r_ctx* ctx, b2r_p_problem* prob, const b2r_p_params* params, uint64_t* keys_dev_out);
+int b2r_p_problem_finish_dev(b2r_ctx* ctx, b2r_p_problem* prob, const b2r_p_params* params, const uint64_t* keys_dev);
 int b2r_p_problem_stage_ms(b2r_ctx* ctx, b2r_p_problem* prob, float ms_out[5]);
 
 /* building blocks of the PnP path (parity tests) */
