@@ -56,15 +56,16 @@ def run_sharded(problem, thr, hyp_begin, hyp_count, seed=0, arith=api.ARITH_EXAC
     p = api.make_params(thr, hyp_count, confidence, sampler=api.SAMPLER_PHILOX, seed=seed, arith=arith,
                         mask_semantics=mask_semantics, refine=refine, hyp_begin=hyp_begin, solver=solver)
     import torch.distributed as dist
-    if device is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 \
-            and dist.get_backend(group) == "nccl":
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if device is not None and (not multi or dist.get_backend(group) == "nccl"):
         # keys never leave the GPU: score -> NCCL MAX all-reduce -> finish, all enqueued on the library's stream
         import torch
         stream = torch.cuda.ExternalStream(problem.ctx.stream, device=device)
         with torch.cuda.stream(stream):
             t = _device_keys(problem.Q, device)
             problem.score_shard_dev(p, t.data_ptr())
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)     # keys < 2^63: int64 MAX == uint64 MAX
+            if multi:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)     # keys < 2^63: int64 MAX == uint64 MAX
             problem.finish_dev(p, t.data_ptr())
         return None
     keys = problem.score_shard(p)
