@@ -291,7 +291,7 @@ __device__ void solve_sym_eig_warp(JacobiWarp9& jw, const double* A_src, const d
     const int lane = threadIdx.x & 31;
     for (int e = lane; e < N * N; e += 32) jw.A[e] = A_src[e];
     __syncwarp();
-    jacobi_eig_warp<N>(jw.A, jw.W, jw.V, jw.indR, jw.indC);
+    jacobi_eig_warp2<N>(jw.A, jw.W, jw.V, jw.indR, jw.indC);
     double thr = 0;
     for (int i = 0; i < N; ++i) thr += fabs(jw.W[i]);
     thr *= DBL_EPSILON * 2;

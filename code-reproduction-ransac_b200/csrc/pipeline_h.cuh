@@ -182,10 +182,11 @@ k_solve_h4(const PointH* __restrict__ pts, int n, const int* __restrict__ sample
 }
 
 // K2, exact solver, thread per solve with the 9x9 matrices in SHARED memory ([element][thread] layout, conflict-free for
-// any per-thread pivot sequence).  One warp per CTA: 32 x 171 doubles = 43 KB of dynamic shared memory, five CTAs per SM.
-// Bit-identical to k_solve_h4; ~8x its throughput (its per-thread local arrays overflow the L1).
+// any per-thread pivot sequence).  One warp per CTA: 32 x 126 doubles (packed upper triangle + eigenvectors) = 31.5 KB of
+// dynamic shared memory, seven CTAs per SM; the decomposition is the divergence-free jacobi_eig_packed.
+// Bit-identical to k_solve_h4; ~25x its throughput (its per-thread local arrays overflow the L1).
 constexpr int K2S_THREADS = 32;
-constexpr size_t K2S_SMEM = sizeof(double) * 171 * K2S_THREADS;
+constexpr size_t K2S_SMEM = sizeof(double) * H4_WS_DOUBLES * K2S_THREADS;
 __global__ void __launch_bounds__(K2S_THREADS)
 k_solve_h4_smem(const PointH* __restrict__ pts, int n, const int* __restrict__ samples, int H_stride, int begin, int len,
                 const RansacState* __restrict__ state, float4* __restrict__ models, double* __restrict__ H64,

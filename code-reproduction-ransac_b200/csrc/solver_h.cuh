@@ -14,18 +14,39 @@
 
 namespace b2r {
 
+// std::hypot as OpenCV's Jacobi uses it: |a| > |b| ? |a| sqrt(1 + (b/a)^2) : (|b| > 0 ? |b| sqrt(1 + (a/b)^2) : 0).
+// Written without branches (operands chosen by selects, one division + square root): the same operations on the same
+// values, but the lanes of a warp that hold different matrices do not serialise the two cases.
 __device__ __forceinline__ double cv_hypot(double a, double b) {
     a = fabs(a);
     b = fabs(b);
-    if (a > b) {
-        b /= a;
-        return a * sqrt(1 + b * b);
+    const bool a_big = a > b;
+    const double big = a_big ? a : b, small = a_big ? b : a;
+    const double q = small / big;
+    const double r = big * sqrt(1 + q * q);
+    return (a_big || b > 0) ? r : 0.;
+}
+
+// Rotation parameters of one Jacobi step (the serial code's  t = |y| + hypot(p, y); s = hypot(p, t); c = t/s; s = p/s;
+// t = (p/t) p;  if (y < 0) s = -s, t = -t)  with one division less on the dependent chain: hypot(p, t) always takes its
+// |p| <= t case (t >= hypot(p, y) >= |p| also after rounding), whose quotient q = |p| / t is p/t up to the sign — IEEE
+// division rounds the magnitude independently of the signs, so copysign(q, p) == p / t bit for bit.  Finite p, y only.
+__device__ __forceinline__ void jacobi_rotation(double p, double y, double& c, double& s, double& t) {
+    const double tt = fabs(y) + cv_hypot(p, y);
+    const double ap = fabs(p);
+    double sh, pt;
+    if (ap > tt) {  // not reachable for finite input; the letter of the serial code
+        sh = cv_hypot(p, tt);
+        pt = p / tt;
+    } else {
+        const double q = ap / tt;
+        sh = tt * sqrt(1 + q * q);
+        pt = copysign(q, p);
     }
-    if (b > 0) {
-        a /= b;
-        return b * sqrt(1 + a * a);
-    }
-    return 0;
+    c = tt / sh;
+    s = p / sh;
+    t = pt * p;
+    if (y < 0) s = -s, t = -t;
 }
 
 // Symmetric eigen-decomposition, n <= 9.  A (n*n, row-major, destroyed), W eigenvalues descending,
@@ -243,6 +264,148 @@ __device__ void jacobi_eig_strided(double* A, double* W, double* V) {
 #undef WW
 }
 
+// ---- the strided eigen-solver, uniform form ---------------------------------------------------------------------------
+// jacobi_eig_strided runs the data-dependent loops of the serial code (i < k, k < i < l, i > l; idx+2 <= i < N; i < idx)
+// as they are written: in a warp of 32 independent decompositions every lane has its own (k, l), the loops diverge, the
+// trip counts add up and the index arrays live in local memory.  This form executes the same arithmetic with
+//   * every loop a full unrolled pass over i = 0..N-1 with the element pair chosen by selects and the store predicated
+//     (no divergence inside a rotation, all loads of a pass independent of each other),
+//   * the searches as tournaments in which the earlier candidate wins ties — the serial scan replaces its maximum only
+//     on a strictly greater value, so both pick the first maximal candidate (finite values; the caller sends a
+//     matrix with a non-finite entry through jacobi_eig_strided),
+//   * indR / indC as 4-bit fields of two 64-bit registers.
+// Operation for operation identical to jacobi_eig<N> on every element.
+struct NibbleArray {
+    unsigned long long v = 0;
+    __device__ __forceinline__ int get(int i) const { return (int)((v >> (4 * i)) & 15ull); }
+    __device__ __forceinline__ void set(int i, int m) { v = (v & ~(15ull << (4 * i))) | ((unsigned long long)m << (4 * i)); }
+};
+
+// first maximal candidate of val[0..CNT): tournament, the earlier one wins ties; tag[] travels along
+template <int CNT>
+__device__ __forceinline__ int first_argmax(double* val, int* tag) {
+#pragma unroll
+    for (int w = 1; w < CNT; w <<= 1)
+#pragma unroll
+        for (int a = 0; a + w < CNT; a += 2 * w)
+            if (val[a] < val[a + w]) val[a] = val[a + w], tag[a] = tag[a + w];
+    return tag[0];
+}
+
+// U: the upper triangle of A INCLUDING the diagonal, packed row-major (element (r, c), r <= c, at T(r) + c with
+// T(r) = r (2N - 1 - r) / 2), N (N + 1) / 2 entries; the serial code never touches the lower triangle and reads the
+// diagonal only to initialise W, so W lives on the diagonal: on return U(k, k) is the k-th eigenvalue (descending) and
+// row k of V its eigenvector.  126 instead of 171 doubles per decomposition for N = 9: 7 instead of 5 resident warps per SM.
+// Precondition: finite entries (normalised-DLT matrices are bounded by construction).
+template <int N, int STRIDE>
+__device__ void jacobi_eig_packed(double* U, double* V) {
+    static_assert(N >= 2 && N <= 15, "4-bit index fields");
+    NibbleArray indR, indC;
+#define TRI(r) (((r) * (2 * N - 1 - (r))) >> 1)
+#define UE(e) U[(e) * STRIDE]
+#define VE(e) V[(e) * STRIDE]
+    // indR[idx]: first maximal |A[idx][i]|, i > idx;  indC[idx]: first maximal |A[i][idx]|, i < idx.
+    // An index outside the searched range is clamped onto the nearest candidate inside it (a duplicate of the first
+    // candidate placed before it, or of the last one placed after it, never changes which index wins).
+    auto refresh = [&](int idx, int t_idx) {
+        double val[N - 1];
+        int tag[N - 1];
+        if (idx < N - 1) {
+#pragma unroll
+            for (int i = 1; i < N; i++) {
+                const int ci = max(i, idx + 1);
+                val[i - 1] = fabs(UE(t_idx + ci));
+                tag[i - 1] = ci;
+            }
+            indR.set(idx, first_argmax<N - 1>(val, tag));
+        }
+        if (idx > 0) {
+            const int t_last = TRI(idx - 1);
+#pragma unroll
+            for (int i = 0; i < N - 1; i++) {
+                const int ci = min(i, idx - 1);
+                val[i] = fabs(UE(min(TRI(i), t_last) + idx));   // T is increasing: T(min(i, idx-1)) = min(T(i), T(idx-1))
+                tag[i] = ci;
+            }
+            indC.set(idx, first_argmax<N - 1>(val, tag));
+        }
+    };
+#pragma unroll 1
+    for (int i = 0; i < N * N; i++) VE(i) = 0;
+#pragma unroll 1
+    for (int k = 0; k < N; k++) {
+        VE(k * N + k) = 1;
+        refresh(k, TRI(k));
+    }
+#pragma unroll 1
+    for (int it = 0; it < N * N * 30; it++) {
+        // pivot: rows 0..N-2 through indR, then columns 1..N-1 through indC
+        double val[2 * (N - 1)];
+        int tag[2 * (N - 1)];
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) {
+            const int r = indR.get(i);
+            val[i] = fabs(UE(TRI(i) + r));
+            tag[i] = i | (r << 4);
+        }
+#pragma unroll
+        for (int i = 1; i < N; i++) {
+            const int c = indC.get(i);
+            val[N - 2 + i] = fabs(UE(TRI(c) + i));
+            tag[N - 2 + i] = c | (i << 4);
+        }
+        const int kl = first_argmax<2 * (N - 1)>(val, tag);
+        const int k = kl & 15, l = kl >> 4;
+        const int tk = TRI(k), tl = TRI(l);
+        const double p = UE(tk + l);
+        if (fabs(p) <= DBL_EPSILON) break;
+        const double wk = UE(tk + k), wl = UE(tl + l);
+        double c, s, t;
+        jacobi_rotation(p, (wl - wk) * 0.5, c, s, t);
+        UE(tk + l) = 0;
+        UE(tk + k) = wk - t;
+        UE(tl + l) = wl + t;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const int e0 = i < k ? TRI(i) + k : tk + i;
+            const int e1 = i < l ? TRI(i) + l : tl + i;
+            const double a0 = UE(e0), b0 = UE(e1);
+            const double n0 = a0 * c - b0 * s, n1 = a0 * s + b0 * c;
+            if (i != k && i != l) {
+                UE(e0) = n0;
+                UE(e1) = n1;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const double a0 = VE(k * N + i), b0 = VE(l * N + i);
+            VE(k * N + i) = a0 * c - b0 * s;
+            VE(l * N + i) = a0 * s + b0 * c;
+        }
+        refresh(k, tk);
+        refresh(l, tl);
+    }
+#pragma unroll 1
+    for (int k = 0; k < N - 1; k++) {
+        int m = k;
+        for (int i = k + 1; i < N; i++)
+            if (UE(TRI(m) + m) < UE(TRI(i) + i)) m = i;
+        if (k != m) {
+            double tmp = UE(TRI(m) + m);
+            UE(TRI(m) + m) = UE(TRI(k) + k);
+            UE(TRI(k) + k) = tmp;
+            for (int i = 0; i < N; i++) {
+                tmp = VE(m * N + i);
+                VE(m * N + i) = VE(k * N + i);
+                VE(k * N + i) = tmp;
+            }
+        }
+    }
+#undef TRI
+#undef UE
+#undef VE
+}
+
 // ---- warp-cooperative form of the same eigen-solver ---------------------------------------------------------------
 // One solve per WARP, matrices in shared memory.  Pivot choice and the rotation parameters are computed redundantly by
 // every lane (broadcast reads, no divergence); lane i then rotates the element pairs of index i — in the serial code
@@ -372,6 +535,155 @@ __device__ void jacobi_eig_warp(double* A, double* W, double* V, int* indR, int*
     }
 }
 
+// The same decomposition with the two index searches spread over the lanes.  Per rotation the form above walks 16 pivot
+// candidates and up to 8 entries per refreshed indR/indC one compare after another, and its rotation step is a chain
+// of branches; measured on a B200 (tools/microbench_jacobi.cu) a rotation costs ~3000 cycles of which the fp64
+// div/sqrt chain that cannot be shortened is ~650.  Here
+//   * the 2(N-1) pivot candidates sit on lanes 0..2N-3 in OpenCV's visiting order and the winner is the LOWEST lane
+//     holding the maximum |value| (the serial loop replaces its maximum only on a strictly greater value), found with
+//     two 32-bit warp max-reductions over the bit pattern of |value| (non-negative doubles order like integers);
+//   * the four refreshed entries indR[k], indC[k], indR[l], indC[l] are searched by four groups of eight lanes with a
+//     three-step butterfly and the same lowest-index tie rule;
+//   * lanes 0..N-1 rotate A, lanes 16..16+N-1 rotate V, lane 31 updates W — one select-addressed code path.
+// Every element still goes through the same IEEE operations: bit-identical to jacobi_eig<N> for finite matrices; a
+// matrix with a non-finite entry (never produced from finite correspondences) is sent through jacobi_eig_warp.
+template <int N>
+__device__ void jacobi_eig_warp2(double* A, double* W, double* V, int* indR, int* indC) {
+    static_assert(N >= 2 && N <= 9, "lane layout: 2(N-1) <= 16 pivot candidates, 8-lane search groups");
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    {
+        bool finite = true;
+        for (int e = lane; e < N * N; e += 32) finite = finite && fabs(A[e]) <= DBL_MAX;
+        if (!__all_sync(FULL, finite)) {
+            jacobi_eig_warp<N>(A, W, V, indR, indC);
+            return;
+        }
+    }
+    for (int e = lane; e < N * N; e += 32) V[e] = (e / N == e % N) ? 1. : 0.;
+    if (lane < N) {
+        const int k = lane;
+        W[k] = A[k * N + k];
+        if (k < N - 1) {
+            double mv = fabs(A[k * N + k + 1]);
+            int m = k + 1;
+            for (int i = k + 2; i < N; i++) {
+                const double val = fabs(A[k * N + i]);
+                if (mv < val) mv = val, m = i;
+            }
+            indR[k] = m;
+        }
+        if (k > 0) {
+            double mv = fabs(A[k]);
+            int m = 0;
+            for (int i = 1; i < k; i++) {
+                const double val = fabs(A[i * N + k]);
+                if (mv < val) mv = val, m = i;
+            }
+            indC[k] = m;
+        }
+    }
+    __syncwarp();
+    // fixed roles of this lane
+    const bool row_cand = lane < N - 1, col_cand = lane >= N - 1 && lane < 2 * (N - 1);
+    const int cand_i = col_cand ? lane - (N - 2) : (row_cand ? lane : 0);
+    const int* cand_ind = col_cand ? indC + cand_i : indR + cand_i;
+    const bool rot_v = lane >= 16;
+    const int rot_i = lane & 15;
+    double* rot_base = rot_v ? V : A;
+    const int grp = lane >> 3, gj = lane & 7;
+    const bool srch_row = (grp & 1) == 0;
+    for (int it = 0; it < N * N * 30; it++) {
+        // ---- pivot ----
+        const int other = *cand_ind;
+        const int ck = col_cand ? other : cand_i, cl = col_cand ? cand_i : other;
+        double cval = fabs(A[ck * N + cl]);
+        if (!(row_cand || col_cand)) cval = 0.;
+        const unsigned hi = (unsigned)__double2hiint(cval), lo = (unsigned)__double2loint(cval);
+        const unsigned mh = __reduce_max_sync(FULL, hi);
+        const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+        const int win = __ffs(__ballot_sync(FULL, hi == mh && lo == ml)) - 1;
+        const int kl = __shfl_sync(FULL, ck | (cl << 8), win);
+        const int k = kl & 255, l = kl >> 8;
+        const double p = A[k * N + l], Wk = W[k], Wl = W[l];
+        if (__all_sync(FULL, fabs(p) <= DBL_EPSILON)) break;
+        // jacobi_rotation() with the two quotients by hypot(p, t) taken on different lanes (one division latency)
+        const double y = (Wl - Wk) * 0.5;
+        const double tt = fabs(y) + cv_hypot(p, y);
+        const double q = fabs(p) / tt;               // |p| <= tt
+        const double sh = tt * sqrt(1 + q * q);
+        const double quo = ((lane & 1) ? p : tt) / sh;
+        const double c = __shfl_sync(FULL, quo, 0);
+        double s = __shfl_sync(FULL, quo, 1);
+        double t = copysign(q, p) * p;
+        if (y < 0) s = -s, t = -t;
+        __syncwarp();  // all lanes have read A[k][l], W[k], W[l]
+        // ---- rotation ----
+        {
+            const int i = rot_i;
+            int e0 = k * N + i, e1 = l * N + i;
+            if (!rot_v) {
+                if (i < k) e0 = i * N + k;
+                if (i < l) e1 = i * N + l;
+            }
+            const bool act = rot_v ? i < N : (i < N && i != k && i != l);
+            if (act) {
+                const double a0 = rot_base[e0], b0 = rot_base[e1];
+                rot_base[e0] = a0 * c - b0 * s;
+                rot_base[e1] = a0 * s + b0 * c;
+            }
+            if (lane == 31) {
+                A[k * N + l] = 0;
+                W[k] = Wk - t;
+                W[l] = Wl + t;
+            }
+        }
+        __syncwarp();
+        // ---- indR[k], indC[k], indR[l], indC[l] ----
+        {
+            const int idx = grp < 2 ? k : l;
+            const int cand = srch_row ? idx + 1 + gj : gj;
+            const bool valid = srch_row ? cand < N : cand < idx;
+            long long key = -1ll;
+            if (valid) key = __double_as_longlong(fabs(srch_row ? A[idx * N + cand] : A[cand * N + idx]));
+            long long gmax = key;
+#pragma unroll
+            for (int sft = 1; sft < 8; sft <<= 1) {
+                const long long o = __shfl_xor_sync(FULL, gmax, sft);
+                gmax = o > gmax ? o : gmax;
+            }
+            const unsigned eq = __ballot_sync(FULL, valid && key == gmax);
+            const int jwin = __ffs((eq >> (grp * 8)) & 255u) - 1;
+            if (gj == 0 && jwin >= 0) {
+                if (srch_row) indR[idx] = idx + 1 + jwin;
+                else indC[idx] = jwin;
+            }
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    // eigenvalues descending, rows of V alongside
+    for (int k = 0; k < N - 1; k++) {
+        int m = k;
+        for (int i = k + 1; i < N; i++)
+            if (W[m] < W[i]) m = i;
+        __syncwarp();
+        if (k != m) {
+            if (lane == 0) {
+                const double tmp = W[m];
+                W[m] = W[k];
+                W[k] = tmp;
+            }
+            if (lane < N) {
+                const double tmp = V[m * N + lane];
+                V[m * N + lane] = V[k * N + lane];
+                V[k * N + lane] = tmp;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __device__ __forceinline__ void mat3_mul(const double* a, const double* b, double* o) {
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) {
@@ -452,8 +764,9 @@ static __device__ int h_solve4(const float* M, const float* m, double* H) {
     return 1;
 }
 
-// 4-point solve on strided (shared-memory) storage: ws = this thread's column of a [171][STRIDE] double workspace
-// (A 81 | V 81 | W 9).  Bit-identical to h_solve4.
+// 4-point solve on strided (shared-memory) storage: ws = this thread's column of a [H4_WS_DOUBLES][STRIDE] double
+// workspace (packed upper triangle of L^T L 45 | V 81).  Bit-identical to h_solve4.
+constexpr int H4_WS_DOUBLES = 45 + 81;
 template <int STRIDE>
 __device__ __forceinline__ int h_solve4_strided(double* ws, const float* M, const float* m, double* H) {
     HNorm nm = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -474,10 +787,9 @@ __device__ __forceinline__ int h_solve4_strided(double* ws, const float* M, cons
     if (fabs(nm.smx) < DBL_EPSILON || fabs(nm.smy) < DBL_EPSILON || fabs(nm.sMx) < DBL_EPSILON || fabs(nm.sMy) < DBL_EPSILON)
         return 0;
     nm.smx = count / nm.smx; nm.smy = count / nm.smy; nm.sMx = count / nm.sMx; nm.sMy = count / nm.sMy;
-    double* A = ws;
-    double* V = ws + 81 * STRIDE;
-    double* W = ws + 162 * STRIDE;
-    for (int e = 0; e < 81; e++) A[e * STRIDE] = 0;
+    double* U = ws;
+    double* V = ws + 45 * STRIDE;
+    for (int e = 0; e < 45; e++) U[e * STRIDE] = 0;
     for (int i = 0; i < count; i++) {
         const double x = ((double)m[2 * i] - nm.cmx) * nm.smx, y = ((double)m[2 * i + 1] - nm.cmy) * nm.smy;
         const double X = ((double)M[2 * i] - nm.cMx) * nm.sMx, Y = ((double)M[2 * i + 1] - nm.cMy) * nm.sMy;
@@ -486,11 +798,9 @@ __device__ __forceinline__ int h_solve4_strided(double* ws, const float* M, cons
 #pragma unroll
         for (int j = 0; j < 9; j++)
 #pragma unroll
-            for (int k = j; k < 9; k++) A[(j * 9 + k) * STRIDE] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+            for (int k = j; k < 9; k++) U[(((j * (17 - j)) >> 1) + k) * STRIDE] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
     }
-    for (int j = 0; j < 9; j++)
-        for (int k = 0; k < j; k++) A[(j * 9 + k) * STRIDE] = A[(k * 9 + j) * STRIDE];
-    jacobi_eig_strided<9, STRIDE>(A, W, V);
+    jacobi_eig_packed<9, STRIDE>(U, V);
     double vec[9];
     for (int i = 0; i < 9; ++i) vec[i] = V[(72 + i) * STRIDE];
     h_from_eigvec(vec, nm, H);
@@ -506,7 +816,7 @@ __device__ __forceinline__ void h_from_LtL_warp(JacobiWarp9& jw, const HNorm& nm
         if (k < j) jw.A[e] = jw.A[k * 9 + j];
     }
     __syncwarp();
-    jacobi_eig_warp<9>(jw.A, jw.W, jw.V, jw.indR, jw.indC);
+    jacobi_eig_warp2<9>(jw.A, jw.W, jw.V, jw.indR, jw.indC);
     double vec[9];
     for (int i = 0; i < 9; ++i) vec[i] = jw.V[72 + i];
     h_from_eigvec(vec, nm, H);

@@ -1,0 +1,455 @@
+// Probe: where the time of one 9x9 Jacobi eigen-decomposition (OpenCV's pivot order, fp64) goes on an SM, and the fp64
+// dependent-issue latencies that bound it.  One warp per decomposition (jacobi_eig_warp), one thread per decomposition
+// (jacobi_eig_strided), and the section cycle counts of the warp form.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -I code-reproduction-ransac_b200/csrc tools/microbench_jacobi.cu -o tools/microbench_jacobi
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <cfloat>
+#include <vector>
+#include <cstring>
+#include "solver_h.cuh"
+using namespace b2r;
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
+
+// ---- dependent-chain latencies (one warp, clock64 around a chain of CH dependent operations) --------------------------
+enum { L_DFMA, L_DADD, L_DDIV, L_DSQRT, L_DSETP_SEL, L_LDS_CHASE, L_SHFL, L_REDUX, L_NLAT };
+template <int KIND>
+__global__ void k_lat(double* out, long long* cyc, double a, double b, int CH) {
+    __shared__ int chase[64];
+    for (int i = threadIdx.x; i < 64; i += 32) chase[i] = (i * 7 + 3) & 63;
+    __syncwarp();
+    double x = a + threadIdx.x * 1e-9;
+    int idx = threadIdx.x & 63;
+    unsigned u = threadIdx.x * 2654435761u;
+    long long t0 = clock64();
+    for (int i = 0; i < CH; ++i) {
+        if (KIND == L_DFMA) x = fma(x, b, a);
+        if (KIND == L_DADD) x = x + b;
+        if (KIND == L_DDIV) x = a / x + b;          // div + add
+        if (KIND == L_DSQRT) x = sqrt(x) + b;       // sqrt + add
+        if (KIND == L_DSETP_SEL) x = (x < b + i) ? x + 1.0 : b;   // compare + select (+ add)
+        if (KIND == L_LDS_CHASE) idx = chase[idx];
+        if (KIND == L_SHFL) u = __shfl_xor_sync(0xffffffffu, u, 1) + 1u;
+        if (KIND == L_REDUX) u = __reduce_max_sync(0xffffffffu, u) + threadIdx.x;
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) *cyc = t1 - t0;
+    out[threadIdx.x] = x + idx + u;
+}
+
+// ---- the warp form with section timers (copy of jacobi_eig_warp; lane 0's clock) ----------------------------------------
+struct Prof { long long pivot, arith, rotate, ind, total; int rotations; };
+
+template <int N>
+__device__ void jacobi_eig_warp_prof(double* A, double* W, double* V, int* indR, int* indC, Prof* pf) {
+    const int lane = threadIdx.x & 31;
+    long long c_p = 0, c_a = 0, c_r = 0, c_i = 0;
+    const long long tstart = clock64();
+    for (int e = lane; e < N * N; e += 32) V[e] = (e / N == e % N) ? 1. : 0.;
+    if (lane < N) {
+        const int k = lane;
+        W[k] = A[k * N + k];
+        if (k < N - 1) {
+            double mv = fabs(A[k * N + k + 1]);
+            int m = k + 1;
+            for (int i = k + 2; i < N; i++) { const double val = fabs(A[k * N + i]); if (mv < val) mv = val, m = i; }
+            indR[k] = m;
+        }
+        if (k > 0) {
+            double mv = fabs(A[k]);
+            int m = 0;
+            for (int i = 1; i < k; i++) { const double val = fabs(A[i * N + k]); if (mv < val) mv = val, m = i; }
+            indC[k] = m;
+        }
+    }
+    __syncwarp();
+    int it;
+    for (it = 0; it < N * N * 30; it++) {
+        long long t0 = clock64();
+        double mv = fabs(A[indR[0]]);
+        int k = 0, l, i;
+        for (i = 1; i < N - 1; i++) { const double val = fabs(A[i * N + indR[i]]); if (mv < val) mv = val, k = i; }
+        l = indR[k];
+        for (i = 1; i < N; i++) { const double val = fabs(A[indC[i] * N + i]); if (mv < val) mv = val, k = indC[i], l = i; }
+        const double p = A[k * N + l];
+        if (fabs(p) <= DBL_EPSILON) break;
+        long long t1 = clock64();
+        const double y = (W[l] - W[k]) * 0.5;
+        double t = fabs(y) + cv_hypot(p, y);
+        double s = cv_hypot(p, t);
+        const double c = t / s;
+        s = p / s;
+        t = (p / t) * p;
+        if (y < 0) s = -s, t = -t;
+        __syncwarp();
+        long long t2 = clock64() + (long long)(c == 12345.678 ? 1 : 0) + (long long)(t == 12345.678 ? 1 : 0);
+        if (lane == 0) { A[k * N + l] = 0; W[k] -= t; W[l] += t; }
+        if (lane < N) {
+            i = lane;
+            double *p0 = nullptr, *p1 = nullptr;
+            if (i < k) { p0 = &A[i * N + k]; p1 = &A[i * N + l]; }
+            else if (i > k && i < l) { p0 = &A[k * N + i]; p1 = &A[i * N + l]; }
+            else if (i > l) { p0 = &A[k * N + i]; p1 = &A[l * N + i]; }
+            if (p0) { const double a0 = *p0, b0 = *p1; *p0 = a0 * c - b0 * s; *p1 = a0 * s + b0 * c; }
+            const double v0 = V[k * N + i], v1 = V[l * N + i];
+            V[k * N + i] = v0 * c - v1 * s;
+            V[l * N + i] = v0 * s + v1 * c;
+        }
+        __syncwarp();
+        long long t3 = clock64();
+        if (lane < 4) {
+            const int idx = lane < 2 ? k : l;
+            if ((lane & 1) == 0) {
+                if (idx < N - 1) {
+                    double m2 = fabs(A[idx * N + idx + 1]);
+                    int m = idx + 1;
+                    for (i = idx + 2; i < N; i++) { const double val = fabs(A[idx * N + i]); if (m2 < val) m2 = val, m = i; }
+                    indR[idx] = m;
+                }
+            } else if (idx > 0) {
+                double m2 = fabs(A[idx]);
+                int m = 0;
+                for (i = 1; i < idx; i++) { const double val = fabs(A[i * N + idx]); if (m2 < val) m2 = val, m = i; }
+                indC[idx] = m;
+            }
+        }
+        __syncwarp();
+        long long t4 = clock64();
+        c_p += t1 - t0; c_a += t2 - t1; c_r += t3 - t2; c_i += t4 - t3;
+    }
+    __syncwarp();
+    if (lane == 0) { pf->pivot = c_p; pf->arith = c_a; pf->rotate = c_r; pf->ind = c_i; pf->rotations = it; pf->total = clock64() - tstart; }
+}
+
+// the lane-parallel form with the same timers (generated copy of jacobi_eig_warp2)
+template <int N>
+__device__ void jacobi_eig_warp2_prof(double* A, double* W, double* V, int* indR, int* indC, Prof* pf) {
+    static_assert(N >= 2 && N <= 9, "lane layout: 2(N-1) <= 16 pivot candidates, 8-lane search groups");
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    {
+        bool finite = true;
+        for (int e = lane; e < N * N; e += 32) finite = finite && fabs(A[e]) <= DBL_MAX;
+        if (!__all_sync(FULL, finite)) {
+            jacobi_eig_warp<N>(A, W, V, indR, indC);
+            return;
+        }
+    }
+    for (int e = lane; e < N * N; e += 32) V[e] = (e / N == e % N) ? 1. : 0.;
+    if (lane < N) {
+        const int k = lane;
+        W[k] = A[k * N + k];
+        if (k < N - 1) {
+            double mv = fabs(A[k * N + k + 1]);
+            int m = k + 1;
+            for (int i = k + 2; i < N; i++) {
+                const double val = fabs(A[k * N + i]);
+                if (mv < val) mv = val, m = i;
+            }
+            indR[k] = m;
+        }
+        if (k > 0) {
+            double mv = fabs(A[k]);
+            int m = 0;
+            for (int i = 1; i < k; i++) {
+                const double val = fabs(A[i * N + k]);
+                if (mv < val) mv = val, m = i;
+            }
+            indC[k] = m;
+        }
+    }
+    __syncwarp();
+    // fixed roles of this lane
+    const bool row_cand = lane < N - 1, col_cand = lane >= N - 1 && lane < 2 * (N - 1);
+    const int cand_i = col_cand ? lane - (N - 2) : (row_cand ? lane : 0);
+    const int* cand_ind = col_cand ? indC + cand_i : indR + cand_i;
+    const bool rot_v = lane >= 16;
+    const int rot_i = lane & 15;
+    double* rot_base = rot_v ? V : A;
+    const int grp = lane >> 3, gj = lane & 7;
+    const bool srch_row = (grp & 1) == 0;
+    long long c_p = 0, c_a = 0, c_r = 0, c_i = 0; const long long tstart = clock64(); int it;
+    for (it = 0; it < N * N * 30; it++) {
+        const long long t0 = clock64();
+        // ---- pivot ----
+        const int other = *cand_ind;
+        const int ck = col_cand ? other : cand_i, cl = col_cand ? cand_i : other;
+        double cval = fabs(A[ck * N + cl]);
+        if (!(row_cand || col_cand)) cval = 0.;
+        const unsigned hi = (unsigned)__double2hiint(cval), lo = (unsigned)__double2loint(cval);
+        const unsigned mh = __reduce_max_sync(FULL, hi);
+        const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+        const int win = __ffs(__ballot_sync(FULL, hi == mh && lo == ml)) - 1;
+        const int kl = __shfl_sync(FULL, ck | (cl << 8), win);
+        const int k = kl & 255, l = kl >> 8;
+        const double p = A[k * N + l], Wk = W[k], Wl = W[l];
+        if (__all_sync(FULL, fabs(p) <= DBL_EPSILON)) break;
+        const long long t1 = clock64();
+        // jacobi_rotation() with the two quotients by hypot(p, t) taken on different lanes (one division latency)
+        const double y = (Wl - Wk) * 0.5;
+        const double tt = fabs(y) + cv_hypot(p, y);
+        const double q = fabs(p) / tt;               // |p| <= tt
+        const double sh = tt * sqrt(1 + q * q);
+        const double quo = ((lane & 1) ? p : tt) / sh;
+        const double c = __shfl_sync(FULL, quo, 0);
+        double s = __shfl_sync(FULL, quo, 1);
+        double t = copysign(q, p) * p;
+        if (y < 0) s = -s, t = -t;
+        __syncwarp();  // all lanes have read A[k][l], W[k], W[l]
+        const long long t2 = clock64() + (long long)(c == 12345.678 ? 1 : 0) + (long long)(t == 12345.678 ? 1 : 0);
+        // ---- rotation ----
+        {
+            const int i = rot_i;
+            int e0 = k * N + i, e1 = l * N + i;
+            if (!rot_v) {
+                if (i < k) e0 = i * N + k;
+                if (i < l) e1 = i * N + l;
+            }
+            const bool act = rot_v ? i < N : (i < N && i != k && i != l);
+            if (act) {
+                const double a0 = rot_base[e0], b0 = rot_base[e1];
+                rot_base[e0] = a0 * c - b0 * s;
+                rot_base[e1] = a0 * s + b0 * c;
+            }
+            if (lane == 31) {
+                A[k * N + l] = 0;
+                W[k] = Wk - t;
+                W[l] = Wl + t;
+            }
+        }
+        __syncwarp();
+        const long long t3 = clock64();
+        // ---- indR[k], indC[k], indR[l], indC[l] ----
+        {
+            const int idx = grp < 2 ? k : l;
+            const int cand = srch_row ? idx + 1 + gj : gj;
+            const bool valid = srch_row ? cand < N : cand < idx;
+            long long key = -1ll;
+            if (valid) key = __double_as_longlong(fabs(srch_row ? A[idx * N + cand] : A[cand * N + idx]));
+            long long gmax = key;
+#pragma unroll
+            for (int sft = 1; sft < 8; sft <<= 1) {
+                const long long o = __shfl_xor_sync(FULL, gmax, sft);
+                gmax = o > gmax ? o : gmax;
+            }
+            const unsigned eq = __ballot_sync(FULL, valid && key == gmax);
+            const int jwin = __ffs((eq >> (grp * 8)) & 255u) - 1;
+            if (gj == 0 && jwin >= 0) {
+                if (srch_row) indR[idx] = idx + 1 + jwin;
+                else indC[idx] = jwin;
+            }
+        }
+        __syncwarp();
+        const long long t4 = clock64();
+        c_p += t1 - t0; c_a += t2 - t1; c_r += t3 - t2; c_i += t4 - t3;
+    }
+    __syncwarp();
+    if (lane == 0) { pf->pivot = c_p; pf->arith = c_a; pf->rotate = c_r; pf->ind = c_i; pf->rotations = it; pf->total = clock64() - tstart; }
+    // eigenvalues descending, rows of V alongside
+    for (int k = 0; k < N - 1; k++) {
+        int m = k;
+        for (int i = k + 1; i < N; i++)
+            if (W[m] < W[i]) m = i;
+        __syncwarp();
+        if (k != m) {
+            if (lane == 0) {
+                const double tmp = W[m];
+                W[m] = W[k];
+                W[k] = tmp;
+            }
+            if (lane < N) {
+                const double tmp = V[m * N + lane];
+                V[m * N + lane] = V[k * N + lane];
+                V[k * N + lane] = tmp;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+
+__global__ void k_warp2_prof(const double* Ain, double* Wout, Prof* pf) {
+    __shared__ JacobiWarp9 jw;
+    for (int e = threadIdx.x; e < 81; e += 32) jw.A[e] = Ain[e];
+    __syncwarp();
+    jacobi_eig_warp2_prof<9>(jw.A, jw.W, jw.V, jw.indR, jw.indC, pf);
+    __syncwarp();
+    if (threadIdx.x < 9) Wout[threadIdx.x] = jw.W[threadIdx.x];
+}
+
+__global__ void k_warp_prof(const double* Ain, double* Wout, Prof* pf) {
+    __shared__ JacobiWarp9 jw;
+    for (int e = threadIdx.x; e < 81; e += 32) jw.A[e] = Ain[e];
+    __syncwarp();
+    jacobi_eig_warp_prof<9>(jw.A, jw.W, jw.V, jw.indR, jw.indC, pf);
+    __syncwarp();
+    if (threadIdx.x < 9) Wout[threadIdx.x] = jw.W[threadIdx.x];
+}
+
+// the production warp form, nw warps per CTA, every warp its own matrix (mats[w])
+__global__ void k_warp(const double* mats, int nmat, double* Wout, double* Vout) {
+    __shared__ JacobiWarp9 jw[8];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * (blockDim.x >> 5) + w;
+    if (g >= nmat) return;
+    for (int e = lane; e < 81; e += 32) jw[w].A[e] = mats[(size_t)g * 81 + e];
+    __syncwarp();
+    jacobi_eig_warp<9>(jw[w].A, jw[w].W, jw[w].V, jw[w].indR, jw[w].indC);
+    __syncwarp();
+    if (lane < 9) Wout[(size_t)g * 9 + lane] = jw[w].W[lane];
+    for (int e = lane; e < 81; e += 32) Vout[(size_t)g * 81 + e] = jw[w].V[e];
+}
+
+// the production thread form ([element][thread] shared memory), 32 threads per CTA
+__global__ void __launch_bounds__(32) k_thread(const double* mats, int nmat, double* Wout, double* Vout) {
+    extern __shared__ double sm[];
+    const int g = blockIdx.x * 32 + threadIdx.x;
+    double* A = sm + threadIdx.x;
+    double* V = A + 81 * 32;
+    double* W = V + 81 * 32;
+    if (g < nmat) {
+        for (int e = 0; e < 81; ++e) A[e * 32] = mats[(size_t)g * 81 + e];
+        jacobi_eig_strided<9, 32>(A, W, V);
+        for (int e = 0; e < 9; ++e) Wout[(size_t)g * 9 + e] = W[e * 32];
+        for (int e = 0; e < 81; ++e) Vout[(size_t)g * 81 + e] = V[e * 32];
+    }
+}
+
+// the uniform thread form on packed upper-triangular storage (126 doubles per decomposition)
+__global__ void __launch_bounds__(32) k_thread2(const double* mats, int nmat, double* Wout, double* Vout) {
+    extern __shared__ double sm[];
+    const int g = blockIdx.x * 32 + threadIdx.x;
+    double* U = sm + threadIdx.x;
+    double* V = U + 45 * 32;
+    if (g < nmat) {
+        for (int r = 0, e = 0; r < 9; ++r)
+            for (int c = r; c < 9; ++c, ++e) U[e * 32] = mats[(size_t)g * 81 + r * 9 + c];
+        jacobi_eig_packed<9, 32>(U, V);
+        for (int r = 0; r < 9; ++r) Wout[(size_t)g * 9 + r] = U[(((r * (17 - r)) >> 1) + r) * 32];
+        for (int e = 0; e < 81; ++e) Vout[(size_t)g * 81 + e] = V[e * 32];
+    }
+}
+
+// the lane-parallel-search warp form
+__global__ void k_warp2(const double* mats, int nmat, double* Wout, double* Vout) {
+    __shared__ JacobiWarp9 jw[8];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * (blockDim.x >> 5) + w;
+    if (g >= nmat) return;
+    for (int e = lane; e < 81; e += 32) jw[w].A[e] = mats[(size_t)g * 81 + e];
+    __syncwarp();
+    jacobi_eig_warp2<9>(jw[w].A, jw[w].W, jw[w].V, jw[w].indR, jw[w].indC);
+    __syncwarp();
+    if (lane < 9) Wout[(size_t)g * 9 + lane] = jw[w].W[lane];
+    for (int e = lane; e < 81; e += 32) Vout[(size_t)g * 81 + e] = jw[w].V[e];
+}
+
+static void make_LtL(unsigned seed, double* LtL) {   // normalised DLT of 4 random correspondences (what runKernel decomposes)
+    srand(seed);
+    double M[4][2], m[4][2];
+    for (int i = 0; i < 4; ++i) {
+        M[i][0] = 4000.0 * rand() / RAND_MAX; M[i][1] = 3000.0 * rand() / RAND_MAX;
+        m[i][0] = 0.9 * M[i][0] + 0.1 * M[i][1] + 30 + 5.0 * rand() / RAND_MAX;
+        m[i][1] = -0.1 * M[i][0] + 1.1 * M[i][1] - 20 + 5.0 * rand() / RAND_MAX;
+    }
+    double cM[2] = {0, 0}, cm[2] = {0, 0}, sM[2] = {0, 0}, sm[2] = {0, 0};
+    for (int i = 0; i < 4; ++i) { cM[0] += M[i][0]; cM[1] += M[i][1]; cm[0] += m[i][0]; cm[1] += m[i][1]; }
+    for (int j = 0; j < 2; ++j) { cM[j] /= 4; cm[j] /= 4; }
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 2; ++j) { sM[j] += fabs(M[i][j] - cM[j]); sm[j] += fabs(m[i][j] - cm[j]); }
+    for (int j = 0; j < 2; ++j) { sM[j] = 4 / sM[j]; sm[j] = 4 / sm[j]; }
+    for (int i = 0; i < 81; ++i) LtL[i] = 0;
+    for (int i = 0; i < 4; ++i) {
+        double x = (m[i][0] - cm[0]) * sm[0], y = (m[i][1] - cm[1]) * sm[1];
+        double X = (M[i][0] - cM[0]) * sM[0], Y = (M[i][1] - cM[1]) * sM[1];
+        double Lx[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x};
+        double Ly[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
+        for (int j = 0; j < 9; ++j)
+            for (int k = j; k < 9; ++k) LtL[j * 9 + k] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+    }
+    for (int j = 0; j < 9; ++j) for (int k = 0; k < j; ++k) LtL[j * 9 + k] = LtL[k * 9 + j];
+}
+
+template <int KIND>
+static void lat(const char* name) {
+    double* out; long long* cyc;
+    CK(cudaMalloc(&out, 32 * 8)); CK(cudaMalloc(&cyc, 8));
+    const int CH = 4096;
+    long long best = 1ll << 60;
+    for (int r = 0; r < 5; ++r) {
+        k_lat<KIND><<<1, 32>>>(out, cyc, 1.2345, 1.0000001, CH);
+        long long h; CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+        if (h < best) best = h;
+    }
+    printf("{\"probe\": \"latency_%s\", \"cycles_per_step\": %.1f}\n", name, (double)best / CH);
+    cudaFree(out); cudaFree(cyc);
+}
+
+int main() {
+    lat<L_DFMA>("dfma"); lat<L_DADD>("dadd"); lat<L_DDIV>("ddiv_plus_dadd"); lat<L_DSQRT>("dsqrt_plus_dadd");
+    lat<L_DSETP_SEL>("dsetp_sel_dadd"); lat<L_LDS_CHASE>("lds_chase"); lat<L_SHFL>("shfl_iadd"); lat<L_REDUX>("redux_max_iadd");
+
+    const int NM = 29312;   // 458 problems x 64 iterations: the first chunk of the reference's sweep
+    std::vector<double> mats((size_t)NM * 81);
+    for (int g = 0; g < NM; ++g) make_LtL(1000 + g, &mats[(size_t)g * 81]);
+    double *dm, *dW, *dV, *dW2, *dV2; Prof* dpf;
+    CK(cudaMalloc(&dm, mats.size() * 8)); CK(cudaMalloc(&dW, (size_t)NM * 9 * 8)); CK(cudaMalloc(&dV, (size_t)NM * 81 * 8));
+    CK(cudaMalloc(&dW2, (size_t)NM * 9 * 8)); CK(cudaMalloc(&dV2, (size_t)NM * 81 * 8)); CK(cudaMalloc(&dpf, sizeof(Prof)));
+    CK(cudaMemcpy(dm, mats.data(), mats.size() * 8, cudaMemcpyHostToDevice));
+    int clk_khz = 0; CK(cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0));
+
+    for (int r = 0; r < 3; ++r) {
+        k_warp_prof<<<1, 32>>>(dm + 81 * r, dW, dpf);
+        Prof pf; CK(cudaMemcpy(&pf, dpf, sizeof(Prof), cudaMemcpyDeviceToHost));
+        printf("{\"probe\": \"warp_sections\", \"matrix\": %d, \"rotations\": %d, \"cycles_total\": %lld, \"per_rotation\": {\"pivot\": %.0f, \"arith\": %.0f, \"rotate\": %.0f, \"ind_update\": %.0f}}\n",
+               r, pf.rotations, pf.total, (double)pf.pivot / pf.rotations, (double)pf.arith / pf.rotations,
+               (double)pf.rotate / pf.rotations, (double)pf.ind / pf.rotations);
+    }
+    for (int r = 0; r < 3; ++r) {
+        k_warp2_prof<<<1, 32>>>(dm + 81 * r, dW, dpf);
+        Prof pf; CK(cudaMemcpy(&pf, dpf, sizeof(Prof), cudaMemcpyDeviceToHost));
+        printf("{\"probe\": \"warp2_sections\", \"matrix\": %d, \"rotations\": %d, \"cycles_total\": %lld, \"per_rotation\": {\"pivot\": %.0f, \"arith\": %.0f, \"rotate\": %.0f, \"ind_update\": %.0f}}\n",
+               r, pf.rotations, pf.total, (double)pf.pivot / pf.rotations, (double)pf.arith / pf.rotations,
+               (double)pf.rotate / pf.rotations, (double)pf.ind / pf.rotations);
+    }
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    auto time_it = [&](const char* name, int nmat, auto launch) {
+        float best = 1e30f;
+        for (int r = 0; r < 4; ++r) {
+            CK(cudaEventRecord(e0)); launch(nmat); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
+        }
+        CK(cudaGetLastError());
+        printf("{\"probe\": \"%s\", \"matrices\": %d, \"us\": %.1f}\n", name, nmat, best * 1e3);
+    };
+    CK(cudaFuncSetAttribute(k_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, 171 * 32 * 8));
+    CK(cudaFuncSetAttribute(k_thread2, cudaFuncAttributeMaxDynamicSharedMemorySize, 126 * 32 * 8));
+    { int nb = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_thread2, 32, 126 * 32 * 8)); printf("{\"probe\": \"thread2_ctas_per_sm\", \"value\": %d}\n", nb); }
+    for (int nmat : {1, 64, 1024, 8192, NM}) {
+        time_it("warp_form", nmat, [&](int n) { k_warp<<<(n + 7) / 8, 256>>>(dm, n, dW, dV); });
+        time_it("thread_form", nmat, [&](int n) { k_thread<<<(n + 31) / 32, 32, 171 * 32 * 8>>>(dm, n, dW2, dV2); });
+        time_it("thread2_form", nmat, [&](int n) { k_thread2<<<(n + 31) / 32, 32, 126 * 32 * 8>>>(dm, n, dW2, dV2); });
+        time_it("warp2_form", nmat, [&](int n) { k_warp2<<<(n + 7) / 8, 256>>>(dm, n, dW2, dV2); });
+    }
+    // the two production forms agree bit for bit
+    std::vector<double> W1((size_t)NM * 9), W2((size_t)NM * 9), V1((size_t)NM * 81), V2((size_t)NM * 81);
+    k_warp<<<(NM + 7) / 8, 256>>>(dm, NM, dW, dV);
+    k_thread<<<(NM + 31) / 32, 32, 171 * 32 * 8>>>(dm, NM, dW2, dV2);
+    CK(cudaMemcpy(W1.data(), dW, W1.size() * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(W2.data(), dW2, W2.size() * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(V1.data(), dV, V1.size() * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(V2.data(), dV2, V2.size() * 8, cudaMemcpyDeviceToHost));
+    size_t diff = 0;
+    for (size_t i = 0; i < W1.size(); ++i) diff += memcmp(&W1[i], &W2[i], 8) != 0;
+    for (size_t i = 0; i < V1.size(); ++i) diff += memcmp(&V1[i], &V2[i], 8) != 0;
+    printf("{\"probe\": \"warp_vs_thread_bit_differences\", \"count\": %zu}\n", diff);
+    k_warp2<<<(NM + 7) / 8, 256>>>(dm, NM, dW2, dV2);
+    CK(cudaMemcpy(W2.data(), dW2, W2.size() * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(V2.data(), dV2, V2.size() * 8, cudaMemcpyDeviceToHost));
+    diff = 0;
+    for (size_t i = 0; i < W1.size(); ++i) diff += memcmp(&W1[i], &W2[i], 8) != 0;
+    for (size_t i = 0; i < V1.size(); ++i) diff += memcmp(&V1[i], &V2[i], 8) != 0;
+    printf("{\"probe\": \"warp_vs_warp2_bit_differences\", \"count\": %zu}\n", diff);
+    k_thread2<<<(NM + 31) / 32, 32, 126 * 32 * 8>>>(dm, NM, dW2, dV2);
+    CK(cudaMemcpy(W2.data(), dW2, W2.size() * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(V2.data(), dV2, V2.size() * 8, cudaMemcpyDeviceToHost));
+    diff = 0;
+    for (size_t i = 0; i < W1.size(); ++i) diff += memcmp(&W1[i], &W2[i], 8) != 0;
+    for (size_t i = 0; i < V1.size(); ++i) diff += memcmp(&V1[i], &V2[i], 8) != 0;
+    printf("{\"probe\": \"warp_vs_thread2_bit_differences\", \"count\": %zu}\n", diff);
+    return 0;
+}
