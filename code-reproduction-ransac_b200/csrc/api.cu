@@ -353,7 +353,7 @@ __global__ void k_resample_winner(const PointH* __restrict__ pts, int n, const u
 // large problem runs on a cooperative grid over all SMs instead (reductions through global memory + grid barriers).
 static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samples, int Hs, const HSelect* sel, float thr_sq,
                            int mask_semantics, int refine, int solver, double* H_out, uint8_t* mask_out, uint8_t* rmask_out,
-                           int* info, const uint8_t* ext_mask, const double* ext_H, int Q) {
+                           int* info, const uint8_t* ext_mask, const double* ext_H, int Q, const float4* models = nullptr) {
     if (Q == 1 && n >= 32768) {
         constexpr int GT = 512;
         static thread_local int coop_ctas[16] = {0};
@@ -368,7 +368,7 @@ static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samp
             double* gs = c->gscratch.as<double>();
             void* args[] = {(void*)&pts, (void*)&n, (void*)&samples, (void*)&Hs, (void*)&sel, (void*)&thr_sq, (void*)&mask_semantics,
                             (void*)&refine, (void*)&solver, (void*)&H_out, (void*)&mask_out, (void*)&rmask_out, (void*)&info,
-                            (void*)&ext_mask, (void*)&ext_H, (void*)&gs};
+                            (void*)&ext_mask, (void*)&ext_H, (void*)&gs, (void*)&models};
             CU(cudaLaunchCooperativeKernel((const void*)k_finalize_h<GT, true>, dim3((unsigned)ctas), dim3(GT), args, 0, c->stream));
             c->launches++;
             return B2R_OK;
@@ -391,10 +391,10 @@ static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samp
     double* no_scratch = nullptr;
     if (threads == 1024)
         CU(cudaLaunchKernelEx(&cfg, k_finalize_h<1024, false>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
-                              mask_out, rmask_out, info, ext_mask, ext_H, no_scratch));
+                              mask_out, rmask_out, info, ext_mask, ext_H, no_scratch, models));
     else
         CU(cudaLaunchKernelEx(&cfg, k_finalize_h<128, false>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
-                              mask_out, rmask_out, info, ext_mask, ext_H, no_scratch));
+                              mask_out, rmask_out, info, ext_mask, ext_H, no_scratch, models));
     c->launches++;
     return B2R_OK;
 }
@@ -420,9 +420,11 @@ static int run_finish(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p, cons
     CU(cudaGetLastError());
     CU(cudaEventRecord(pr->ev[3], c->stream));
     const int Hs = n == 4 ? 1 : H;
+    // the winner's fp32 model as K3 scored it is still in pr->models unless it came from another rank's shard
+    const float4* stored = (n > 4 && !keys_host && !keys_dev) ? pr->models.as<float4>() : nullptr;
     int rc = launch_finalize(c, pr->pts.as<PointH>(), n, pr->samples.as<int>(), Hs, pr->sel.as<HSelect>(), thr_sq,
                              p->mask_semantics, p->refine, p->solver, pr->H.as<double>(), pr->mask.as<uint8_t>(),
-                             pr->rmask.as<uint8_t>(), pr->info.as<int>(), nullptr, nullptr, Q);
+                             pr->rmask.as<uint8_t>(), pr->info.as<int>(), nullptr, nullptr, Q, stored);
     if (rc) return rc;
     CU(cudaGetLastError());
     CU(cudaEventRecord(pr->ev[4], c->stream));

@@ -90,64 +90,127 @@ k_philox_sample_solve_h(const PointH* __restrict__ pts, int n, int H, long long 
     }
 }
 
-// ---- K1 (replay of cv::RNG): sequential per problem, one WARP per problem ---------------------------------------
+// ---- K1 (replay of cv::RNG): one WARP per problem ---------------------------------------------------------------------
 // Generates the subsets of iterations [begin, begin+len) (clipped to the problem's current iteration bound),
 // continuing the RNG stream stored in the problem's state.  samples : [Q][H_stride][4]
-// The stream is sequential and data-dependent (duplicate draws and rejected subsets consume RNG outputs), so one lane
-// walks it; a problem gets a warp of its own because 32 problems sharing a warp would all pay for the unluckiest one's
-// rejections at every iteration.  The other lanes stage the points in shared memory when they fit (n <= 2048).
+// OpenCV's loop is sequential — duplicate draws and subsets rejected by checkSubset consume RNG outputs — but only the
+// LABELLING of the stream depends on the data: attempt a is the a-th group of four distinct indices of the stream
+// whatever checkSubset says, and iteration j takes the j-th attempt that passes.  So the warp works on windows of 128
+// stream outputs:
+//   1. every lane walks the 128 multiply-with-carry steps (one IMAD.WIDE each) and keeps its four outputs, reduced
+//      modulo n in parallel (the modulo is the expensive part of a draw);
+//   2. every lane walks the 128 indices through the distinct-index state machine (integer compares only) and keeps
+//      the four indices of attempt number `lane` (at most 32 attempts per window);
+//   3. the lanes run checkSubset (fp64 determinants, the expensive part of an attempt) on their attempts in parallel;
+//   4. the pass mask is turned into iteration numbers in order, with getSubset's bound of CV_MAX_ATTEMPTS attempts per
+//      iteration; the stream position is rewound to the end of the last attempt that was consumed.
+// ~150 cycles per attempt instead of ~3000 for a single lane walking the serial code; identical samples.
+// The points are staged in shared memory when they fit (n <= 2048).
 constexpr int K1_SMEM_PTS = 2048;
+constexpr int K1_WINDOW = 128;
 __global__ void __launch_bounds__(32)
 k_cv_sample_h(const PointH* __restrict__ pts, int n, int H_stride, int begin, int len,
               int* __restrict__ samples, RansacState* __restrict__ state, int Q) {
     __shared__ PointH sp[K1_SMEM_PTS];
-    const int q = blockIdx.x;
+    __shared__ __align__(16) int draws[K1_WINDOW];
+    const int q = blockIdx.x, lane = threadIdx.x;
     if (q >= Q) return;
     RansacState st = state[q];
     if (st.done || begin >= st.niters || st.gen < begin) return;
     const PointH* P = pts + (size_t)q * n;
     if (n <= K1_SMEM_PTS) {
-        for (int i = threadIdx.x; i < n; i += 32) sp[i] = P[i];
-        __syncwarp();
+        for (int i = lane; i < n; i += 32) sp[i] = P[i];
         P = sp;
     }
-    if (threadIdx.x != 0) return;
-    int* S = samples + (size_t)q * H_stride * 4;
-    CvRng rng;
-    rng.state = st.rng;
+    int4* S = reinterpret_cast<int4*>(samples + (size_t)q * H_stride * 4);
+    constexpr uint32_t MWC_A = 4164903690u;
+    uint64_t base = st.rng;                  // stream position at the start of the window
     const int end = min(begin + len, st.niters);
     int it = begin;
-    for (; it < end; ++it) {
-        int idx[4];
-        float ms1[8], ms2[8];
-        bool found = false;
-        for (int attempts = 0; attempts < CV_MAX_ATTEMPTS; ++attempts) {
-            for (int i = 0; i < 4; ++i) {
-                int idx_i;
-                bool dup;
-                do {
-                    idx_i = (int)(rng.next() % (uint32_t)n);
-                    dup = false;
-                    for (int t = 0; t < i; ++t) dup |= (idx[t] == idx_i);
-                } while (dup);
-                idx[i] = idx_i;
-            }
+    int ci = 0, c0 = 0, c1 = 0, c2 = 0;      // the attempt under construction (carried across windows)
+    int tries = 0;                           // attempts made for iteration `it` so far
+    bool stop = false;
+    while (!stop) {
+        // 1. the window's 128 outputs
+        uint64_t r = base;
+        uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+        for (int w = 0; w < K1_WINDOW / 4; ++w) {
+            r = (uint64_t)(uint32_t)r * MWC_A + (uint32_t)(r >> 32);
+            const uint32_t t0 = (uint32_t)r;
+            r = (uint64_t)(uint32_t)r * MWC_A + (uint32_t)(r >> 32);
+            const uint32_t t1 = (uint32_t)r;
+            r = (uint64_t)(uint32_t)r * MWC_A + (uint32_t)(r >> 32);
+            const uint32_t t2 = (uint32_t)r;
+            r = (uint64_t)(uint32_t)r * MWC_A + (uint32_t)(r >> 32);
+            const uint32_t t3 = (uint32_t)r;
+            if (w == lane) o0 = t0, o1 = t1, o2 = t2, o3 = t3;
+        }
+        __syncwarp();   // the previous window's draws have been read by every lane
+        reinterpret_cast<int4*>(draws)[lane] = make_int4((int)(o0 % (uint32_t)n), (int)(o1 % (uint32_t)n),
+                                                         (int)(o2 % (uint32_t)n), (int)(o3 % (uint32_t)n));
+        __syncwarp();
+        // 2. group the indices into attempts of four distinct ones
+        int n_att = 0, my_end = 0;
+        int4 mine = make_int4(0, 0, 0, 0);
+        for (int w = 0; w < K1_WINDOW / 4; ++w) {
+            const int4 d4 = reinterpret_cast<const int4*>(draws)[w];
+            const int dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int u = 0; u < 4; ++u) {
+                const int d = dd[u];
+                if (ci == 0) {
+                    c0 = d; ci = 1;
+                } else if (ci == 1) {
+                    if (d != c0) { c1 = d; ci = 2; }
+                } else if (ci == 2) {
+                    if (d != c0 && d != c1) { c2 = d; ci = 3; }
+                } else if (d != c0 && d != c1 && d != c2) {
+                    if (n_att == lane) { mine = make_int4(c0, c1, c2, d); my_end = 4 * w + u + 1; }
+                    ++n_att;
+                    ci = 0;
+                }
+            }
+        }
+        // 3. checkSubset, one attempt per lane
+        bool pass = false;
+        if (lane < n_att) {
+            const int idx[4] = {mine.x, mine.y, mine.z, mine.w};
+            float ms1[8], ms2[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {   // P may point to shared memory: generic loads
                 const float4 v = *reinterpret_cast<const float4*>(P + idx[k]);
                 ms1[2 * k] = v.x; ms1[2 * k + 1] = v.y; ms2[2 * k] = -v.z; ms2[2 * k + 1] = -v.w;
             }
-            if (h_check_subset4(ms1, ms2)) {
-                found = true;
+            pass = h_check_subset4(ms1, ms2);
+        }
+        const unsigned passmask = __ballot_sync(0xffffffffu, pass);
+        // 4. iterations in order
+        int consumed = -1;   // index of the attempt at which the walk ends inside this window
+        for (int a = 0; a < n_att; ++a) {
+            ++tries;
+            if ((passmask >> a) & 1u) {
+                if (lane == a) S[it] = mine;
+                ++it;
+                tries = 0;
+                if (it >= end) { consumed = a; break; }
+            } else if (tries >= CV_MAX_ATTEMPTS) {   // getSubset gives up: the RANSAC loop ends at this iteration
+                consumed = a;
                 break;
             }
         }
-        if (!found) break;
-        reinterpret_cast<int4*>(S)[it] = make_int4(idx[0], idx[1], idx[2], idx[3]);
+        if (consumed >= 0) {
+            const int steps = __shfl_sync(0xffffffffu, my_end, consumed);
+            for (int j = 0; j < steps; ++j) base = (uint64_t)(uint32_t)base * MWC_A + (uint32_t)(base >> 32);
+            stop = true;
+        } else {
+            base = r;
+        }
     }
-    st.rng = rng.state;
-    st.gen = it;
-    state[q] = st;
+    if (lane == 0) {
+        st.rng = base;
+        st.gen = it;
+        state[q] = st;
+    }
 }
 
 // ---- K2: batched 4-point solves from stored samples -------------------------------------------------------
@@ -308,6 +371,8 @@ struct HFinalizeShared {
 //   rmask      : [Q][n] RANSAC-stage mask (output)
 //   H_out      : [Q][9], mask_out : [Q][n], info : [Q] (b2r_h_info layout = 12 int32)
 //   ext_mask/ext_H : refine-only entry (b2r_refine_h): caller-supplied inlier mask and initial model
+//   models     : (optional) [Q][Hs] fp32 models as scored by K3; when given, the RANSAC-stage mask is taken with the stored
+//                winner and its fp64 form (one more 9x9 decomposition) is only recomputed if it is the returned model
 // GRID = true: ONE problem on a cooperative grid of gridDim.x CTAs (all SMs), reductions through gscratch + grid barriers
 // instead of distributed shared memory — a cluster is limited to 8 SMs, which made the passes over the points the bulk
 // of the finalize time of a large single problem.
@@ -317,7 +382,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
              const HSelect* __restrict__ sel, float thr_sq, int mask_semantics, int refine, int fast_solver,
              double* __restrict__ H_out, uint8_t* __restrict__ mask_out, uint8_t* __restrict__ rmask_out,
              int* __restrict__ info, const uint8_t* __restrict__ ext_mask, const double* __restrict__ ext_H,
-             double* __restrict__ gscratch) {
+             double* __restrict__ gscratch, const float4* __restrict__ models) {
     __shared__ HFinalizeShared sh;
     __shared__ ClusterRed R;
     __shared__ JacobiWarp9 jw;   // workspace of the warp-cooperative eigen-solver (warp 0)
@@ -348,23 +413,33 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
         return;
     }
     const int4 smp = ext_mask ? make_int4(-1, -1, -1, -1) : reinterpret_cast<const int4*>(samples)[(size_t)q * Hs + s.best];
-    if (tid < 32) {  // warp 0: the winning minimal model (every lane computes / receives the same values)
-        double Hm[9];
-        if (ext_mask) {
-            for (int i = 0; i < 9; ++i) Hm[i] = ext_H[(size_t)q * 9 + i];
-        } else {
-            const int idx[4] = {smp.x, smp.y, smp.z, smp.w};
-            float ms1[8], ms2[8];
-            gather4(P, idx, ms1, ms2);
-            if (fast_solver) h_solve4_fast(ms1, ms2, Hm); else h_solve4_warp(jw, ms1, ms2, Hm);
+    const bool stored_model = models != nullptr && !ext_mask;
+    auto minimal_model64 = [&]() {   // warp 0: the winning minimal model in fp64 (every lane computes the same values)
+        if (tid < 32) {
+            double Hm[9];
+            if (ext_mask) {
+                for (int i = 0; i < 9; ++i) Hm[i] = ext_H[(size_t)q * 9 + i];
+            } else {
+                const int idx[4] = {smp.x, smp.y, smp.z, smp.w};
+                float ms1[8], ms2[8];
+                gather4(P, idx, ms1, ms2);
+                if (fast_solver) h_solve4_fast(ms1, ms2, Hm); else h_solve4_warp(jw, ms1, ms2, Hm);
+            }
+            if (tid == 0) {
+                for (int i = 0; i < 9; ++i) sh.H[i] = Hm[i];
+                if (!stored_model)
+                    for (int i = 0; i < 8; ++i) sh.Hf[i] = (float)Hm[i];
+            }
         }
-        if (tid == 0) {
-            for (int i = 0; i < 9; ++i) sh.H[i] = Hm[i];
-            for (int i = 0; i < 8; ++i) sh.Hf[i] = (float)Hm[i];
-            sh.lm_iters = 0;
-        }
+        __syncthreads();
+    };
+    if (tid == 0) sh.lm_iters = 0;
+    if (stored_model) {
+        if (tid < 8) sh.Hf[tid] = reinterpret_cast<const float*>(models + 2 * ((size_t)q * Hs + s.best))[tid];
+        __syncthreads();
+    } else {
+        minimal_model64();
     }
-    __syncthreads();
 
     // RANSAC-stage mask with the winning minimal model
     int k_local = 0;
@@ -384,8 +459,10 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
         TEAM_REDUCE(1, 0, kv);
     }
     const int k = (int)R.out[0];
+    const bool refit = refine && n > 4 && k >= 4;
+    if (stored_model && !refit) minimal_model64();   // the minimal model is what is returned
 
-    if (refine && n > 4 && k >= 4) {
+    if (refit) {
         // ---- refit on the inliers: normalisation statistics, L^T L, eigenvector -------------------------
         HNorm nm;
         {
@@ -409,6 +486,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
         }
         const bool degenerate = fabs(nm.smx) < DBL_EPSILON || fabs(nm.smy) < DBL_EPSILON ||
                                 fabs(nm.sMx) < DBL_EPSILON || fabs(nm.sMy) < DBL_EPSILON;
+        if (degenerate && stored_model) minimal_model64();   // runKernel fails on the inliers: the LM starts from the minimal model
         if (!degenerate) {
             nm.smx = k / nm.smx; nm.smy = k / nm.smy; nm.sMx = k / nm.sMx; nm.sMy = k / nm.sMy;
             // L^T L = [[P, 0, -Px], [0, P, -Py], [-Px, -Py, Pxy]] with the 3x3 symmetric blocks
