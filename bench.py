@@ -361,6 +361,19 @@ def extras(ctx, args, rank, world, device, src, dst):
     pnp["fast"]["k3_tflops_at_26_flop_per_eval"] = pnp["fast"]["k3_evals_per_s"] * 26.0 / 1e12
     pp.free()
     out["pnp_model"] = pnp
+    # ---- homography model in parity arithmetic (OpenCV's DLT + Jacobi solver, un-fused fp32 scoring), same shape ------------------
+    prob = ctx.upload(src, dst)
+    par = ransac_b200.make_params(THR_PX, H, sampler=ransac_b200.SAMPLER_PHILOX, seed=3, arith=ransac_b200.ARITH_EXACT,
+                                  solver=ransac_b200.SOLVER_EXACT)
+    best = None
+    for _ in range(4):
+        prob.run(par)
+        prob.fetch(want_mask=False)
+        ms = prob.stage_ms()
+        best = ms if best is None or ms["total"] < best["total"] else best
+    out["h_model_exact"] = {"k3_evals_per_s": float(N) * H / (best["score"] * 1e-3), "step_evals_per_s": float(N) * H / (best["total"] * 1e-3),
+                            "stage_ms": best, "what": "bit-exact models and inlier counts for the given samples (Philox sampler)"}
+    prob.free()
     # ---- other BASELINE configs (homography model, fast arithmetic, Philox) -----------------------------------------------------
     other = {}
     for cfg, Q in ((1, 1), (4, 4096)):

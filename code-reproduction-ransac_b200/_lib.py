@@ -77,6 +77,7 @@ SIGNATURES = {
     "b2r_sample_philox": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int32, C.c_uint64, C.c_int32, C.c_int64,
                                     C.c_int32, c_i32_p]),
     "b2r_refine_h": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int32, c_u8_p, c_double_p, c_i32_p]),
+    "b2r_jacobi_eig": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, C.c_int32, C.c_int32, c_double_p, c_double_p]),
     "b2r_selftest_rcp": (C.c_int, [C.c_void_p, c_u64_p, c_u64_p]),
     "b2r_probe_fp32_peak": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     # ---- PnP path

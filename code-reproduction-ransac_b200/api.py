@@ -461,6 +461,17 @@ class Context:
                                          _ptr(H, C.c_double), C.byref(it)))
         return H.reshape(3, 3), it.value
 
+    def jacobi_eig(self, A, form=1):
+        """Eigenvalues (descending) and eigenvectors (rows) of symmetric matrices A (n_mat, n, n), 2 <= n <= 9, by the
+        eigen-solver of the exact-mode kernels (form 0 thread / 1 warp / 2 packed shared memory, n = 9)."""
+        A = np.ascontiguousarray(np.asarray(A, dtype=np.float64))
+        if A.ndim == 2:
+            A = A[None]
+        n_mat, n = A.shape[0], A.shape[1]
+        W, V = np.zeros((n_mat, n)), np.zeros((n_mat, n, n))
+        self._check(self._L.b2r_jacobi_eig(self._c, _ptr(A, C.c_double), n_mat, n, int(form), _ptr(W, C.c_double), _ptr(V, C.c_double)))
+        return W, V
+
     def selftest_rcp(self):
         bad, tested = C.c_uint64(0), C.c_uint64(0)
         self._check(self._L.b2r_selftest_rcp(self._c, C.byref(bad), C.byref(tested)))

@@ -732,7 +732,91 @@ __global__ void k_select_dummy(HSelect* sel) {
     sel[0] = s;
 }
 
+// ---- building block: the three forms of the eigen-solver on caller-supplied matrices -----------------------------------
+template <int N>
+__global__ void __launch_bounds__(64) k_jacobi_thread(const double* __restrict__ mats, int n_mat, double* __restrict__ Wout,
+                                                     double* __restrict__ Vout) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_mat) return;
+    double A[N * N], W[N], V[N * N];
+    for (int e = 0; e < N * N; ++e) A[e] = mats[(size_t)g * N * N + e];
+    jacobi_eig<N>(A, W, V);
+    for (int e = 0; e < N; ++e) Wout[(size_t)g * N + e] = W[e];
+    for (int e = 0; e < N * N; ++e) Vout[(size_t)g * N * N + e] = V[e];
+}
+
+template <int N>
+__global__ void __launch_bounds__(256) k_jacobi_warp(const double* __restrict__ mats, int n_mat, double* __restrict__ Wout,
+                                                    double* __restrict__ Vout) {
+    __shared__ JacobiWarp9 jw[8];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * 8 + w;
+    if (g >= n_mat) return;
+    for (int e = lane; e < N * N; e += 32) jw[w].A[e] = mats[(size_t)g * N * N + e];
+    __syncwarp();
+    jacobi_eig_warp2<N>(jw[w].A, jw[w].W, jw[w].V, jw[w].indR, jw[w].indC);
+    __syncwarp();
+    if (lane < N) Wout[(size_t)g * N + lane] = jw[w].W[lane];
+    for (int e = lane; e < N * N; e += 32) Vout[(size_t)g * N * N + e] = jw[w].V[e];
+}
+
+__global__ void __launch_bounds__(K2S_THREADS) k_jacobi_packed9(const double* __restrict__ mats, int n_mat,
+                                                                double* __restrict__ Wout, double* __restrict__ Vout) {
+    extern __shared__ __align__(16) double k2s_ws[];
+    const int g = blockIdx.x * K2S_THREADS + threadIdx.x;
+    if (g >= n_mat) return;
+    double* U = k2s_ws + threadIdx.x;
+    double* V = U + 45 * K2S_THREADS;
+    for (int r = 0, e = 0; r < 9; ++r)
+        for (int c = r; c < 9; ++c, ++e) U[e * K2S_THREADS] = mats[(size_t)g * 81 + r * 9 + c];
+    jacobi_eig_packed<9, K2S_THREADS>(U, V);
+    for (int r = 0; r < 9; ++r) Wout[(size_t)g * 9 + r] = U[(((r * (17 - r)) >> 1) + r) * K2S_THREADS];
+    for (int e = 0; e < 81; ++e) Vout[(size_t)g * 81 + e] = V[e * K2S_THREADS];
+}
+
+template <int N>
+static int jacobi_launch(b2r_ctx* c, int form, const double* mats, int n_mat, double* W, double* V) {
+    if (form == 0) LAUNCH(c, k_jacobi_thread<N>, (unsigned)((n_mat + 63) / 64), 64, 0, mats, n_mat, W, V);
+    else LAUNCH(c, k_jacobi_warp<N>, (unsigned)((n_mat + 7) / 8), 256, 0, mats, n_mat, W, V);
+    return B2R_OK;
+}
+
 extern "C" {
+
+int b2r_jacobi_eig(b2r_ctx* c, const double* A, int32_t n_mat, int32_t n, int32_t form, double* W_out, double* V_out) {
+    if (!c || !A || !W_out || !V_out || n_mat < 1) return fail(B2R_ERR_ARG, "null argument or no matrices%s%s");
+    if (n < 2 || n > 9 || form < 0 || form > 2 || (form == 2 && n != 9))
+        return fail(B2R_ERR_ARG, "b2r_jacobi_eig: 2 <= n <= 9, form 0..2 (form 2: n = 9 only)%s%s");
+    CU(cudaSetDevice(c->device));
+    const size_t ab = sizeof(double) * (size_t)n_mat * n * n, wb = sizeof(double) * (size_t)n_mat * n;
+    CU(c->scratch0.reserve(ab));
+    CU(c->scratch1.reserve(ab));
+    CU(c->scratch2.reserve(wb));
+    double *dA = c->scratch0.as<double>(), *dV = c->scratch1.as<double>(), *dW = c->scratch2.as<double>();
+    CU(cudaMemcpyAsync(dA, A, ab, cudaMemcpyHostToDevice, c->stream));
+    int rc = B2R_OK;
+    if (form == 2) {
+        if ((rc = k2s_prepare(c))) return rc;
+        CU(cudaFuncSetAttribute(k_jacobi_packed9, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2S_SMEM));
+        LAUNCH(c, k_jacobi_packed9, (unsigned)((n_mat + K2S_THREADS - 1) / K2S_THREADS), K2S_THREADS, K2S_SMEM, dA, n_mat, dW, dV);
+    } else {
+        switch (n) {
+            case 2: rc = jacobi_launch<2>(c, form, dA, n_mat, dW, dV); break;
+            case 3: rc = jacobi_launch<3>(c, form, dA, n_mat, dW, dV); break;
+            case 4: rc = jacobi_launch<4>(c, form, dA, n_mat, dW, dV); break;
+            case 5: rc = jacobi_launch<5>(c, form, dA, n_mat, dW, dV); break;
+            case 6: rc = jacobi_launch<6>(c, form, dA, n_mat, dW, dV); break;
+            case 7: rc = jacobi_launch<7>(c, form, dA, n_mat, dW, dV); break;
+            case 8: rc = jacobi_launch<8>(c, form, dA, n_mat, dW, dV); break;
+            default: rc = jacobi_launch<9>(c, form, dA, n_mat, dW, dV); break;
+        }
+    }
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(W_out, dW, wb, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(V_out, dV, ab, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2R_OK;
+}
 
 // refine-only entry: a finalize launch whose winning sample is replaced by a caller-supplied model and mask
 int b2r_refine_h(b2r_ctx* c, const float* src, const float* dst, int32_t n, const uint8_t* mask, double* H_io,

@@ -710,7 +710,8 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                 }
             }
             __syncthreads();
-            if (sh.need_diag == 2 && tid < 32) solve_sym_eig_warp<9>(jw, sh.A, nullptr, nullptr, sh.diag);
+            // lambda was 0 in this iteration: the step came from the eigen-decomposition of this same A (Ap = A + 0 D)
+            if (sh.need_diag == 2 && tid < 32) solve_sym_eig_warp<9>(jw, sh.A, nullptr, nullptr, sh.diag, sh.use_eig != 0);
             __syncthreads();
             if (tid == 0) {
                 if (sh.need_diag) {

@@ -469,7 +469,8 @@ __device__ void pnp_refine_lm(ClusterRed& R, PnpLsqShared& sh, JacobiWarp9& jw, 
             }
         }
         __syncthreads();
-        if (sh.need_diag && threadIdx.x < 32) solve_sym_eig_warp<6>(jw, sh.A, nullptr, nullptr, sh.diag);
+        // need_diag is only set with lambda == 0: this iteration's step came from the decomposition of this same A
+        if (sh.need_diag && threadIdx.x < 32) solve_sym_eig_warp<6>(jw, sh.A, nullptr, nullptr, sh.diag, true);
         __syncthreads();
         if (threadIdx.x == 0) {
             if (sh.need_diag) {

@@ -169,6 +169,13 @@ int b2r_sample_philox(b2r_ctx* ctx, const float* src_host, const float* dst_host
 /* K4 refinement only: refit on the masked points + LM(10).  H_io: in = RANSAC model, out = refined. */
 int b2r_refine_h(b2r_ctx* ctx, const float* src_host, const float* dst_host, int32_t n, const uint8_t* mask_host,
                  double* H_io, int32_t* lm_iters_out);
+/* The symmetric eigen-solver every exact-mode stage rests on (cv::eigen's Jacobi as calib3d calls it: runKernel's
+ * L^T L, cv::solve(DECOMP_EIG) of the LM steps), n x n with 2 <= n <= 9.  A_host (n_mat, n*n) row-major symmetric;
+ * W_out (n_mat, n) eigenvalues descending, V_out (n_mat, n*n) eigenvectors in rows.
+ * form 0: one thread per matrix in registers/local memory (reference form); 1: one warp per matrix (finalize kernels);
+ * 2: one thread per matrix on packed strided shared memory (K2 exact solver; n = 9 only).  All bit-identical. */
+int b2r_jacobi_eig(b2r_ctx* ctx, const double* A_host, int32_t n_mat, int32_t n, int32_t form, double* W_out,
+                   double* V_out);
 /* Sweeps all 2^32 bit patterns of x and compares the scoring kernel's reciprocal with IEEE 1.0f/x inside the
  * kernel's fast range; *mismatches_out must be 0. */
 int b2r_selftest_rcp(b2r_ctx* ctx, uint64_t* mismatches_out, uint64_t* tested_out);

@@ -40,6 +40,48 @@ def test_sampler_replays_cv_rng_stream(ctx, oracle, n, seed):
     np.testing.assert_array_equal(got[:k], ref["samples"])
 
 
+@pytest.mark.parametrize("n,seed", [(5, 30), (6, 31), (9, 32), (16, 33), (25, 34)])
+def test_sampler_under_heavy_rejection(ctx, oracle, n, seed):
+    """Lattice points: most 4-subsets contain three collinear points, so checkSubset rejects attempt after attempt and
+    duplicate draws are frequent (n = 5: a quarter of the last draws) — the labelling of the RNG stream into attempts and
+    iterations (warp-parallel in k_cv_sample_h) must still be OpenCV's, sample for sample."""
+    rng = np.random.default_rng(seed)
+    side = int(np.ceil(np.sqrt(n)))
+    grid = np.array([(100.0 * (i % side), 100.0 * (i // side)) for i in range(n)])
+    s = grid + rng.normal(0, 1e-3, grid.shape) * (rng.random((n, 1)) < 0.3)     # a few points slightly off the lattice
+    Hgt = np.array([[0.9, 0.05, 10.0], [-0.04, 1.1, 5.0], [1e-5, 2e-5, 1.0]])
+    hp = np.c_[s, np.ones(n)] @ Hgt.T
+    d = hp[:, :2] / hp[:, 2:]
+    bad = rng.permutation(n)[:max(2, n // 3)]                  # outliers keep the adaptive bound from ending the loop
+    d[bad] += rng.uniform(20, 60, (len(bad), 2))
+    ref = oracle.h_ransac_stage(_quant(s), _quant(d), 3.0, max_iters=200, confidence=1.0)
+    got = ctx.sample_cv(_quant(s), _quant(d), 200)
+    assert ref["iters"] == 200 and ref["draws"] > 1000         # > 5 RNG outputs per accepted subset
+    np.testing.assert_array_equal(got, ref["samples"])
+
+
+@pytest.mark.parametrize("n", [3, 6, 9])
+def test_jacobi_forms_bit_identical_to_oracle(ctx, oracle, n):
+    """cv::eigen's Jacobi as calib3d uses it (runKernel's L^T L, cv::solve(DECOMP_EIG) in the LM): the thread, warp and
+    packed-shared-memory forms return the oracle's eigenvalues and eigenvectors bit for bit, on well- and ill-conditioned
+    matrices (rank-deficient J^T J included)."""
+    rng = np.random.default_rng(40 + n)
+    mats = []
+    for t in range(96):
+        rows = n + 3 if t % 3 else n - 1                       # every third matrix is rank deficient
+        B = rng.normal(size=(rows, n)) * (10.0 ** rng.uniform(-3, 3, size=(1, n)) if t % 2 else 1.0)
+        mats.append(B.T @ B)
+    mats.append(np.diag(np.arange(n, 0, -1.0)))                # already diagonal: no rotation at all
+    mats.append(np.zeros((n, n)))
+    A = np.array(mats)
+    ref = [oracle.jacobi(a) for a in A]
+    Wr, Vr = np.array([r[0] for r in ref]), np.array([r[1] for r in ref])
+    for form in (0, 1, 2) if n == 9 else (0, 1):
+        W, V = ctx.jacobi_eig(A, form=form)
+        assert np.array_equal(W.view(np.uint64), Wr.view(np.uint64)), f"eigenvalues differ, form {form}"
+        assert np.array_equal(V.view(np.uint64), Vr.view(np.uint64)), f"eigenvectors differ, form {form}"
+
+
 @pytest.mark.parametrize("n,seed", [(12, 5), (500, 6), (5000, 7)])
 def test_solver_bit_exact_and_check_subset(ctx, oracle, n, seed):
     s, d = _problem(n, 0.3, seed)
