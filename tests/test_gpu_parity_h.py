@@ -168,6 +168,26 @@ def test_find_homography_four_points_and_errors(ctx, oracle):
     assert H is None and mask.sum() == 0
 
 
+def test_non_finite_input_terminates(ctx, oracle):
+    """NaN / inf coordinates: OpenCV's comparisons are all false on NaN, so such subsets pass checkSubset, their models
+    count no inliers and the loop runs to its bound.  The GPU path must come back (no hang in the eigen-solver or the
+    sampler) with the oracle's mask; with every point NaN there is no model."""
+    import time
+    s, d = _problem(40, 0.3, 70)
+    s2, d2 = s.copy(), d.copy()
+    s2[3] = np.nan
+    d2[7, 1] = np.inf
+    t = time.perf_counter()
+    H, mask, info = ctx.find_homography(s2, d2, 3.0, max_iters=500)
+    Hr, mr = oracle.find_homography(s2, d2, 3.0, max_iters=500)
+    assert (H is None) == (Hr is None)
+    np.testing.assert_array_equal(mask.ravel(), mr.ravel())
+    assert mask[3] == 0 and mask[7] == 0
+    Hn, maskn, _ = ctx.find_homography(np.full((12, 2), np.nan), np.full((12, 2), np.nan), 3.0, max_iters=200)
+    assert Hn is None and maskn.sum() == 0
+    assert time.perf_counter() - t < 5.0
+
+
 def test_batch_equals_singles(ctx, oracle):
     rng = np.random.default_rng(40)
     Q, n = 37, 60
