@@ -54,6 +54,27 @@ def _info_dict(i):
                 sample=[int(x) for x in i.sample], n_inliers=i.n_inliers, lm_iters=i.lm_iters)
 
 
+class _InfoSeq:
+    """The per-problem info records of a batched call (b2r_h_info / b2r_p_info array), read-only.  Behaves like the list of
+    dicts it replaces (len, indexing, iteration) but builds a dict only when one is asked for: a sweep of hundreds of
+    candidates spent more host time building dicts than the GPU spent on RANSAC.  `.status` is the vector of all statuses."""
+
+    def __init__(self, arr, to_dict):
+        self._arr, self._to_dict = arr, to_dict
+        self.status = np.frombuffer(arr, dtype=np.int32).reshape(len(arr), -1)[:, 0].copy() if len(arr) else np.zeros(0, np.int32)
+
+    def __len__(self):
+        return len(self._arr)
+
+    def __getitem__(self, q):
+        if isinstance(q, slice):
+            return [self._to_dict(self._arr[i]) for i in range(*q.indices(len(self._arr)))]
+        return self._to_dict(self._arr[q])
+
+    def __iter__(self):
+        return (self._to_dict(i) for i in self._arr)
+
+
 class HomographyProblem:
     """Q homography-RANSAC problems of n correspondences each, resident in HBM (b2r_h_problem)."""
 
@@ -116,7 +137,7 @@ class HomographyProblem:
         info = (HInfo * self.Q)()
         self.ctx._check(self.ctx._L.b2r_h_problem_fetch(self.ctx._c, self._h, _ptr(H, C.c_double),
                                                         _ptr(mask, C.c_uint8) if want_mask else None, info))
-        return H, mask, [_info_dict(i) for i in info]
+        return H, mask, _InfoSeq(info, _info_dict)
 
     def stage_ms(self):
         ms = (C.c_float * 5)()
@@ -225,7 +246,7 @@ class PnPProblem:
         self.ctx._check(self.ctx._L.b2r_p_problem_fetch(self.ctx._c, self._h, _ptr(rvec, C.c_double), _ptr(tvec, C.c_double),
                                                         _ptr(inl, C.c_int32) if want_inliers else None, _ptr(ninl, C.c_int32), info))
         lists = [inl[q, :ninl[q]].copy() for q in range(self.Q)] if want_inliers else None
-        return rvec, tvec, lists, [_p_info_dict(i) for i in info]
+        return rvec, tvec, lists, _InfoSeq(info, _p_info_dict)
 
     def stage_ms(self):
         ms = (C.c_float * 5)()
@@ -312,9 +333,8 @@ class Context:
         info = (HInfo * Q)()
         self._check(self._L.b2r_find_homography_batch(self._c, _ptr(src, C.c_double), _ptr(dst, C.c_double), 1 if shared else 0,
                                                       Q, n, C.byref(p), _ptr(H, C.c_double), _ptr(mask, C.c_uint8), info))
-        infos = [_info_dict(i) for i in info]
-        ok = np.array([i["status"] == OK for i in infos])
-        return H, ok, mask, infos
+        infos = _InfoSeq(info, _info_dict)
+        return H, infos.status == OK, mask, infos
 
     def upload(self, src, dst, dst_shared=None):
         return HomographyProblem(self, src, dst, dst_shared)
@@ -332,7 +352,7 @@ class Context:
         self._check(self._L.b2r_camera_sweep(self._c, _ptr(pos3d, C.c_double), _ptr(pixels, C.c_double), n, _ptr(cams, C.c_double), Q,
                                              C.byref(p), _ptr(scores, C.c_double), _ptr(M, C.c_double), _ptr(H, C.c_double),
                                              _ptr(mask, C.c_uint8), info, C.byref(best)))
-        return dict(scores=scores, M=M, H=H, mask=mask, infos=[_info_dict(i) for i in info], best=int(best.value))
+        return dict(scores=scores, M=M, H=H, mask=mask, infos=_InfoSeq(info, _info_dict), best=int(best.value))
 
     # ---- cv2.solvePnPRansac / solvePnPRefineLM ----------------------------------------------------------
     def solve_pnp_ransac(self, obj, img, K, iterations_count=100, reprojection_error=8.0, confidence=0.99, **kw):
@@ -370,9 +390,8 @@ class Context:
         self._check(self._L.b2r_solve_pnp_ransac_batch(self._c, _ptr(obj, C.c_double), _ptr(img, C.c_double), 1 if shared else 0,
                                                        Q, n, _ptr(Kq, C.c_double), C.byref(p), _ptr(rvec, C.c_double),
                                                        _ptr(tvec, C.c_double), _ptr(inl, C.c_int32), _ptr(ninl, C.c_int32), info))
-        infos = [_p_info_dict(i) for i in info]
-        ok = np.array([i["status"] == OK for i in infos])
-        return ok, rvec, tvec, [inl[q, :ninl[q]].copy() for q in range(Q)], infos
+        infos = _InfoSeq(info, _p_info_dict)
+        return infos.status == OK, rvec, tvec, [inl[q, :ninl[q]].copy() for q in range(Q)], infos
 
     def solve_pnp_refine_lm(self, obj, img, K, rvec, tvec, max_iters=20):
         """cv2.solvePnPRefineLM(obj, img, K, zeros, rvec, tvec) on the GPU (main_v1.py:508).  Returns (rvec (3,1), tvec (3,1), iters)."""

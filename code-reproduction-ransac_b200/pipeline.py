@@ -81,7 +81,7 @@ def find_homographies(recs, camera_locations, im=None, show=False, ransacbound=7
     if fused:
         res = ctx.camera_sweep(pos3ds[good], pixels[good], loc3ds, ransacbound, **ransac_kw)
         H, mask, infos = res["H"], res["mask"], res["infos"]
-        ok = np.array([i["status"] == api.OK for i in infos])
+        ok = infos.status == api.OK
         pos2 = None
         for i in range(Q):
             if grids[i] >= grid_code_min:
