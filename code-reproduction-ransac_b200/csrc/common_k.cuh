@@ -284,7 +284,7 @@ __device__ void solve_sym_eig(const double* A, const double* b, double* x, doubl
     }
 }
 
-// solve_sym_eig executed by ONE WARP through the warp-cooperative Jacobi (jacobi_eig_warp): same arithmetic, ~10x
+// solve_sym_eig executed by ONE WARP through the warp-cooperative Jacobi (jacobi_eig_warp2): same arithmetic, ~2x
 // less latency.  A_src, b, x, inv_diag live in shared memory; x / inv_diag may be null.
 // reuse = true: jw.W / jw.V already hold the decomposition of this matrix (the previous call's), skip the Jacobi.
 template <int N>

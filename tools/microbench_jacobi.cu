@@ -10,6 +10,121 @@
 #include <cstring>
 #include "solver_h.cuh"
 using namespace b2r;
+
+// The strided thread form as it was before jacobi_eig_packed: the serial code's loops as written (kept here as the baseline).
+namespace b2r {
+// Element e of A / V / W lives at base[e * STRIDE]: with STRIDE = threads per CTA and base = shared-memory column of the
+// calling thread, a warp's accesses hit 32 different banks whatever element each lane works on (every solve follows its
+// own pivot sequence), while per-thread local arrays of 171 doubles would overflow the L1 as soon as a few warps are
+// resident.  Operation for operation identical to jacobi_eig<N>.
+template <int N, int STRIDE>
+__device__ void jacobi_eig_strided(double* A, double* W, double* V) {
+    signed char indR[N], indC[N];
+    int i, k, l, m;
+#define AA(r, c) A[((r) * N + (c)) * STRIDE]
+#define VV(r, c) V[((r) * N + (c)) * STRIDE]
+#define WW(r) W[(r) * STRIDE]
+    for (i = 0; i < N * N; i++) V[i * STRIDE] = 0;
+    for (i = 0; i < N; i++) VV(i, i) = 1;
+    for (k = 0; k < N; k++) {
+        WW(k) = AA(k, k);
+        if (k < N - 1) {
+            double mv = fabs(AA(k, k + 1));
+            m = k + 1;
+            for (i = k + 2; i < N; i++) {
+                double val = fabs(AA(k, i));
+                if (mv < val) mv = val, m = i;
+            }
+            indR[k] = (signed char)m;
+        }
+        if (k > 0) {
+            double mv = fabs(AA(0, k));
+            m = 0;
+            for (i = 1; i < k; i++) {
+                double val = fabs(AA(i, k));
+                if (mv < val) mv = val, m = i;
+            }
+            indC[k] = (signed char)m;
+        }
+    }
+    for (int it = 0; it < N * N * 30; it++) {
+        double mv = fabs(AA(0, indR[0]));
+        k = 0;
+        for (i = 1; i < N - 1; i++) {
+            double val = fabs(AA(i, indR[i]));
+            if (mv < val) mv = val, k = i;
+        }
+        l = indR[k];
+        for (i = 1; i < N; i++) {
+            double val = fabs(AA(indC[i], i));
+            if (mv < val) mv = val, k = indC[i], l = i;
+        }
+        double p = AA(k, l);
+        if (fabs(p) <= DBL_EPSILON) break;
+        double y = (WW(l) - WW(k)) * 0.5;
+        double t = fabs(y) + cv_hypot(p, y);
+        double s = cv_hypot(p, t);
+        double c = t / s;
+        s = p / s;
+        t = (p / t) * p;
+        if (y < 0) s = -s, t = -t;
+        AA(k, l) = 0;
+        WW(k) -= t;
+        WW(l) += t;
+#define B2R_ROTS(v0, v1)             \
+    {                                \
+        double a0 = (v0), b0 = (v1); \
+        (v0) = a0 * c - b0 * s;      \
+        (v1) = a0 * s + b0 * c;      \
+    }
+        for (i = 0; i < k; i++) B2R_ROTS(AA(i, k), AA(i, l));
+        for (i = k + 1; i < l; i++) B2R_ROTS(AA(k, i), AA(i, l));
+        for (i = l + 1; i < N; i++) B2R_ROTS(AA(k, i), AA(l, i));
+        for (i = 0; i < N; i++) B2R_ROTS(VV(k, i), VV(l, i));
+#undef B2R_ROTS
+        for (int j = 0; j < 2; j++) {
+            int idx = j == 0 ? k : l;
+            if (idx < N - 1) {
+                mv = fabs(AA(idx, idx + 1));
+                m = idx + 1;
+                for (i = idx + 2; i < N; i++) {
+                    double val = fabs(AA(idx, i));
+                    if (mv < val) mv = val, m = i;
+                }
+                indR[idx] = (signed char)m;
+            }
+            if (idx > 0) {
+                mv = fabs(AA(0, idx));
+                m = 0;
+                for (i = 1; i < idx; i++) {
+                    double val = fabs(AA(i, idx));
+                    if (mv < val) mv = val, m = i;
+                }
+                indC[idx] = (signed char)m;
+            }
+        }
+    }
+    for (k = 0; k < N - 1; k++) {
+        m = k;
+        for (i = k + 1; i < N; i++)
+            if (WW(m) < WW(i)) m = i;
+        if (k != m) {
+            double tmp = WW(m);
+            WW(m) = WW(k);
+            WW(k) = tmp;
+            for (i = 0; i < N; i++) {
+                tmp = VV(m, i);
+                VV(m, i) = VV(k, i);
+                VV(k, i) = tmp;
+            }
+        }
+    }
+#undef AA
+#undef VV
+#undef WW
+}
+
+}  // namespace b2r
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
 
 // ---- dependent-chain latencies (one warp, clock64 around a chain of CH dependent operations) --------------------------
