@@ -396,7 +396,7 @@ __device__ void pnp_refine_cvlevmarq(ClusterRed& R, PnpLsqShared& sh, const PnpP
                 const double lambda = pow10[sh.lg + 16];
                 for (int i = 0; i < 36; ++i) An[i] = sh.A[i];
                 for (int a = 0; a < 6; ++a) An[a * 6 + a] *= 1. + lambda;
-                cv_solve_svd(An, sh.g, 6, 6, st);
+                cv_solve_svd<6, 6>(An, sh.g, st);
                 for (int a = 0; a < 6; ++a) sh.p[a] = sh.prev[a] - st[a];
             }
             __syncthreads();

@@ -39,7 +39,7 @@ static __device__ void rodrigues_mat2vec(const double* Rin, double* r) {
     double At[9], w[3], Vt[9], R[9];
     for (int i = 0; i < 3; i++)
         for (int k = 0; k < 3; k++) At[i * 3 + k] = Rin[k * 3 + i];
-    jacobi_svd(At, 3, w, Vt, 3, 3, 3, 3);
+    jacobi_svd<3, 3, true>(At, w, Vt);
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) {
             double acc = 0;
@@ -271,7 +271,7 @@ static __device__ bool epnp5(const double* obj, const double* img, double fu, do
                 ut[a * 12 + b] = ut[b * 12 + a] = s;  // symmetric: the transposed copy the SVD works on is the matrix itself
             }
     }
-    jacobi_svd(ut, 12, d, nullptr, 0, 12, 12, 12);
+    jacobi_svd<12, 12, false>(ut, d, nullptr);
     double L[60], rho[6];
     {
         const double* v[4] = {ut + 12 * 11, ut + 12 * 10, ut + 12 * 9, ut + 12 * 8};
@@ -309,7 +309,7 @@ static __device__ bool epnp5(const double* obj, const double* img, double fu, do
         for (int i = 0; i < 6; i++) {
             A[i * 4] = L[i * 10]; A[i * 4 + 1] = L[i * 10 + 1]; A[i * 4 + 2] = L[i * 10 + 3]; A[i * 4 + 3] = L[i * 10 + 6];
         }
-        cv_solve_svd(A, rho, 6, 4, b4);
+        cv_solve_svd<6, 4>(A, rho, b4);
         if (b4[0] < 0) {
             be[0] = sqrt(-b4[0]); be[1] = -b4[1] / be[0]; be[2] = -b4[2] / be[0]; be[3] = -b4[3] / be[0];
         } else {
@@ -323,7 +323,7 @@ static __device__ bool epnp5(const double* obj, const double* img, double fu, do
         for (int i = 0; i < 6; i++) {
             A[i * 3] = L[i * 10]; A[i * 3 + 1] = L[i * 10 + 1]; A[i * 3 + 2] = L[i * 10 + 2];
         }
-        cv_solve_svd(A, rho, 6, 3, b3);
+        cv_solve_svd<6, 3>(A, rho, b3);
         if (b3[0] < 0) {
             be[0] = sqrt(-b3[0]); be[1] = (b3[2] < 0) ? sqrt(-b3[2]) : 0.0;
         } else {
@@ -338,7 +338,7 @@ static __device__ bool epnp5(const double* obj, const double* img, double fu, do
         double A[30], b5[5], be[4];
         for (int i = 0; i < 6; i++)
             for (int j = 0; j < 5; j++) A[i * 5 + j] = L[i * 10 + j];
-        cv_solve_svd(A, rho, 6, 5, b5);
+        cv_solve_svd<6, 5>(A, rho, b5);
         if (b5[0] < 0) {
             be[0] = sqrt(-b5[0]); be[1] = (b5[2] < 0) ? sqrt(-b5[2]) : 0.0;
         } else {

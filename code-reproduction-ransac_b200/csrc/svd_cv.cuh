@@ -9,32 +9,48 @@
 
 namespace b2r {
 
-// At: n rows x m (row i = column i of A), destroyed -> rows become the left singular vectors (first n1 normalised)
-// W: n singular values, descending.  Vt: n x n right singular vectors (rows) or nullptr.
-static __device__ void jacobi_svd(double* At, int astep, double* Wout, double* Vt, int vstep, int m, int n, int n1) {
+// At: N rows x M (row i = column i of A), destroyed -> rows become the left singular vectors (normalised)
+// W: N singular values, descending.  Vt: N x N right singular vectors (rows), touched only when HAS_VT.
+// The sizes are template parameters so that every pass over the M (or N) entries of a row is unrolled: the loads of a
+// pass are independent and issue back to back, while the sums keep OpenCV's order (k ascending).  With run-time bounds
+// each of the ~66 x sweeps dot products of the 12x12 case was a chain of 12 load-then-add round trips.
+template <int M, int N, bool HAS_VT>
+static __device__ void jacobi_svd(double* At, double* Wout, double* Vt) {
+    constexpr int astep = M, vstep = N, m = M, n = N, n1 = N;
     const double minval = DBL_MIN, eps = DBL_EPSILON * 10;
-    double W[12];
+    double W[N];
     int i, j, k, iter;
-    const int max_iter = m > 30 ? m : 30;
+    constexpr int max_iter = m > 30 ? m : 30;
     double c, s, sd;
+#pragma unroll 1
     for (i = 0; i < n; i++) {
-        for (k = 0, sd = 0; k < m; k++) {
+        sd = 0;
+#pragma unroll
+        for (k = 0; k < m; k++) {
             const double t = At[i * astep + k];
             sd += t * t;
         }
         W[i] = sd;
-        if (Vt) {
+        if (HAS_VT) {
+#pragma unroll
             for (k = 0; k < n; k++) Vt[i * vstep + k] = 0;
             Vt[i * vstep + i] = 1;
         }
     }
+#pragma unroll 1
     for (iter = 0; iter < max_iter; iter++) {
         bool changed = false;
+#pragma unroll 1
         for (i = 0; i < n - 1; i++)
+#pragma unroll 1
             for (j = i + 1; j < n; j++) {
                 double *Ai = At + i * astep, *Aj = At + j * astep;
                 double a = W[i], p = 0, b = W[j];
-                for (k = 0; k < m; k++) p += Ai[k] * Aj[k];
+                double ai[M], aj[M];
+#pragma unroll
+                for (k = 0; k < m; k++) { ai[k] = Ai[k]; aj[k] = Aj[k]; }
+#pragma unroll
+                for (k = 0; k < m; k++) p += ai[k] * aj[k];
                 if (fabs(p) <= eps * sqrt(a * b)) continue;
                 p *= 2;
                 const double beta = a - b, gamma = cv_hypot(p, beta);
@@ -47,9 +63,10 @@ static __device__ void jacobi_svd(double* At, int astep, double* Wout, double* V
                     s = p / (gamma * c * 2);
                 }
                 a = b = 0;
+#pragma unroll
                 for (k = 0; k < m; k++) {
-                    const double t0 = c * Ai[k] + s * Aj[k];
-                    const double t1 = -s * Ai[k] + c * Aj[k];
+                    const double t0 = c * ai[k] + s * aj[k];
+                    const double t1 = -s * ai[k] + c * aj[k];
                     Ai[k] = t0;
                     Aj[k] = t1;
                     a += t0 * t0;
@@ -58,25 +75,29 @@ static __device__ void jacobi_svd(double* At, int astep, double* Wout, double* V
                 W[i] = a;
                 W[j] = b;
                 changed = true;
-                if (Vt) {
+                if (HAS_VT) {
                     double *Vi = Vt + i * vstep, *Vj = Vt + j * vstep;
+#pragma unroll
                     for (k = 0; k < n; k++) {
-                        const double t0 = c * Vi[k] + s * Vj[k];
-                        const double t1 = -s * Vi[k] + c * Vj[k];
-                        Vi[k] = t0;
-                        Vj[k] = t1;
+                        const double v0 = Vi[k], v1 = Vj[k];
+                        Vi[k] = c * v0 + s * v1;
+                        Vj[k] = -s * v0 + c * v1;
                     }
                 }
             }
         if (!changed) break;
     }
+#pragma unroll 1
     for (i = 0; i < n; i++) {
-        for (k = 0, sd = 0; k < m; k++) {
+        sd = 0;
+#pragma unroll
+        for (k = 0; k < m; k++) {
             const double t = At[i * astep + k];
             sd += t * t;
         }
         W[i] = sqrt(sd);
     }
+#pragma unroll 1
     for (i = 0; i < n - 1; i++) {
         j = i;
         for (k = i + 1; k < n; k++)
@@ -85,12 +106,14 @@ static __device__ void jacobi_svd(double* At, int astep, double* Wout, double* V
             double t = W[i];
             W[i] = W[j];
             W[j] = t;
+#pragma unroll
             for (k = 0; k < m; k++) {
                 t = At[i * astep + k];
                 At[i * astep + k] = At[j * astep + k];
                 At[j * astep + k] = t;
             }
-            if (Vt)
+            if (HAS_VT)
+#pragma unroll
                 for (k = 0; k < n; k++) {
                     t = Vt[i * vstep + k];
                     Vt[i * vstep + k] = Vt[j * vstep + k];
@@ -100,8 +123,10 @@ static __device__ void jacobi_svd(double* At, int astep, double* Wout, double* V
     }
     for (i = 0; i < n; i++) Wout[i] = W[i];
     unsigned long long rng = 0x12345678ull;
+#pragma unroll 1
     for (i = 0; i < n1; i++) {
         sd = i < n ? W[i] : 0;
+#pragma unroll 1
         for (int ii = 0; ii < 100 && sd <= minval; ii++) {
             // exactly-zero singular value: OpenCV builds the left vector from a +-1/m pattern of its own RNG
             const double val0 = 1. / m;
@@ -131,16 +156,19 @@ static __device__ void jacobi_svd(double* At, int astep, double* Wout, double* V
             }
         }
         s = sd > minval ? 1 / sd : 0.;
+#pragma unroll
         for (k = 0; k < m; k++) At[i * astep + k] *= s;
     }
 }
 
-// cv::solve(A (m x n), b, x, DECOMP_SVD), m <= 6, n <= 6
-static __device__ void cv_solve_svd(const double* A, const double* b, int m, int n, double* x) {
-    double At[36], w[6], Vt[36];
+// cv::solve(A (M x N), b, x, DECOMP_SVD), M <= 6, N <= 6
+template <int M, int N>
+static __device__ void cv_solve_svd(const double* A, const double* b, double* x) {
+    constexpr int m = M, n = N;
+    double At[M * N], w[N], Vt[N * N];
     for (int i = 0; i < n; i++)
         for (int k = 0; k < m; k++) At[i * m + k] = A[k * n + i];
-    jacobi_svd(At, m, w, Vt, n, m, n, n);
+    jacobi_svd<M, N, true>(At, w, Vt);
     double threshold = 0;
     for (int i = 0; i < n; i++) x[i] = 0;
     for (int i = 0; i < n; i++) threshold += w[i];
@@ -161,7 +189,7 @@ static __device__ void cv_invert3_svd(const double* A, double* inv) {
     double At[9], w[3], Vt[9];
     for (int i = 0; i < 3; i++)
         for (int k = 0; k < 3; k++) At[i * 3 + k] = A[k * 3 + i];
-    jacobi_svd(At, 3, w, Vt, 3, 3, 3, 3);
+    jacobi_svd<3, 3, true>(At, w, Vt);
     const double threshold = (w[0] + w[1] + w[2]) * (DBL_EPSILON * 2);
     for (int i = 0; i < 9; i++) inv[i] = 0;
     for (int i = 0; i < 3; i++) {
@@ -179,7 +207,7 @@ static __device__ void cv_invert3_svd(const double* A, double* inv) {
 static __device__ void cv_svd3(const double* A, double* w, double* Ut, double* Vt) {
     for (int i = 0; i < 3; i++)
         for (int k = 0; k < 3; k++) Ut[i * 3 + k] = A[k * 3 + i];
-    jacobi_svd(Ut, 3, w, Vt, 3, 3, 3, 3);
+    jacobi_svd<3, 3, true>(Ut, w, Vt);
 }
 
 }  // namespace b2r
