@@ -197,7 +197,7 @@ static int p_run_score(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p) {
     for (int begin = 0, len = 256; begin < H; begin += len, len *= 2) {
         if (len > H - begin) len = H - begin;
         CU(cudaMemsetAsync(not_done, 0, sizeof(int), c->stream));
-        LAUNCH(c, k_cv_sample_p, (unsigned)((Q + 31) / 32), 32, 0, n, H, begin, len, pr->samples.as<int>(), st, Q);
+        LAUNCH(c, k_cv_sample_p, (unsigned)Q, 32, 0, n, H, begin, len, pr->samples.as<int>(), st, Q);
         dim3 grid((unsigned)((len + 63) / 64), (unsigned)Q);
         LAUNCH(c, k_epnp_solve_p, grid, 64, 0, pr->px.as<PointPX>(), pr->pts_stride(), n, H, begin, len, (const RansacState*)st,
                pr->Kq.as<double>(), pr->centre.as<double>(), cstride, 0, 0LL, (uint64_t)0, pr->samples.as<int>(), mx, mf,

@@ -57,39 +57,86 @@ __global__ void k_pack_points_p(const double* __restrict__ obj, const double* __
 // ---- K1: samplers --------------------------------------------------------------------------------------------
 // Replay of the subsets RANSACPointSetRegistrator::getSubset draws for a callback without checkSubset
 // (SURVEY.md A.3): cv::RNG(2^64-1), `next() % n` per slot, duplicates re-drawn one at a time.  The stream depends
-// on n only; one thread per problem continues it over iterations [begin, begin+len) (clipped to the problem's current
-// iteration bound) and writes samples[q][it][0..4].
-__global__ void k_cv_sample_p(int n, int H_stride, int begin, int len, int* __restrict__ samples, RansacState* __restrict__ state,
-                              int Q) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+// on n only; one WARP per problem continues it over iterations [begin, begin+len) (clipped to the problem's current
+// iteration bound) and writes samples[q][it][0..4].  As in k_cv_sample_h the warp works on windows of 128 stream
+// outputs: every lane walks the multiply-with-carry steps, the modulo (the expensive part of a draw) is taken
+// lane-parallel, every lane walks the indices through the distinct-index state machine and lane a keeps attempt a.
+__global__ void __launch_bounds__(32)
+k_cv_sample_p(int n, int H_stride, int begin, int len, int* __restrict__ samples, RansacState* __restrict__ state, int Q) {
+    __shared__ __align__(16) int draws[128];
+    const int q = blockIdx.x, lane = threadIdx.x;
     if (q >= Q) return;
     RansacState st = state[q];
     if (st.done || begin >= st.niters || st.gen < begin) return;
     int* S = samples + (size_t)q * H_stride * PNP_MP;
-    CvRng rng;
-    rng.state = st.rng;
     const int end = min(begin + len, st.niters);
-    for (int it = begin; it < end; ++it) {
-        int idx[PNP_MP];
-        if (n > PNP_MP) {
-            for (int i = 0; i < PNP_MP; ++i) {
-                int idx_i;
-                bool dup;
-                do {
-                    idx_i = (int)(rng.next() % (uint32_t)n);
-                    dup = false;
-                    for (int t = 0; t < i; ++t) dup |= (idx[t] == idx_i);
-                } while (dup);
-                idx[i] = idx_i;
+    constexpr uint32_t MWC_A = 4164903690u;
+    uint64_t base = st.rng;
+    if (n <= PNP_MP) {   // getSubset is not called: the sample is all the points
+        for (int e = begin * PNP_MP + lane; e < end * PNP_MP; e += 32) S[e] = e % PNP_MP;
+    } else {
+        int it = begin;
+        int ci = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;   // the subset under construction (carried across windows)
+        while (it < end) {
+            uint64_t r = base;
+            uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+            for (int w = 0; w < 32; ++w) {
+                r = (uint64_t)(uint32_t)r * MWC_A + (uint32_t)(r >> 32);
+                const uint32_t t0 = (uint32_t)r;
+                r = (uint64_t)(uint32_t)r * MWC_A + (uint32_t)(r >> 32);
+                const uint32_t t1 = (uint32_t)r;
+                r = (uint64_t)(uint32_t)r * MWC_A + (uint32_t)(r >> 32);
+                const uint32_t t2 = (uint32_t)r;
+                r = (uint64_t)(uint32_t)r * MWC_A + (uint32_t)(r >> 32);
+                const uint32_t t3 = (uint32_t)r;
+                if (w == lane) o0 = t0, o1 = t1, o2 = t2, o3 = t3;
             }
-        } else {
-            for (int i = 0; i < PNP_MP; ++i) idx[i] = i;
+            __syncwarp();   // the previous window's draws have been read by every lane
+            reinterpret_cast<int4*>(draws)[lane] = make_int4((int)(o0 % (uint32_t)n), (int)(o1 % (uint32_t)n),
+                                                             (int)(o2 % (uint32_t)n), (int)(o3 % (uint32_t)n));
+            __syncwarp();
+            int n_att = 0, my_end = 0;
+            int m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0;
+            for (int w = 0; w < 32; ++w) {
+                const int4 d4 = reinterpret_cast<const int4*>(draws)[w];
+                const int dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int d = dd[u];
+                    if (ci == 0) {
+                        c0 = d; ci = 1;
+                    } else if (ci == 1) {
+                        if (d != c0) { c1 = d; ci = 2; }
+                    } else if (ci == 2) {
+                        if (d != c0 && d != c1) { c2 = d; ci = 3; }
+                    } else if (ci == 3) {
+                        if (d != c0 && d != c1 && d != c2) { c3 = d; ci = 4; }
+                    } else if (d != c0 && d != c1 && d != c2 && d != c3) {
+                        if (n_att == lane) { m0 = c0; m1 = c1; m2 = c2; m3 = c3; m4 = d; my_end = 4 * w + u + 1; }
+                        ++n_att;
+                        ci = 0;
+                    }
+                }
+            }
+            const int usable = min(n_att, end - it);   // at most 25 subsets per window
+            if (lane < usable) {
+                int* o = S + (size_t)(it + lane) * PNP_MP;
+                o[0] = m0; o[1] = m1; o[2] = m2; o[3] = m3; o[4] = m4;
+            }
+            it += usable;
+            if (it >= end) {   // the stream stops at the end of the last subset that was used
+                const int steps = __shfl_sync(0xffffffffu, my_end, usable - 1);
+                for (int j = 0; j < steps; ++j) base = (uint64_t)(uint32_t)base * MWC_A + (uint32_t)(base >> 32);
+            } else {
+                base = r;
+            }
         }
-        for (int i = 0; i < PNP_MP; ++i) S[it * PNP_MP + i] = idx[i];
     }
-    st.rng = rng.state;
-    st.gen = end;
-    state[q] = st;
+    if (lane == 0) {
+        st.rng = base;
+        st.gen = end;
+        state[q] = st;
+    }
 }
 
 // 5 distinct indices in [0, n) from two Philox blocks (same no-rejection scheme as distinct4)
