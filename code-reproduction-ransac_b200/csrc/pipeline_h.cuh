@@ -156,19 +156,18 @@ k_cv_sample_h(const PointH* __restrict__ pts, int n, int H_stride, int begin, in
             const int4 d4 = reinterpret_cast<const int4*>(draws)[w];
             const int dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 4; ++u) {   // selects only: the chain through ci is a few cycles per index
                 const int d = dd[u];
-                if (ci == 0) {
-                    c0 = d; ci = 1;
-                } else if (ci == 1) {
-                    if (d != c0) { c1 = d; ci = 2; }
-                } else if (ci == 2) {
-                    if (d != c0 && d != c1) { c2 = d; ci = 3; }
-                } else if (d != c0 && d != c1 && d != c2) {
-                    if (n_att == lane) { mine = make_int4(c0, c1, c2, d); my_end = 4 * w + u + 1; }
-                    ++n_att;
-                    ci = 0;
-                }
+                const bool fresh = !((ci > 0 && d == c0) || (ci > 1 && d == c1) || (ci > 2 && d == c2));
+                const bool complete = fresh && ci == 3;
+                const bool take = complete && n_att == lane;
+                mine = take ? make_int4(c0, c1, c2, d) : mine;
+                my_end = take ? 4 * w + u + 1 : my_end;
+                n_att += complete ? 1 : 0;
+                c0 = (fresh && ci == 0) ? d : c0;
+                c1 = (fresh && ci == 1) ? d : c1;
+                c2 = (fresh && ci == 2) ? d : c2;
+                ci = complete ? 0 : ci + (fresh ? 1 : 0);
             }
         }
         // 3. checkSubset, one attempt per lane
