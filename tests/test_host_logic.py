@@ -48,6 +48,27 @@ def test_no_cpu_fallback():
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
 
 
+def test_info_records_are_lazy_but_list_like():
+    """Batched calls hand back their per-problem info records as a sequence that builds a dict on access; it must still
+    behave like the list of dicts the callers index, slice and iterate (pipeline.py, dist.py, the tests)."""
+    from ransac_b200 import api, _lib
+    arr = (_lib.HInfo * 4)()
+    for q in range(4):
+        arr[q].status, arr[q].iters_run, arr[q].best_count = (1 if q == 2 else 0), 10 * q, q
+        for j in range(4):
+            arr[q].sample[j] = q + j
+    seq = api._InfoSeq(arr, api._info_dict)
+    assert len(seq) == 4 and seq.status.tolist() == [0, 0, 1, 0]
+    assert seq[3]["iters_run"] == 30 and seq[1]["sample"] == [1, 2, 3, 4]
+    assert [d["best_count"] for d in seq] == [0, 1, 2, 3]
+    assert [d["iters_run"] for d in seq[1:3]] == [10, 20]
+    parr = (_lib.PInfo * 2)()
+    parr[1].status, parr[1].mean_inlier_err = -3, 2.5
+    pseq = api._InfoSeq(parr, api._p_info_dict)
+    assert pseq.status.tolist() == [0, -3] and pseq[1]["mean_inlier_err"] == 2.5
+    assert len(api._InfoSeq((_lib.HInfo * 0)(), api._info_dict)) == 0
+
+
 def test_utm_transform_check_values():
     from ransac_b200 import geo
     e, n = geo.wgs84_to_utm50n(119.390036, 26.098989)           # testpro-K.py:199
