@@ -374,7 +374,9 @@ static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samp
             return B2R_OK;
         }
     }
-    const int threads = n >= 2048 ? 1024 : 128;
+    // a big batch of mid-size problems is bound by the sequential part of each problem (one thread's small linear algebra):
+    // 64-thread CTAs keep eight problems per SM in flight instead of four
+    const int threads = n >= 2048 ? 1024 : ((Q >= 4 * c->sm_count && n >= 256) ? 64 : 128);
     const int csize = n >= 32768 ? 8 : (n >= 8192 ? 2 : 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(Q * csize));
@@ -391,6 +393,9 @@ static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samp
     double* no_scratch = nullptr;
     if (threads == 1024)
         CU(cudaLaunchKernelEx(&cfg, k_finalize_h<1024, false>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
+                              mask_out, rmask_out, info, ext_mask, ext_H, no_scratch, models));
+    else if (threads == 64)
+        CU(cudaLaunchKernelEx(&cfg, k_finalize_h<64, false>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
                               mask_out, rmask_out, info, ext_mask, ext_H, no_scratch, models));
     else
         CU(cudaLaunchKernelEx(&cfg, k_finalize_h<128, false>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,

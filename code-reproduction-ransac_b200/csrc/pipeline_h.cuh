@@ -323,32 +323,36 @@ __device__ __forceinline__ float h_err_exact(const float* Hf, float X, float Y, 
 }
 
 // Eigenvector of the smallest eigenvalue of the symmetric PSD 9x9 L^T L by shifted inverse iteration
-// (fast-solver mode; the exact mode runs OpenCV's Jacobi).  false -> caller falls back to Jacobi.
-__device__ __forceinline__ bool smallest_eigvec9(const double* LtL_upper_full, double* vec) {
-    double A[81], L[81];
+// (fast-solver mode; the exact mode runs OpenCV's Jacobi).  One warp; LtL (upper triangle filled), A, L, b, x in shared
+// memory; the result is left in b.  false -> caller falls back to Jacobi.
+__device__ __forceinline__ bool smallest_eigvec9_warp(const double* LtL, double* A, double* L, double* b, double* x) {
+    const int lane = threadIdx.x & 31;
+    for (int e = lane; e < 81; e += 32) {
+        const int j = e / 9, k = e % 9;
+        A[e] = j <= k ? LtL[j * 9 + k] : LtL[k * 9 + j];
+    }
+    __syncwarp();
     double tr = 0;
-    for (int j = 0; j < 9; ++j)
-        for (int k = 0; k < 9; ++k) A[j * 9 + k] = j <= k ? LtL_upper_full[j * 9 + k] : LtL_upper_full[k * 9 + j];
     for (int j = 0; j < 9; ++j) tr += A[j * 9 + j];
     const double mu = tr * 1e-13;
-    for (int j = 0; j < 9; ++j) A[j * 9 + j] += mu;
-    if (!cholesky<9>(A, L)) return false;
-    double b[9], x[9];
-    for (int j = 0; j < 9; ++j) b[j] = 1. / 3.;
+    __syncwarp();
+    if (lane < 9) A[lane * 10] += mu;
+    __syncwarp();
+    if (!cholesky_warp<9>(A, L)) return false;
+    if (lane < 9) b[lane] = 1. / 3.;
+    __syncwarp();
     for (int it = 0; it < 16; ++it) {
-        cholesky_solve<9>(L, b, x);
+        cholesky_solve_warp<9>(L, b, x);
         double nrm = 0;
         for (int j = 0; j < 9; ++j) nrm += x[j] * x[j];
         nrm = 1. / sqrt(nrm);
         double diff = 0;
-        for (int j = 0; j < 9; ++j) {
-            const double v = x[j] * nrm;
-            diff = fmax(diff, fabs(v - b[j]));
-            b[j] = v;
-        }
+        for (int j = 0; j < 9; ++j) diff = fmax(diff, fabs(x[j] * nrm - b[j]));
+        __syncwarp();
+        if (lane < 9) b[lane] = x[lane] * nrm;
+        __syncwarp();
         if (it > 1 && diff < 1e-15) break;
     }
-    for (int j = 0; j < 9; ++j) vec[j] = b[j];
     return true;
 }
 
@@ -357,6 +361,7 @@ struct HFinalizeShared {
     double x[9], xd[9];   // LM parameter vectors (all nine entries of H, as OpenCV 4.13 refines them)
     double A[81], v[9], D[9], d[9];
     double Ap[81], diag[9];
+    double L[81];          // Cholesky factor of the damped / regularised J^T J
     double Ac[81], vc[9];  // J^T J and J^T r at the trial point (become A, v when the step is accepted)
     double S, Sd, lambda, lc, rmax, nu;
     float Hf[8];
@@ -376,7 +381,7 @@ struct HFinalizeShared {
 // instead of distributed shared memory — a cluster is limited to 8 SMs, which made the passes over the points the bulk
 // of the finalize time of a large single problem.
 template <int THREADS, bool GRID = false>
-__global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 1)   // small problems come in batches: keep 4 CTAs per SM resident
+__global__ void __launch_bounds__(THREADS, THREADS <= 64 ? 8 : (THREADS <= 128 ? 4 : 1))   // small problems come in batches: keep several CTAs per SM resident
 k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samples, int Hs,
              const HSelect* __restrict__ sel, float thr_sq, int mask_semantics, int refine, int fast_solver,
              double* __restrict__ H_out, uint8_t* __restrict__ mask_out, uint8_t* __restrict__ rmask_out,
@@ -531,14 +536,10 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                 __syncwarp();
                 double Hm[9], vec[9];
                 bool done = false;
-                if (fast_solver) {
-                    if (tid == 0) sh.flag = smallest_eigvec9(LtL, sh.diag) ? 1 : 0;
-                    __syncwarp();
-                    if (sh.flag) {
-                        for (int i = 0; i < 9; ++i) vec[i] = sh.diag[i];
-                        h_from_eigvec(vec, nm, Hm);
-                        done = true;
-                    }
+                if (fast_solver && smallest_eigvec9_warp(LtL, jw.V, sh.L, sh.diag, sh.d)) {
+                    for (int i = 0; i < 9; ++i) vec[i] = sh.diag[i];
+                    h_from_eigvec(vec, nm, Hm);
+                    done = true;
                 }
                 if (!done) h_from_LtL_warp(jw, nm, Hm);
                 if (tid == 0)
@@ -629,33 +630,34 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
             __syncthreads();
         }
         for (int iter = 0;;) {
-            if (tid == 0) {
+            if (tid < 32) {   // warp 0
                 // J^T J is singular along h itself (the projection is scale-invariant): with lambda == 0 only the
                 // eigen-decomposition solve with OpenCV's cut-off is meaningful; with lambda > 0 the matrix is SPD
                 double* Ap = sh.Ap;
-                for (int i = 0; i < 81; ++i) Ap[i] = sh.A[i];
-                for (int i = 0; i < 9; ++i) Ap[i * 9 + i] += sh.lambda * sh.D[i];
-                double dd[9], L[81];
+                const double lambda = sh.lambda;
+                for (int e = tid; e < 81; e += 32) Ap[e] = sh.A[e];
+                __syncwarp();
+                if (tid < 9) Ap[tid * 10] += lambda * sh.D[tid];
+                __syncwarp();
                 bool solved = false;
-                if (sh.lambda > 0) {
-                    solved = cholesky<9>(Ap, L);
+                if (lambda > 0) {
+                    solved = cholesky_warp<9>(Ap, sh.L);
                 } else if (fast_solver) {
                     // throughput mode: the null direction is known (n = x/|x|, J n = 0, hence n.v = 0), so the
                     // minimum-norm solution is that of the SPD system (A + s n n^T) d = v
                     double nn = 0, tr = 0;
                     for (int i = 0; i < 9; ++i) { nn += sh.x[i] * sh.x[i]; tr += sh.A[i * 9 + i]; }
                     const double sg = tr / (9 * nn);
-                    for (int i = 0; i < 9; ++i)
-                        for (int j = 0; j < 9; ++j) Ap[i * 9 + j] += sg * sh.x[i] * sh.x[j];
-                    solved = cholesky<9>(Ap, L);
-                    if (!solved)
-                        for (int i = 0; i < 81; ++i) Ap[i] = sh.A[i];
+                    for (int e = tid; e < 81; e += 32) Ap[e] += sg * sh.x[e / 9] * sh.x[e % 9];
+                    __syncwarp();
+                    solved = cholesky_warp<9>(Ap, sh.L);
+                    if (!solved) {
+                        __syncwarp();
+                        for (int e = tid; e < 81; e += 32) Ap[e] = sh.A[e];
+                    }
                 }
-                if (solved) {
-                    cholesky_solve<9>(L, sh.v, dd);
-                    for (int i = 0; i < 9; ++i) sh.d[i] = dd[i];
-                }
-                sh.use_eig = solved ? 0 : 1;
+                if (solved) cholesky_solve_warp<9>(sh.L, sh.v, sh.d);
+                if (tid == 0) sh.use_eig = solved ? 0 : 1;
             }
             __syncthreads();
             if (sh.use_eig && tid < 32) solve_sym_eig_warp<9>(jw, sh.Ap, sh.v, sh.d, nullptr);   // cv::solve(..., DECOMP_EIG)
@@ -685,28 +687,29 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     nu = fmin(fmax(nu, 2.), 10.);
                     sh.nu = nu;
                     if (sh.lambda == 0) {
-                        bool have = false;
-                        if (fast_solver) {  // diag of the pseudo-inverse = diag((A + s n n^T)^-1) - n_i^2 / s
-                            double Ar[81], L[81], nn = 0, tr = 0;
-                            for (int i = 0; i < 9; ++i) { nn += sh.x[i] * sh.x[i]; tr += sh.A[i * 9 + i]; }
-                            const double sg = tr / (9 * nn);
-                            for (int i = 0; i < 9; ++i)
-                                for (int j = 0; j < 9; ++j) Ar[i * 9 + j] = sh.A[i * 9 + j] + sg * sh.x[i] * sh.x[j];
-                            if (cholesky<9>(Ar, L)) {
-                                have = true;
-                                for (int j = 0; j < 9; ++j) {
-                                    double e[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, y[9];
-                                    e[j] = 1;
-                                    cholesky_solve<9>(L, e, y);
-                                    sh.diag[j] = y[j] - sh.x[j] * sh.x[j] / (nn * sg);
-                                }
-                            }
-                        }
-                        sh.need_diag = have ? 1 : 2;   // 2: take it from the eigen-decomposition
+                        sh.need_diag = fast_solver ? 3 : 2;   // 3: Cholesky route first (warp 0, below); 2: from the eigen-decomposition
                     } else {
                         sh.lambda *= nu;
                     }
                 }
+            }
+            __syncthreads();
+            if (sh.need_diag == 3 && tid < 32) {   // diag of the pseudo-inverse = diag((A + s n n^T)^-1) - n_i^2 / s
+                double nn = 0, tr = 0;
+                for (int i = 0; i < 9; ++i) { nn += sh.x[i] * sh.x[i]; tr += sh.A[i * 9 + i]; }
+                const double sg = tr / (9 * nn);
+                for (int e = tid; e < 81; e += 32) sh.Ap[e] = sh.A[e] + sg * sh.x[e / 9] * sh.x[e % 9];
+                __syncwarp();
+                const bool have = cholesky_warp<9>(sh.Ap, sh.L);
+                if (have)
+                    for (int j = 0; j < 9; ++j) {
+                        if (tid < 9) jw.W[tid] = tid == j ? 1. : 0.;
+                        __syncwarp();
+                        cholesky_solve_warp<9>(sh.L, jw.W, jw.V);
+                        if (tid == 0) sh.diag[j] = jw.V[j] - sh.x[j] * sh.x[j] / (nn * sg);
+                        __syncwarp();
+                    }
+                if (tid == 0) sh.need_diag = have ? 1 : 2;
             }
             __syncthreads();
             // lambda was 0 in this iteration: the step came from the eigen-decomposition of this same A (Ap = A + 0 D)
