@@ -14,6 +14,7 @@ SAMPLER_CV_REPLAY, SAMPLER_PHILOX = 0, 1
 ARITH_EXACT, ARITH_FAST = 0, 1
 MASK_CV413, MASK_LEGACY = 0, 1
 SOLVER_EXACT, SOLVER_FAST, SOLVER_EXACT_WARP = 0, 1, 2
+REFINE_NONE, REFINE_CV, REFINE_PARALLEL = 0, 1, 2
 OK, NO_MODEL = 0, 1
 
 
@@ -43,7 +44,7 @@ def make_params(thr, max_iters=2000, confidence=0.995, sampler=SAMPLER_CV_REPLAY
     p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     p.arith = int(arith)
     p.mask_semantics = int(mask_semantics)
-    p.refine = 1 if refine else 0
+    p.refine = int(refine)   # True/1: as cv2 (REFINE_CV); 2: REFINE_PARALLEL; False/0: none
     p.hyp_begin = int(hyp_begin)
     p.solver = int(solver)
     return p

@@ -145,6 +145,7 @@ static int check_params(const b2r_h_params* p) {
     if (p->arith != B2R_ARITH_EXACT && p->arith != B2R_ARITH_FAST) return fail(B2R_ERR_ARG, "bad arith%s%s");
     if (p->solver != B2R_SOLVER_EXACT && p->solver != B2R_SOLVER_FAST) return fail(B2R_ERR_ARG, "bad solver%s%s");
     if (p->max_iters > (1 << 30)) return fail(B2R_ERR_ARG, "max_iters too large%s%s");
+    if (p->refine < B2R_REFINE_NONE || p->refine > B2R_REFINE_PARALLEL) return fail(B2R_ERR_ARG, "bad refine%s%s");
     return B2R_OK;
 }
 
@@ -354,6 +355,8 @@ __global__ void k_resample_winner(const PointH* __restrict__ pts, int n, const u
 static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samples, int Hs, const HSelect* sel, float thr_sq,
                            int mask_semantics, int refine, int solver, double* H_out, uint8_t* mask_out, uint8_t* rmask_out,
                            int* info, const uint8_t* ext_mask, const double* ext_H, int Q, const float4* models = nullptr) {
+    // problems of the reference's size with the exact solver: sums in OpenCV's order, eigen-solves only (kernel comment)
+    int seq = (solver == B2R_SOLVER_EXACT && refine == B2R_REFINE_CV && n > 4 && n <= 128) ? 1 : 0;
     if (Q == 1 && n >= 32768) {
         constexpr int GT = 512;
         static thread_local int coop_ctas[16] = {0};
@@ -368,7 +371,7 @@ static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samp
             double* gs = c->gscratch.as<double>();
             void* args[] = {(void*)&pts, (void*)&n, (void*)&samples, (void*)&Hs, (void*)&sel, (void*)&thr_sq, (void*)&mask_semantics,
                             (void*)&refine, (void*)&solver, (void*)&H_out, (void*)&mask_out, (void*)&rmask_out, (void*)&info,
-                            (void*)&ext_mask, (void*)&ext_H, (void*)&gs, (void*)&models};
+                            (void*)&ext_mask, (void*)&ext_H, (void*)&gs, (void*)&models, (void*)&seq};
             CU(cudaLaunchCooperativeKernel((const void*)k_finalize_h<GT, true>, dim3((unsigned)ctas), dim3(GT), args, 0, c->stream));
             c->launches++;
             return B2R_OK;
@@ -381,7 +384,7 @@ static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samp
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(Q * csize));
     cfg.blockDim = dim3((unsigned)threads);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = seq ? sizeof(double) * 20 * (size_t)n : 0;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -393,13 +396,13 @@ static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samp
     double* no_scratch = nullptr;
     if (threads == 1024)
         CU(cudaLaunchKernelEx(&cfg, k_finalize_h<1024, false>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
-                              mask_out, rmask_out, info, ext_mask, ext_H, no_scratch, models));
+                              mask_out, rmask_out, info, ext_mask, ext_H, no_scratch, models, seq));
     else if (threads == 64)
         CU(cudaLaunchKernelEx(&cfg, k_finalize_h<64, false>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
-                              mask_out, rmask_out, info, ext_mask, ext_H, no_scratch, models));
+                              mask_out, rmask_out, info, ext_mask, ext_H, no_scratch, models, seq));
     else
         CU(cudaLaunchKernelEx(&cfg, k_finalize_h<128, false>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
-                              mask_out, rmask_out, info, ext_mask, ext_H, no_scratch, models));
+                              mask_out, rmask_out, info, ext_mask, ext_H, no_scratch, models, seq));
     c->launches++;
     return B2R_OK;
 }

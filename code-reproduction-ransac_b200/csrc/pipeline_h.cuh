@@ -375,6 +375,12 @@ struct HFinalizeShared {
 //   rmask      : [Q][n] RANSAC-stage mask (output)
 //   H_out      : [Q][9], mask_out : [Q][n], info : [Q] (b2r_h_info layout = 12 int32)
 //   ext_mask/ext_H : refine-only entry (b2r_refine_h): caller-supplied inlier mask and initial model
+//   seq        : 1 = sums in OpenCV's order (problems of n <= THREADS points, one CTA each, exact solver): the centroid and
+//                scale sums, L^T L, J^T J, J^T r and |r|^2 are accumulated point by point in index order by one thread per
+//                entry, with the products OpenCV forms, and every LM step is solved through the eigen-decomposition as
+//                cv::solve(DECOMP_EIG) does — the refined H is then bit-identical to the CPU restatement, so the
+//                ill-conditioned problems of the reference's size (12-28 points, where the early-stopped LM turns a last-bit
+//                difference into 1e-3) cannot drift.  Needs n * 20 doubles of dynamic shared memory.
 //   models     : (optional) [Q][Hs] fp32 models as scored by K3; when given, the RANSAC-stage mask is taken with the stored
 //                winner and its fp64 form (one more 9x9 decomposition) is only recomputed if it is the returned model
 // GRID = true: ONE problem on a cooperative grid of gridDim.x CTAs (all SMs), reductions through gscratch + grid barriers
@@ -386,10 +392,11 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
              const HSelect* __restrict__ sel, float thr_sq, int mask_semantics, int refine, int fast_solver,
              double* __restrict__ H_out, uint8_t* __restrict__ mask_out, uint8_t* __restrict__ rmask_out,
              int* __restrict__ info, const uint8_t* __restrict__ ext_mask, const double* __restrict__ ext_H,
-             double* __restrict__ gscratch, const float4* __restrict__ models) {
+             double* __restrict__ gscratch, const float4* __restrict__ models, int seq) {
     __shared__ HFinalizeShared sh;
     __shared__ ClusterRed R;
     __shared__ JacobiWarp9 jw;   // workspace of the warp-cooperative eigen-solver (warp 0)
+    extern __shared__ __align__(16) double seq_tab[];   // seq mode: [n][20] per-point rows (L or J: x row 9 | y row 9 | rx | ry)
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned csize = GRID ? gridDim.x : cluster.num_blocks(), crank = GRID ? blockIdx.x : cluster.block_rank();
 #define TEAM_REDUCE(NV, NMAX, arr)                                                        \
@@ -469,7 +476,34 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
     if (refit) {
         // ---- refit on the inliers: normalisation statistics, L^T L, eigenvector -------------------------
         HNorm nm;
-        {
+        if (seq) {   // one thread per sum, points in index order
+            __syncthreads();   // rmask of all points visible
+            if (tid < 4) {
+                double c = 0;
+                for (int i = 0; i < n; ++i)
+                    if (rmask[i]) {
+                        const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
+                        c += (double)(tid == 0 ? -p.z : tid == 1 ? -p.w : tid == 2 ? p.x : p.y);
+                    }
+                R.out[tid] = c;
+            }
+            __syncthreads();
+            nm.cmx = R.out[0] / k; nm.cmy = R.out[1] / k; nm.cMx = R.out[2] / k; nm.cMy = R.out[3] / k;
+            __syncthreads();
+            if (tid < 4) {
+                const double ctr = tid == 0 ? nm.cmx : tid == 1 ? nm.cmy : tid == 2 ? nm.cMx : nm.cMy;
+                double a = 0;
+                for (int i = 0; i < n; ++i)
+                    if (rmask[i]) {
+                        const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
+                        a += fabs((double)(tid == 0 ? -p.z : tid == 1 ? -p.w : tid == 2 ? p.x : p.y) - ctr);
+                    }
+                R.out[tid] = a;
+            }
+            __syncthreads();
+            nm.smx = R.out[0]; nm.smy = R.out[1]; nm.sMx = R.out[2]; nm.sMy = R.out[3];
+            __syncthreads();
+        } else {
             double c[4] = {0, 0, 0, 0};
             for (int i = gtid; i < n; i += gstride)
                 if (rmask[i]) {
@@ -496,10 +530,34 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
             // L^T L = [[P, 0, -Px], [0, P, -Py], [-Px, -Py, Pxy]] with the 3x3 symmetric blocks
             // P = sum p p^T, Px = sum x p p^T, Py = sum y p p^T, Pxy = sum (x^2+y^2) p p^T, p = (X, Y, 1):
             // 4 x 6 = 24 sums instead of the 45 entries of the upper triangle.
+            if (seq) {   // the rows of L per point, then one thread per entry of the upper triangle, points in index order
+                if (tid < n && rmask[tid]) {
+                    const float4 p = __ldg(reinterpret_cast<const float4*>(P + tid));
+                    const double x = ((double)(-p.z) - nm.cmx) * nm.smx, y = ((double)(-p.w) - nm.cmy) * nm.smy;
+                    const double X = ((double)p.x - nm.cMx) * nm.sMx, Y = ((double)p.y - nm.cMy) * nm.sMy;
+                    double* t = seq_tab + tid * 20;
+                    t[0] = X; t[1] = Y; t[2] = 1; t[3] = 0; t[4] = 0; t[5] = 0; t[6] = -x * X; t[7] = -x * Y; t[8] = -x;
+                    t[9] = 0; t[10] = 0; t[11] = 0; t[12] = X; t[13] = Y; t[14] = 1; t[15] = -y * X; t[16] = -y * Y; t[17] = -y;
+                }
+                __syncthreads();
+                if (tid < 45) {
+                    int j = 0, e = tid;
+                    while (e >= 9 - j) { e -= 9 - j; ++j; }
+                    const int kk = j + e;
+                    double acc = 0;
+                    for (int i = 0; i < n; ++i)
+                        if (rmask[i]) {
+                            const double* t = seq_tab + i * 20;
+                            acc += t[j] * t[kk] + t[9 + j] * t[9 + kk];
+                        }
+                    jw.A[j * 9 + kk] = acc;
+                }
+                __syncthreads();
+            }
             double L[24];
 #pragma unroll
             for (int j = 0; j < 24; ++j) L[j] = 0;
-            for (int i = gtid; i < n; i += gstride)
+            for (int i = gtid; i < n && !seq; i += gstride)
                 if (rmask[i]) {
                     const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
                     const double x = ((double)(-p.z) - nm.cmx) * nm.smx, y = ((double)(-p.w) - nm.cmy) * nm.smy;
@@ -514,14 +572,15 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                         L[18 + j] += r2 * pp[j];
                     }
                 }
-            TEAM_REDUCE(24, 0, L);
+            if (!seq) TEAM_REDUCE(24, 0, L);
             if (tid < 32) {  // warp 0
                 // index of (a,b), a<=b, in the packed symmetric 3x3: (0,0)=0 (0,1)=1 (0,2)=2 (1,1)=3 (1,2)=4 (2,2)=5
                 const int sym[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
                 double* LtL = jw.A;
-                for (int j = tid; j < 81; j += 32) LtL[j] = 0;
+                if (!seq)
+                    for (int j = tid; j < 81; j += 32) LtL[j] = 0;
                 __syncwarp();
-                if (tid == 0)
+                if (tid == 0 && !seq)
                     for (int a = 0; a < 3; ++a)
                         for (int b = 0; b < 3; ++b) {
                             const int e = sym[a][b];
@@ -556,7 +615,62 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
         // per-thread accumulators  S | aa (6) | xi aa (6) | yi aa (6) | (xi^2+yi^2) aa (6) | a rx (3) | a ry (3) | (xi rx + yi ry) a (3) = 34
         // One pass + ONE cluster reduction per evaluation: |r|^2, max |r_i| and the 33 sums of J^T J / J^T r together
         // (the Jacobian terms of a rejected trial point are simply discarded).  Results: return value (S, rmax), sh.Ac, sh.vc.
+        auto eval_seq = [&](const double* h) -> double2 {   // seq mode: OpenCV's products and order of summation
+            if (tid < n && rmask[tid]) {
+                const float4 p = __ldg(reinterpret_cast<const float4*>(P + tid));
+                const double Mx = (double)p.x, My = (double)p.y;
+                double ww = h[6] * Mx + h[7] * My + h[8];
+                ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
+                const double xi = (h[0] * Mx + h[1] * My + h[2]) * ww;
+                const double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
+                double* t = seq_tab + tid * 20;
+                t[0] = Mx * ww; t[1] = My * ww; t[2] = ww; t[3] = 0; t[4] = 0; t[5] = 0;
+                t[6] = -Mx * ww * xi; t[7] = -My * ww * xi; t[8] = -ww * xi;
+                t[9] = 0; t[10] = 0; t[11] = 0; t[12] = Mx * ww; t[13] = My * ww; t[14] = ww;
+                t[15] = -Mx * ww * yi; t[16] = -My * ww * yi; t[17] = -ww * yi;
+                t[18] = xi - (double)(-p.z);
+                t[19] = yi - (double)(-p.w);
+            }
+            __syncthreads();
+            if (tid < 81) {
+                const int j = tid / 9, kk = tid % 9;
+                double acc = 0;
+                for (int i = 0; i < n; ++i)
+                    if (rmask[i]) {
+                        const double* t = seq_tab + i * 20;
+                        acc += t[j] * t[kk];
+                        acc += t[9 + j] * t[9 + kk];
+                    }
+                sh.Ac[tid] = acc;
+            } else if (tid < 90) {
+                const int j = tid - 81;
+                double acc = 0;
+                for (int i = 0; i < n; ++i)
+                    if (rmask[i]) {
+                        const double* t = seq_tab + i * 20;
+                        acc += t[j] * t[18];
+                        acc += t[9 + j] * t[19];
+                    }
+                sh.vc[j] = acc;
+            } else if (tid == 90) {
+                double S = 0, rmax = 0;
+                for (int i = 0; i < n; ++i)
+                    if (rmask[i]) {
+                        const double rx = seq_tab[i * 20 + 18], ry = seq_tab[i * 20 + 19];
+                        S += rx * rx;
+                        S += ry * ry;
+                        rmax = fmax(rmax, fmax(fabs(rx), fabs(ry)));
+                    }
+                R.out[0] = S;
+                R.out[34] = rmax;
+            }
+            __syncthreads();
+            const double2 res = make_double2(R.out[0], R.out[34]);
+            __syncthreads();
+            return res;
+        };
         auto eval = [&](const double* h) -> double2 {
+            if (seq) return eval_seq(h);
             double acc[35];
 #pragma unroll
             for (int j = 0; j < 35; ++j) acc[j] = 0;
@@ -640,7 +754,9 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                 if (tid < 9) Ap[tid * 10] += lambda * sh.D[tid];
                 __syncwarp();
                 bool solved = false;
-                if (lambda > 0) {
+                if (seq) {
+                    // cv::solve(DECOMP_EIG) for every step, as OpenCV
+                } else if (lambda > 0) {
                     solved = cholesky_warp<9>(Ap, sh.L);
                 } else if (fast_solver) {
                     // throughput mode: the null direction is known (n = x/|x|, J n = 0, hence n.v = 0), so the

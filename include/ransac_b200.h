@@ -53,6 +53,11 @@ extern "C" {
 #define B2R_SOLVER_EXACT_WARP 2 /* b2r_solve_h4 only: the exact solver's one-warp-per-solve kernel (same bits; the
                                    pipeline picks it by itself for small batches, where latency matters)  */
 /* which mask cv2.findHomography returns */
+#define B2R_REFINE_NONE 0
+#define B2R_REFINE_CV 1        /* as cv2; with the exact solver and n <= 128 the sums run in OpenCV's order and every LM step is
+                                  solved by eigen-decomposition: the refined H is bit-identical to the CPU restatement   */
+#define B2R_REFINE_PARALLEL 2  /* same algorithm, parallel reductions and Cholesky for damped steps at every size (last-bit
+                                  differences; 0.2 ms less latency on a 12-point problem)                                */
 #define B2R_MASK_CV413 0  /* OpenCV 4.13: mask re-derived from the refined H   */
 #define B2R_MASK_LEGACY 1 /* older OpenCV (the reference's debug.log): RANSAC-stage mask */
 
@@ -66,7 +71,7 @@ typedef struct {
     uint64_t seed;       /* Philox key (ignored for CV_REPLAY, whose seed OpenCV fixes at 2^64-1)            */
     int32_t arith;       /* B2R_ARITH_*                                                                      */
     int32_t mask_semantics; /* B2R_MASK_*                                                                    */
-    int32_t refine;      /* 1: refit on inliers + 10 Levenberg-Marquardt iterations, as cv2 does; 0: skip    */
+    int32_t refine;      /* B2R_REFINE_* : 1 refit on inliers + 10 Levenberg-Marquardt iterations, as cv2 does; 0 skip */
     /* hypothesis-id shard of this rank (PHILOX only): ids [hyp_begin, hyp_begin + max_iters) are scored.   */
     int64_t hyp_begin;
     int32_t solver;      /* B2R_SOLVER_*                                                                     */

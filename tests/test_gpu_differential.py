@@ -41,8 +41,12 @@ def test_homography_batches_of_messy_problems(ctx, oracle, n, Q, seed):
         n_model += 1
         assert infos[q]["iters_run"] == det["iters"], q
         np.testing.assert_array_equal(mask_legacy[q], det["ransac_mask"])            # RANSAC stage: bit-exact
-        # the refined H of a tiny / degenerate inlier set is ill-conditioned: compare where the oracle's own LM is stable
-        if np.abs(H[q] - Hr).max() / np.abs(Hr).max() < 1e-6:
+        # the refined H of a tiny / degenerate inlier set is ill-conditioned (the early-stopped LM amplifies last bits), which
+        # is why the refinement of problems this small is summed in OpenCV's order: H and the final mask are bit-identical
+        if n <= 128:
+            np.testing.assert_array_equal(H[q], Hr)
+            np.testing.assert_array_equal(mask[q], mr.ravel())
+        elif np.abs(H[q] - Hr).max() / np.abs(Hr).max() < 1e-6:
             np.testing.assert_array_equal(mask[q], mr.ravel())
     assert n_model > Q // 3
 

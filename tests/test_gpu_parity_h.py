@@ -149,6 +149,11 @@ def test_find_homography_matches_oracle(ctx, oracle, n, outliers, thr, seed):
     assert info["best_count"] == int(det["ransac_mask"].sum())
     np.testing.assert_array_equal(mask, mr)  # final (4.13) mask: identical index set
     assert np.abs(H - Hr).max() / np.abs(Hr).max() < REL_H_TOL
+    if n <= 128:   # the reference's problem sizes: refinement summed in OpenCV's order, bit-identical H
+        np.testing.assert_array_equal(H, Hr)
+        Hp, maskp, _ = ctx.find_homography(s, d, thr, refine=ransac_b200.REFINE_PARALLEL)
+        np.testing.assert_array_equal(maskp, mr)
+        assert np.abs(Hp - Hr).max() / np.abs(Hr).max() < REL_H_TOL
     # legacy semantics return the RANSAC-stage mask
     _, mask_l, _ = ctx.find_homography(s, d, thr, mask_semantics=ransac_b200.MASK_LEGACY)
     np.testing.assert_array_equal(mask_l.ravel(), det["ransac_mask"])
