@@ -9,7 +9,7 @@ from ransac_b200 import synth
 seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 rng = np.random.default_rng(seed)
 ctx = ransac_b200.Context(0)
-stats = dict(h_problems=0, h_stage_mismatch=0, h_iters_mismatch=0, h_final_mask_mismatch=0, h_H_worst=0.0, h_none=0,
+stats = dict(h_problems=0, h_stage_mismatch=0, h_iters_mismatch=0, h_final_mask_mismatch=0, h_H_worst=0.0, h_none=0, h_small=0, h_small_bit_equal=0,
              p_problems=0, p_inlier_mismatch=0, p_iters_mismatch=0, p_ok_mismatch=0, p_pose_worst=0.0, p_none=0)
 t0 = time.time()
 for batch in range(40):
@@ -35,6 +35,9 @@ for batch in range(40):
         stats["h_iters_mismatch"] += infos[q]["iters_run"] != det["iters"]
         stats["h_stage_mismatch"] += not np.array_equal(ml[q], det["ransac_mask"])
         rel = float(np.abs(H[q] - Hr).max() / np.abs(Hr).max())
+        if n <= 128:   # refinement summed in OpenCV's order: the refined H must be the oracle's, bit for bit
+            stats["h_small"] += 1
+            stats["h_small_bit_equal"] += int(np.array_equal(H[q], Hr))
         if rel < 1e-6:
             stats["h_final_mask_mismatch"] += not np.array_equal(mask[q], mr.ravel())
         stats["h_H_worst"] = max(stats["h_H_worst"], rel)
