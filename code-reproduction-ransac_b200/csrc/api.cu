@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(256) k_jacobi_warp(const double* __restrict__ 
     if (g >= n_mat) return;
     for (int e = lane; e < N * N; e += 32) jw[w].A[e] = mats[(size_t)g * N * N + e];
     __syncwarp();
-    jacobi_eig_warp2<N>(jw[w].A, jw[w].W, jw[w].V, jw[w].indR, jw[w].indC);
+    jacobi_eig_warp3<N>(jw[w].A, jw[w].W, jw[w].V, jw[w].indR, jw[w].indC);
     __syncwarp();
     if (lane < N) Wout[(size_t)g * N + lane] = jw[w].W[lane];
     for (int e = lane; e < N * N; e += 32) Vout[(size_t)g * N * N + e] = jw[w].V[e];

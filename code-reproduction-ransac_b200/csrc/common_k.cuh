@@ -284,7 +284,7 @@ __device__ void solve_sym_eig(const double* A, const double* b, double* x, doubl
     }
 }
 
-// solve_sym_eig executed by ONE WARP through the warp-cooperative Jacobi (jacobi_eig_warp2): same arithmetic, ~2x
+// solve_sym_eig executed by ONE WARP through the warp-cooperative Jacobi (jacobi_eig_warp3): same arithmetic, ~2.5x
 // less latency.  A_src, b, x, inv_diag live in shared memory; x / inv_diag may be null.
 // reuse = true: jw.W / jw.V already hold the decomposition of this matrix (the previous call's), skip the Jacobi.
 template <int N>
@@ -294,7 +294,7 @@ __device__ void solve_sym_eig_warp(JacobiWarp9& jw, const double* A_src, const d
     if (!reuse) {
         for (int e = lane; e < N * N; e += 32) jw.A[e] = A_src[e];
         __syncwarp();
-        jacobi_eig_warp2<N>(jw.A, jw.W, jw.V, jw.indR, jw.indC);
+        jacobi_eig_warp3<N>(jw.A, jw.W, jw.V, jw.indR, jw.indC);
     }
     double thr = 0;
     for (int i = 0; i < N; ++i) thr += fabs(jw.W[i]);

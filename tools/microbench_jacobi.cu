@@ -124,6 +124,157 @@ __device__ void jacobi_eig_strided(double* A, double* W, double* V) {
 #undef WW
 }
 
+
+// The intermediate warp form (lane-parallel searches through shared-memory index arrays), kept as a baseline.
+// The same decomposition with the two index searches spread over the lanes.  Per rotation the form above walks 16 pivot
+// candidates and up to 8 entries per refreshed indR/indC one compare after another, and its rotation step is a chain
+// of branches; measured on a B200 (tools/microbench_jacobi.cu) a rotation costs ~3000 cycles of which the fp64
+// div/sqrt chain that cannot be shortened is ~650.  Here
+//   * the 2(N-1) pivot candidates sit on lanes 0..2N-3 in OpenCV's visiting order and the winner is the LOWEST lane
+//     holding the maximum |value| (the serial loop replaces its maximum only on a strictly greater value), found with
+//     two 32-bit warp max-reductions over the bit pattern of |value| (non-negative doubles order like integers);
+//   * the four refreshed entries indR[k], indC[k], indR[l], indC[l] are searched by four groups of eight lanes with a
+//     three-step butterfly and the same lowest-index tie rule;
+//   * lanes 0..N-1 rotate A, lanes 16..16+N-1 rotate V, lane 31 updates W — one select-addressed code path.
+// Every element still goes through the same IEEE operations: bit-identical to jacobi_eig<N> for finite matrices; a
+// matrix with a non-finite entry (never produced from finite correspondences) is sent through jacobi_eig_warp.
+template <int N>
+__device__ void jacobi_eig_warp2(double* A, double* W, double* V, int* indR, int* indC) {
+    static_assert(N >= 2 && N <= 9, "lane layout: 2(N-1) <= 16 pivot candidates, 8-lane search groups");
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    {
+        bool finite = true;
+        for (int e = lane; e < N * N; e += 32) finite = finite && fabs(A[e]) <= DBL_MAX;
+        if (!__all_sync(FULL, finite)) {
+            jacobi_eig_warp<N>(A, W, V, indR, indC);
+            return;
+        }
+    }
+    for (int e = lane; e < N * N; e += 32) V[e] = (e / N == e % N) ? 1. : 0.;
+    if (lane < N) {
+        const int k = lane;
+        W[k] = A[k * N + k];
+        if (k < N - 1) {
+            double mv = fabs(A[k * N + k + 1]);
+            int m = k + 1;
+            for (int i = k + 2; i < N; i++) {
+                const double val = fabs(A[k * N + i]);
+                if (mv < val) mv = val, m = i;
+            }
+            indR[k] = m;
+        }
+        if (k > 0) {
+            double mv = fabs(A[k]);
+            int m = 0;
+            for (int i = 1; i < k; i++) {
+                const double val = fabs(A[i * N + k]);
+                if (mv < val) mv = val, m = i;
+            }
+            indC[k] = m;
+        }
+    }
+    __syncwarp();
+    // fixed roles of this lane
+    const bool row_cand = lane < N - 1, col_cand = lane >= N - 1 && lane < 2 * (N - 1);
+    const int cand_i = col_cand ? lane - (N - 2) : (row_cand ? lane : 0);
+    const int* cand_ind = col_cand ? indC + cand_i : indR + cand_i;
+    const bool rot_v = lane >= 16;
+    const int rot_i = lane & 15;
+    double* rot_base = rot_v ? V : A;
+    const int grp = lane >> 3, gj = lane & 7;
+    const bool srch_row = (grp & 1) == 0;
+    for (int it = 0; it < N * N * 30; it++) {
+        // ---- pivot ----
+        const int other = *cand_ind;
+        const int ck = col_cand ? other : cand_i, cl = col_cand ? cand_i : other;
+        double cval = fabs(A[ck * N + cl]);
+        if (!(row_cand || col_cand)) cval = 0.;
+        const unsigned hi = (unsigned)__double2hiint(cval), lo = (unsigned)__double2loint(cval);
+        const unsigned mh = __reduce_max_sync(FULL, hi);
+        const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+        const int win = __ffs(__ballot_sync(FULL, hi == mh && lo == ml)) - 1;
+        const int kl = __shfl_sync(FULL, ck | (cl << 8), win);
+        const int k = kl & 255, l = kl >> 8;
+        const double p = A[k * N + l], Wk = W[k], Wl = W[l];
+        if (__all_sync(FULL, fabs(p) <= DBL_EPSILON)) break;
+        // jacobi_rotation() with the two quotients by hypot(p, t) taken on different lanes (one division latency)
+        const double y = (Wl - Wk) * 0.5;
+        const double tt = fabs(y) + cv_hypot(p, y);
+        const double q = fabs(p) / tt;               // |p| <= tt
+        const double sh = tt * sqrt(1 + q * q);
+        const double quo = ((lane & 1) ? p : tt) / sh;
+        const double c = __shfl_sync(FULL, quo, 0);
+        double s = __shfl_sync(FULL, quo, 1);
+        double t = copysign(q, p) * p;
+        if (y < 0) s = -s, t = -t;
+        __syncwarp();  // all lanes have read A[k][l], W[k], W[l]
+        // ---- rotation ----
+        {
+            const int i = rot_i;
+            int e0 = k * N + i, e1 = l * N + i;
+            if (!rot_v) {
+                if (i < k) e0 = i * N + k;
+                if (i < l) e1 = i * N + l;
+            }
+            const bool act = rot_v ? i < N : (i < N && i != k && i != l);
+            if (act) {
+                const double a0 = rot_base[e0], b0 = rot_base[e1];
+                rot_base[e0] = a0 * c - b0 * s;
+                rot_base[e1] = a0 * s + b0 * c;
+            }
+            if (lane == 31) {
+                A[k * N + l] = 0;
+                W[k] = Wk - t;
+                W[l] = Wl + t;
+            }
+        }
+        __syncwarp();
+        // ---- indR[k], indC[k], indR[l], indC[l] ----
+        {
+            const int idx = grp < 2 ? k : l;
+            const int cand = srch_row ? idx + 1 + gj : gj;
+            const bool valid = srch_row ? cand < N : cand < idx;
+            long long key = -1ll;
+            if (valid) key = __double_as_longlong(fabs(srch_row ? A[idx * N + cand] : A[cand * N + idx]));
+            long long gmax = key;
+#pragma unroll
+            for (int sft = 1; sft < 8; sft <<= 1) {
+                const long long o = __shfl_xor_sync(FULL, gmax, sft);
+                gmax = o > gmax ? o : gmax;
+            }
+            const unsigned eq = __ballot_sync(FULL, valid && key == gmax);
+            const int jwin = __ffs((eq >> (grp * 8)) & 255u) - 1;
+            if (gj == 0 && jwin >= 0) {
+                if (srch_row) indR[idx] = idx + 1 + jwin;
+                else indC[idx] = jwin;
+            }
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    // eigenvalues descending, rows of V alongside
+    for (int k = 0; k < N - 1; k++) {
+        int m = k;
+        for (int i = k + 1; i < N; i++)
+            if (W[m] < W[i]) m = i;
+        __syncwarp();
+        if (k != m) {
+            if (lane == 0) {
+                const double tmp = W[m];
+                W[m] = W[k];
+                W[k] = tmp;
+            }
+            if (lane < N) {
+                const double tmp = V[m * N + lane];
+                V[m * N + lane] = V[k * N + lane];
+                V[k * N + lane] = tmp;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace b2r
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
 
@@ -393,6 +544,217 @@ __global__ void k_warp2_prof(const double* Ain, double* Wout, Prof* pf) {
     if (threadIdx.x < 9) Wout[threadIdx.x] = jw.W[threadIdx.x];
 }
 
+// the register-resident form with timers (generated copy of jacobi_eig_warp3)
+template <int N>
+__device__ void jacobi_eig_warp3_prof(double* A, double* W, double* V, int* indR, int* indC, Prof* pf) {
+    static_assert(N >= 2 && N <= 9, "lane layout");
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int BIG = 0x7fffffff;
+    const int lane = threadIdx.x & 31;
+    {
+        bool finite = true;
+        for (int e = lane; e < N * N; e += 32) finite = finite && fabs(A[e]) <= DBL_MAX;
+        if (!__all_sync(FULL, finite)) {
+            jacobi_eig_warp<N>(A, W, V, indR, indC);
+            return;
+        }
+    }
+    for (int e = lane; e < N * N; e += 32) V[e] = (e / N == e % N) ? 1. : 0.;
+    const bool alane = lane < N;
+    const int i = alane ? lane : 0;
+    const bool vlane = lane >= 16 && lane < 16 + N;
+    const int vi = lane - 16;
+    double Wreg = A[i * N + i];
+    // own candidates: first maximal |A[i][j]|, j > i, and first maximal |A[j][i]|, j < i
+    int ind_r = 0, ind_c = 0;
+    double val_r = 0, val_c = 0;
+    bool ok_r = alane && i < N - 1, ok_c = alane && i > 0;
+    if (ok_r) {
+        double mv = fabs(A[i * N + i + 1]);
+        ind_r = i + 1;
+        for (int j = i + 2; j < N; j++) {
+            const double v = fabs(A[i * N + j]);
+            if (mv < v) mv = v, ind_r = j;
+        }
+        val_r = A[i * N + ind_r];
+    }
+    if (ok_c) {
+        double mv = fabs(A[i]);
+        ind_c = 0;
+        for (int j = 1; j < i; j++) {
+            const double v = fabs(A[j * N + i]);
+            if (mv < v) mv = v, ind_c = j;
+        }
+        val_c = A[ind_c * N + i];
+    }
+    __syncwarp();
+    bool have_grp = false;          // the previous rotation's pair elements stand for its four refreshed candidates
+    int gk = 0, gl = 0;             // ... its pivot
+    double na0 = 0, nb0 = 0;        // ... this lane's new (i, gk) and (i, gl) elements
+    bool pend = false;              // refreshed candidates of the rotation before, to be installed on lanes pk, pl
+    int pk = 0, pl = 0, rR_k = -1, rC_k = -1, rR_l = -1, rC_l = -1;
+    double vR_k = 0, vC_k = 0, vR_l = 0, vC_l = 0;
+
+    long long c_p = 0, c_a = 0, c_r = 0, c_i = 0; const long long tstart = clock64(); int it;
+    for (it = 0; it < N * N * 30; it++) {
+        const long long t0 = clock64();
+        // ---- install the candidates refreshed one rotation ago, then account for the last rotation ----
+        if (pend) {
+            if (alane && i == pk) { ind_r = rR_k; val_r = vR_k; ok_r = rR_k >= 0; ind_c = rC_k; val_c = vC_k; ok_c = rC_k >= 0; }
+            if (alane && i == pl) { ind_r = rR_l; val_r = vR_l; ok_r = rR_l >= 0; ind_c = rC_l; val_c = vC_l; ok_c = rC_l >= 0; }
+        }
+        if (have_grp) {
+            if (i == gk || i == gl) {
+                ok_r = false;
+                ok_c = false;
+            } else {
+                if (ok_r) val_r = ind_r == gk ? na0 : (ind_r == gl ? nb0 : val_r);
+                if (ok_c) val_c = ind_c == gk ? na0 : (ind_c == gl ? nb0 : val_c);
+            }
+        }
+        // ---- pivot: best of this lane's entries, then best of the warp ----
+        // four entries per lane at most; keys = bit pattern of |value| (-1: no entry), ties to the lower visiting order
+        const bool g_a = have_grp && alane && i != gk, g_b = have_grp && alane && i != gl;
+        const long long k1 = ok_r ? __double_as_longlong(fabs(val_r)) : -1ll, k2 = ok_c ? __double_as_longlong(fabs(val_c)) : -1ll;
+        const long long k3 = g_a ? __double_as_longlong(fabs(na0)) : -1ll, k4 = g_b ? __double_as_longlong(fabs(nb0)) : -1ll;
+        const int o1 = i * 16, o2 = (N - 2 + i) * 16;
+        const int o3 = (i > gk ? gk : N - 2 + gk) * 16 + i, o4 = (i > gl ? gl : N - 2 + gl) * 16 + i;
+        const int kl1 = i | (ind_r << 8), kl2 = ind_c | (i << 8);
+        const int kl3 = i > gk ? (gk | (i << 8)) : (i | (gk << 8)), kl4 = i > gl ? (gl | (i << 8)) : (i | (gl << 8));
+        const bool s12 = k2 > k1 || (k2 == k1 && o2 < o1);      // entry 2 beats entry 1
+        const bool s34 = k4 > k3 || (k4 == k3 && o4 < o3);
+        const long long ka = s12 ? k2 : k1, kb = s34 ? k4 : k3;
+        const int oa = s12 ? o2 : o1, ob = s34 ? o4 : o3;
+        const double va = s12 ? val_c : val_r, vb = s34 ? nb0 : na0;
+        const int kla = s12 ? kl2 : kl1, klb = s34 ? kl4 : kl3;
+        const bool sab = kb > ka || (kb == ka && ob < oa);
+        const long long kbest = sab ? kb : ka;
+        const double bv = sab ? vb : va;
+        const int bo = kbest < 0 ? BIG : (sab ? ob : oa), bkl = sab ? klb : kla;
+        const bool any = bo != BIG;
+        const double abv = fabs(bv);
+        const unsigned hi = any ? (unsigned)__double2hiint(abv) : 0u, lo = any ? (unsigned)__double2loint(abv) : 0u;
+        const unsigned mh = __reduce_max_sync(FULL, hi);
+        const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+        const bool holder = any && hi == mh && lo == ml;
+        const int mo = __reduce_min_sync(FULL, holder ? bo : BIG);
+        const int win = __ffs(__ballot_sync(FULL, holder && bo == mo)) - 1;
+        const int kl = __shfl_sync(FULL, bkl, win);
+        const double p = __shfl_sync(FULL, bv, win);
+        const int k = kl & 255, l = kl >> 8;
+        if (fabs(p) <= DBL_EPSILON) break;
+        const double Wk = __shfl_sync(FULL, Wreg, k), Wl = __shfl_sync(FULL, Wreg, l);
+        const long long t1 = clock64() + (long long)(Wk == 1.2345e-300 ? 1 : 0);
+        // ---- operands of the rotation (shared memory is current: barrier at the end of the previous rotation) ----
+        const bool rot_a = alane && i != k && i != l;
+        int e0 = k * N + i, e1 = l * N + i;
+        if (alane) {
+            if (i < k) e0 = i * N + k;
+            if (i < l) e1 = i * N + l;
+        } else if (vlane) {
+            e0 = k * N + vi;
+            e1 = l * N + vi;
+        }
+        double a0 = 0, b0 = 0;
+        if (rot_a) { a0 = A[e0]; b0 = A[e1]; }
+        if (vlane) { a0 = V[e0]; b0 = V[e1]; }
+        const long long t2 = clock64() + (long long)(a0 == 1.2345e-300 ? 1 : 0);
+        // ---- rotation parameters (jacobi_rotation with the two quotients by hypot(p, t) on different lanes), and, in the
+        // issue slots its three divisions and two square roots leave idle, the indices refreshed by the PREVIOUS rotation:
+        // four groups — row gk (i > gk) and column gk (i < gk) over the (i, gk) elements, row gl and column gl over the
+        // (i, gl) ones; first maximum = lowest lane.  The stages are placed between the long operations by hand: the
+        // compiler does not move instructions across the slow-path branches of a division.
+        const bool in_rk = alane && i > gk, in_ck = alane && i < gk, in_rl = alane && i > gl, in_cl = alane && i < gl;
+        const double aa = fabs(na0), ab = fabs(nb0);
+        const unsigned ha = (unsigned)__double2hiint(aa), la = (unsigned)__double2loint(aa);
+        const unsigned hb = (unsigned)__double2hiint(ab), lb = (unsigned)__double2loint(ab);
+        const double y = (Wl - Wk) * 0.5;
+        const double ap = fabs(p), ay = fabs(y);
+        const bool p_big = ap > ay;
+        const double big1 = p_big ? ap : ay, small1 = p_big ? ay : ap;
+        // stage 1: high words
+        const unsigned h_rk = __reduce_max_sync(FULL, in_rk ? ha : 0u), h_ck = __reduce_max_sync(FULL, in_ck ? ha : 0u);
+        const unsigned h_rl = __reduce_max_sync(FULL, in_rl ? hb : 0u), h_cl = __reduce_max_sync(FULL, in_cl ? hb : 0u);
+        const double q1 = small1 / big1;                           // cv_hypot(p, y), written out
+        // stage 2: low words among the holders of the maximal high word
+        const unsigned l_rk = __reduce_max_sync(FULL, in_rk && ha == h_rk ? la : 0u), l_ck = __reduce_max_sync(FULL, in_ck && ha == h_ck ? la : 0u);
+        const unsigned l_rl = __reduce_max_sync(FULL, in_rl && hb == h_rl ? lb : 0u), l_cl = __reduce_max_sync(FULL, in_cl && hb == h_cl ? lb : 0u);
+        const double r1 = big1 * sqrt(1 + q1 * q1);
+        const double hyp1 = (p_big || ay > 0) ? r1 : 0.;
+        const double tt = ay + hyp1;
+        // stage 3: lowest holder of each group
+        const int w_rk = __ffs(__ballot_sync(FULL, in_rk && ha == h_rk && la == l_rk)) - 1;
+        const int w_ck = __ffs(__ballot_sync(FULL, in_ck && ha == h_ck && la == l_ck)) - 1;
+        const int w_rl = __ffs(__ballot_sync(FULL, in_rl && hb == h_rl && lb == l_rl)) - 1;
+        const int w_cl = __ffs(__ballot_sync(FULL, in_cl && hb == h_cl && lb == l_cl)) - 1;
+        const double q = ap / tt;                                  // |p| <= tt: hypot(p, tt) takes this case
+        // stage 4: the winners' values
+        const double x_rk = __shfl_sync(FULL, na0, w_rk < 0 ? 0 : w_rk), x_ck = __shfl_sync(FULL, na0, w_ck < 0 ? 0 : w_ck);
+        const double x_rl = __shfl_sync(FULL, nb0, w_rl < 0 ? 0 : w_rl), x_cl = __shfl_sync(FULL, nb0, w_cl < 0 ? 0 : w_cl);
+        const double sh = tt * sqrt(1 + q * q);
+        if (have_grp) {
+            rR_k = w_rk; rC_k = w_ck; rR_l = w_rl; rC_l = w_cl;
+            vR_k = x_rk; vC_k = x_ck; vR_l = x_rl; vC_l = x_cl;
+            pk = gk;
+            pl = gl;
+            pend = true;
+        }
+        const double quo = ((lane & 1) ? p : tt) / sh;
+        const double c = __shfl_sync(FULL, quo, 0);
+        double sn = __shfl_sync(FULL, quo, 1);
+        double t = copysign(q, p) * p;
+        if (y < 0) sn = -sn, t = -t;
+        const long long t3 = clock64() + (long long)(c == 1.2345e-300 ? 1 : 0) + (long long)(t == 1.2345e-300 ? 1 : 0);
+        // ---- rotate ----
+        const double n0 = a0 * c - b0 * sn, n1 = a0 * sn + b0 * c;
+        if (rot_a) { A[e0] = n0; A[e1] = n1; }
+        if (vlane) { V[e0] = n0; V[e1] = n1; }
+        na0 = n0;
+        nb0 = n1;
+        if (alane && i == k) { Wreg = Wreg - t; nb0 = 0; A[k * N + l] = 0; }   // A[k][l] = 0 belongs to column l's group
+        if (alane && i == l) { Wreg = Wreg + t; na0 = 0; }                      // ... and to row k's
+        gk = k;
+        gl = l;
+        have_grp = true;
+        __syncwarp();
+        const long long t4 = clock64();
+        c_p += t1 - t0; c_i += t2 - t1; c_a += t3 - t2; c_r += t4 - t3;
+    }
+    if (lane == 0) { pf->pivot = c_p; pf->arith = c_a; pf->rotate = c_r; pf->ind = c_i; pf->rotations = it; pf->total = clock64() - tstart; }
+    if (alane) W[i] = Wreg;
+    __syncwarp();
+    // eigenvalues descending, rows of V alongside
+    for (int k = 0; k < N - 1; k++) {
+        int m = k;
+        for (int j = k + 1; j < N; j++)
+            if (W[m] < W[j]) m = j;
+        __syncwarp();
+        if (k != m) {
+            if (lane == 0) {
+                const double tmp = W[m];
+                W[m] = W[k];
+                W[k] = tmp;
+            }
+            if (lane < N) {
+                const double tmp = V[m * N + lane];
+                V[m * N + lane] = V[k * N + lane];
+                V[k * N + lane] = tmp;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+
+__global__ void k_warp3_prof(const double* Ain, double* Wout, Prof* pf) {
+    __shared__ JacobiWarp9 jw;
+    for (int e = threadIdx.x; e < 81; e += 32) jw.A[e] = Ain[e];
+    __syncwarp();
+    jacobi_eig_warp3_prof<9>(jw.A, jw.W, jw.V, jw.indR, jw.indC, pf);
+    __syncwarp();
+    if (threadIdx.x < 9) Wout[threadIdx.x] = jw.W[threadIdx.x];
+}
+
 __global__ void k_warp_prof(const double* Ain, double* Wout, Prof* pf) {
     __shared__ JacobiWarp9 jw;
     for (int e = threadIdx.x; e < 81; e += 32) jw.A[e] = Ain[e];
@@ -443,6 +805,19 @@ __global__ void __launch_bounds__(32) k_thread2(const double* mats, int nmat, do
         for (int r = 0; r < 9; ++r) Wout[(size_t)g * 9 + r] = U[(((r * (17 - r)) >> 1) + r) * 32];
         for (int e = 0; e < 81; ++e) Vout[(size_t)g * 81 + e] = V[e * 32];
     }
+}
+
+// the register-resident warp form
+__global__ void k_warp3(const double* mats, int nmat, double* Wout, double* Vout) {
+    __shared__ JacobiWarp9 jw[8];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * (blockDim.x >> 5) + w;
+    if (g >= nmat) return;
+    for (int e = lane; e < 81; e += 32) jw[w].A[e] = mats[(size_t)g * 81 + e];
+    __syncwarp();
+    jacobi_eig_warp3<9>(jw[w].A, jw[w].W, jw[w].V, jw[w].indR, jw[w].indC);
+    __syncwarp();
+    if (lane < 9) Wout[(size_t)g * 9 + lane] = jw[w].W[lane];
+    for (int e = lane; e < 81; e += 32) Vout[(size_t)g * 81 + e] = jw[w].V[e];
 }
 
 // the lane-parallel-search warp form
@@ -525,6 +900,13 @@ int main() {
                r, pf.rotations, pf.total, (double)pf.pivot / pf.rotations, (double)pf.arith / pf.rotations,
                (double)pf.rotate / pf.rotations, (double)pf.ind / pf.rotations);
     }
+    for (int r = 0; r < 2; ++r) {
+        k_warp3_prof<<<1, 32>>>(dm + 81 * r, dW, dpf);
+        Prof pf; CK(cudaMemcpy(&pf, dpf, sizeof(Prof), cudaMemcpyDeviceToHost));
+        printf("{\"probe\": \"warp3_sections\", \"matrix\": %d, \"rotations\": %d, \"cycles_total\": %lld, \"per_rotation\": {\"install_pivot\": %.0f, \"prefetch_refresh\": %.0f, \"arith\": %.0f, \"rotate_sync\": %.0f}}\n",
+               r, pf.rotations, pf.total, (double)pf.pivot / pf.rotations, (double)pf.ind / pf.rotations, (double)pf.arith / pf.rotations,
+               (double)pf.rotate / pf.rotations);
+    }
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     auto time_it = [&](const char* name, int nmat, auto launch) {
         float best = 1e30f;
@@ -542,6 +924,7 @@ int main() {
         time_it("warp_form", nmat, [&](int n) { k_warp<<<(n + 7) / 8, 256>>>(dm, n, dW, dV); });
         time_it("thread_form", nmat, [&](int n) { k_thread<<<(n + 31) / 32, 32, 171 * 32 * 8>>>(dm, n, dW2, dV2); });
         time_it("thread2_form", nmat, [&](int n) { k_thread2<<<(n + 31) / 32, 32, 126 * 32 * 8>>>(dm, n, dW2, dV2); });
+        time_it("warp3_form", nmat, [&](int n) { k_warp3<<<(n + 7) / 8, 256>>>(dm, n, dW2, dV2); });
         time_it("warp2_form", nmat, [&](int n) { k_warp2<<<(n + 7) / 8, 256>>>(dm, n, dW2, dV2); });
     }
     // the two production forms agree bit for bit
@@ -560,6 +943,12 @@ int main() {
     for (size_t i = 0; i < W1.size(); ++i) diff += memcmp(&W1[i], &W2[i], 8) != 0;
     for (size_t i = 0; i < V1.size(); ++i) diff += memcmp(&V1[i], &V2[i], 8) != 0;
     printf("{\"probe\": \"warp_vs_warp2_bit_differences\", \"count\": %zu}\n", diff);
+    k_warp3<<<(NM + 7) / 8, 256>>>(dm, NM, dW2, dV2);
+    CK(cudaMemcpy(W2.data(), dW2, W2.size() * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(V2.data(), dV2, V2.size() * 8, cudaMemcpyDeviceToHost));
+    diff = 0;
+    for (size_t i = 0; i < W1.size(); ++i) diff += memcmp(&W1[i], &W2[i], 8) != 0;
+    for (size_t i = 0; i < V1.size(); ++i) diff += memcmp(&V1[i], &V2[i], 8) != 0;
+    printf("{\"probe\": \"warp_vs_warp3_bit_differences\", \"count\": %zu}\n", diff);
     k_thread2<<<(NM + 31) / 32, 32, 126 * 32 * 8>>>(dm, NM, dW2, dV2);
     CK(cudaMemcpy(W2.data(), dW2, W2.size() * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(V2.data(), dV2, V2.size() * 8, cudaMemcpyDeviceToHost));
     diff = 0;
