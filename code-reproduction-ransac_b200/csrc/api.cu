@@ -272,7 +272,7 @@ static int run_score(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p) {
             if (len > H - begin) len = H - begin;
             CU(cudaMemsetAsync(not_done, 0, sizeof(int), c->stream));
             LAUNCH(c, k_cv_sample_h, (unsigned)Q, 32, 0, pr->pts.as<PointH>(), n, H, begin, len, pr->samples.as<int>(), st, Q);
-            if (p->solver == B2R_SOLVER_EXACT && (long long)active * len <= 32LL * c->sm_count) {
+            if (p->solver == B2R_SOLVER_EXACT && (long long)active * len <= 20LL * c->sm_count) {   // crossover measured at ~3200 solves (tools/microbench_jacobi.cu)
                 // few solves (a single problem, or the stragglers of a batch: finished problems' warps exit at once):
                 // one warp each — 4x less latency than a thread each, and the redundant fp64 work does not matter
                 dim3 grid((unsigned)((len + 7) / 8), (unsigned)Q);
