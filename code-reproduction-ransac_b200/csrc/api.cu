@@ -266,9 +266,10 @@ static int run_score(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p) {
         RansacState* st = pr->state.as<RansacState>();
         int* not_done = reinterpret_cast<int*>(st + Q);
         LAUNCH(c, k_state_init, (unsigned)((Q + 127) / 128), 128, 0, st, p->max_iters, Q);
-        // chunk boundaries 64, 128, 256, 512, ...: on the reference's data OpenCV stops after 13-173 iterations (median 24)
+        // chunk lengths 64, 128, 256, ... (boundaries 64, 192, 448, 960, ...): every chunk costs one solver latency, so the lengths
+        // grow geometrically; on the reference's data OpenCV stops after 13-173 iterations (median 24): two chunks at most
         int active = Q;   // problems still iterating (from the "not done" counter of the previous chunk)
-        for (int begin = 0, len = 64; begin < H; begin += len, len = begin) {
+        for (int begin = 0, len = 64; begin < H; begin += len, len *= 2) {
             if (len > H - begin) len = H - begin;
             CU(cudaMemsetAsync(not_done, 0, sizeof(int), c->stream));
             LAUNCH(c, k_cv_sample_h, (unsigned)Q, 32, 0, pr->pts.as<PointH>(), n, H, begin, len, pr->samples.as<int>(), st, Q);

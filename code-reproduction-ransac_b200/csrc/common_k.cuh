@@ -30,7 +30,7 @@ __device__ __forceinline__ int ransac_update_num_iters(double p, double ep, int 
 }
 
 // Running state of OpenCV's sequential RANSAC loop, one per problem.  The replay path scores the
-// iterations in growing chunks (boundaries 64, 128, 256, 512, ... for the homography; 256, 768, ... for PnP): after each chunk the rule below
+// iterations in chunks of doubling length (boundaries 64, 192, 448, ... for the homography; 256, 768, ... for PnP): after each chunk the rule below
 // is advanced over the chunk's counts, and chunks that start beyond the current iteration bound are never generated,
 // solved or scored — the reference typically stops after tens of iterations out of maxIters = 2000 / 5000.
 struct RansacState {
