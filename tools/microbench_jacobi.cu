@@ -591,18 +591,11 @@ __device__ void jacobi_eig_warp3_prof(double* A, double* W, double* V, int* indR
     bool have_grp = false;          // the previous rotation's pair elements stand for its four refreshed candidates
     int gk = 0, gl = 0;             // ... its pivot
     double na0 = 0, nb0 = 0;        // ... this lane's new (i, gk) and (i, gl) elements
-    bool pend = false;              // refreshed candidates of the rotation before, to be installed on lanes pk, pl
-    int pk = 0, pl = 0, rR_k = -1, rC_k = -1, rR_l = -1, rC_l = -1;
-    double vR_k = 0, vC_k = 0, vR_l = 0, vC_l = 0;
 
     long long c_p = 0, c_a = 0, c_r = 0, c_i = 0; const long long tstart = clock64(); int it;
     for (it = 0; it < N * N * 30; it++) {
         const long long t0 = clock64();
-        // ---- install the candidates refreshed one rotation ago, then account for the last rotation ----
-        if (pend) {
-            if (alane && i == pk) { ind_r = rR_k; val_r = vR_k; ok_r = rR_k >= 0; ind_c = rC_k; val_c = vC_k; ok_c = rC_k >= 0; }
-            if (alane && i == pl) { ind_r = rR_l; val_r = vR_l; ok_r = rR_l >= 0; ind_c = rC_l; val_c = vC_l; ok_c = rC_l >= 0; }
-        }
+        // ---- account for the last rotation: its pivot lanes are represented by the pair elements, the others re-read ----
         if (have_grp) {
             if (i == gk || i == gl) {
                 ok_r = false;
@@ -692,12 +685,9 @@ __device__ void jacobi_eig_warp3_prof(double* A, double* W, double* V, int* indR
         const double x_rk = __shfl_sync(FULL, na0, w_rk < 0 ? 0 : w_rk), x_ck = __shfl_sync(FULL, na0, w_ck < 0 ? 0 : w_ck);
         const double x_rl = __shfl_sync(FULL, nb0, w_rl < 0 ? 0 : w_rl), x_cl = __shfl_sync(FULL, nb0, w_cl < 0 ? 0 : w_cl);
         const double sh = tt * sqrt(1 + q * q);
-        if (have_grp) {
-            rR_k = w_rk; rC_k = w_ck; rR_l = w_rl; rC_l = w_cl;
-            vR_k = x_rk; vC_k = x_ck; vR_l = x_rl; vC_l = x_cl;
-            pk = gk;
-            pl = gl;
-            pend = true;
+        if (have_grp) {   // lanes gk, gl get their refreshed candidates back (they sat out the pivot search above)
+            if (alane && i == gk) { ind_r = w_rk; val_r = x_rk; ok_r = w_rk >= 0; ind_c = w_ck; val_c = x_ck; ok_c = w_ck >= 0; }
+            if (alane && i == gl) { ind_r = w_rl; val_r = x_rl; ok_r = w_rl >= 0; ind_c = w_cl; val_c = x_cl; ok_c = w_cl >= 0; }
         }
         const double quo = ((lane & 1) ? p : tt) / sh;
         const double c = __shfl_sync(FULL, quo, 0);
