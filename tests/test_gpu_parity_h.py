@@ -159,6 +159,21 @@ def test_find_homography_matches_oracle(ctx, oracle, n, outliers, thr, seed):
     np.testing.assert_array_equal(mask_l.ravel(), det["ransac_mask"])
 
 
+@pytest.mark.parametrize("max_iters", [1, 2, 63, 64, 65, 191, 192, 193, 447, 448, 449, 1000])
+def test_iteration_bound_at_chunk_boundaries(ctx, oracle, max_iters):
+    """The replay loop runs in chunks of 64, 128, 256 ... iterations (boundaries 64, 192, 448 ...): a caller's maxIters on,
+    just below and just above a boundary, on data whose best model arrives late (60 % outliers: the bound stays above 500
+    iterations, the inlier set still improves after iteration 64 and after 192)."""
+    s, d = _problem(40, 0.6, 92)
+    H, mask, info = ctx.find_homography(s, d, 2.0, max_iters=max_iters, confidence=0.999999)
+    Hr, mr, det = oracle.find_homography(s, d, 2.0, max_iters=max_iters, confidence=0.999999, details=True)
+    assert (H is None) == (Hr is None)
+    assert info["iters_run"] == det["iters"]
+    np.testing.assert_array_equal(mask.ravel(), mr.ravel())
+    if Hr is not None:
+        np.testing.assert_array_equal(H, Hr)          # 40 points: bit-identical refinement
+
+
 def test_find_homography_four_points_and_errors(ctx, oracle):
     s, d = _problem(4, 0.0, 30)
     H, mask, _ = ctx.find_homography(s, d, 3.0)

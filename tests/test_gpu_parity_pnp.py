@@ -170,6 +170,21 @@ def test_solve_pnp_ransac_matches_oracle(ctx, oracle, n, outliers, thr, seed):
     assert relerr(rvec, r_o) < REL_POSE_TOL and relerr(tvec, t_o) < REL_POSE_TOL
 
 
+@pytest.mark.parametrize("iterations", [1, 255, 256, 257, 767, 768, 769, 1500])
+def test_iteration_count_at_chunk_boundaries(ctx, oracle, iterations):
+    """The PnP replay loop runs in chunks of 256, 512, 1024 ... iterations (boundaries 256, 768, 1792 ...): iterationsCount on,
+    just below and just above a boundary, with 70 % outliers so that the bound stays high."""
+    rng = np.random.default_rng(77)
+    P, px, _ = synth.pnp_set(60, 0.7, rng)
+    ok, rvec, tvec, inl, info = ctx.solve_pnp_ransac(P, px, K, iterations, 4.0, 0.999999)
+    ok_o, r_o, t_o, inl_o, det = oracle.solve_pnp_ransac(P, px, K, iterations, 4.0, 0.999999, details=True)
+    assert ok == ok_o
+    if ok:
+        assert info["iters_run"] == det["iters"]
+        np.testing.assert_array_equal(inl, inl_o)
+        assert relerr(rvec, r_o) < REL_POSE_TOL and relerr(tvec, t_o) < REL_POSE_TOL
+
+
 def test_per_iteration_counts_match_oracle(ctx, oracle):
     """Every executed RANSAC iteration scores the same number of inliers as the CPU path (replayed samples, EPnP
     models, exact scoring): checked through the building blocks on the reference's data."""
