@@ -51,6 +51,29 @@ def test_homography_batches_of_messy_problems(ctx, oracle, n, Q, seed):
     assert n_model > Q // 3
 
 
+def test_thousands_of_reference_sized_problems_in_one_call(ctx, oracle):
+    """A sweep ten times the reference's: 4000 problems of 12 correspondences in one batched call (one CTA per problem in
+    the finalize kernel, several waves).  A random sample of them against the oracle: everything bit-identical, refined
+    H included; and the whole batch against itself run as singles on a subset."""
+    rng = np.random.default_rng(50)
+    Q, n = 4000, 12
+    src, dst = np.zeros((Q, n, 2)), np.zeros((Q, n, 2))
+    base_s, base_d, _ = synth.homography_set(n, 0.25, rng, noise_px=2.0)
+    for q in range(Q):
+        src[q] = base_s + rng.normal(0, 3.0, base_s.shape)
+        dst[q] = base_d + rng.normal(0, 3.0, base_d.shape)
+    H, ok, mask, infos = ctx.find_homography_batch(src, dst, 20.0)
+    assert ok.sum() > Q // 2
+    for q in rng.choice(Q, 120, replace=False):
+        Hr, mr, det = oracle.find_homography(src[q], dst[q], 20.0, details=True)
+        assert bool(ok[q]) == (Hr is not None)
+        if Hr is None:
+            continue
+        assert infos[int(q)]["iters_run"] == det["iters"]
+        np.testing.assert_array_equal(mask[q], mr.ravel())
+        np.testing.assert_array_equal(H[q], Hr)
+
+
 @pytest.mark.parametrize("n,Q,seed", [(6, 40, 5), (12, 40, 6), (40, 30, 7)])
 def test_pnp_batches_with_own_points(ctx, oracle, n, Q, seed):
     """b2r_solve_pnp_ransac_batch with per-problem points (pts_shared = 0) and per-problem camera matrices."""
