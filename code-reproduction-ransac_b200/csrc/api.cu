@@ -186,11 +186,8 @@ static int score_models(b2r_ctx* c, const float4* models, int H, const PointH* p
     } else {
         CU(cudaMemset2DAsync(counts + begin, sizeof(int) * (size_t)H_stride, 0, sizeof(int) * (size_t)H, (size_t)Q, c->stream));
     }
-    // measured on B200 at 100k x 100k (profiles/r01b_microbench_k3_variants.jsonl): fast arithmetic is fastest with 4
-    // hypothesis pairs per thread and 512-point tiles (2.57e12/s), exact arithmetic with 2 pairs (1.30e12/s); with few
-    // hypotheses 2 pairs per thread keep more CTAs in flight
-    if (arith == B2R_ARITH_FAST && (long long)H * Q >= 32768)
-        return launch_k3<4>(c, models + 2 * (size_t)begin, H, H_stride, pts, n, thr_sq, counts + begin, Q, arith, 512);
+    // measured on B200 at 100k x 100k (profiles/r01g_microbench_k3_forms.jsonl): both arithmetic modes are fastest with 2
+    // hypothesis pairs per thread and 1024-point tiles (fast: 2.83e12/s with the division-free margin; exact: 1.30e12/s)
     return launch_k3<2>(c, models + 2 * (size_t)begin, H, H_stride, pts, n, thr_sq, counts + begin, Q, arith, 1024);
 }
 

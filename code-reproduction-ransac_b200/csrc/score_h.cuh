@@ -122,14 +122,54 @@ struct HEval {
             return f2_fma(dx, dx, f2_mul(dy, dy));
         }
     }
+    // FAST only.  Signed margin of one point against two hypotheses: negative <=> inlier.  The caller counts sign bits
+    // (one LEA.HI per evaluation instead of FSETP + two IADD3); a NaN is the canonical 0x7FFFFFFF, sign clear: outlier.
+    //   FORM 1: err - thr' with MUFU.RCP, thr' = the float above thr (so "< thr'" is "<= thr"): 10 FMA-pipe ops + 1 MUFU.
+    //   FORM 2: division-free, (sx - u w)^2 + (sy - v w)^2 - thr' w^2 (the same inequality times w^2): 12 FMA-pipe ops.
+    //   FORM 3: as 2 with h0..h5 and -u, -v pre-scaled by s = thr'^-1/2 (hypotheses at load, the point tile once per CTA
+    //           in shared memory): (s sx - s u w)^2 + (s sy - s v w)^2 - w^2: 11 FMA-pipe ops.
+    // MUFU.RCP and FFMA2 do not overlap freely on sm_100 (profiles/r01_pipeprobe.jsonl: 4 FFMA2 + 1 MUFU take 12.4
+    // cycles, not 8): the reciprocal costs more issue time than the one or two extra FFMA2 that replace it.
+    template <int FORM>
+    __device__ __forceinline__ static f2_t margin(const f2_t (&h)[8], f2_t X, f2_t Y, f2_t nu, f2_t nv, f2_t one, f2_t nthr) {
+        const f2_t w = f2_fma(h[6], X, f2_fma(h[7], Y, one));
+        const f2_t sx = f2_fma(h[0], X, f2_fma(h[1], Y, h[2]));
+        const f2_t sy = f2_fma(h[3], X, f2_fma(h[4], Y, h[5]));
+        if (FORM == 1) {
+            float w0, w1;
+            f2_unpack(w, w0, w1);
+            const f2_t ww = f2_pack(rcp_approx(w0), rcp_approx(w1));
+            const f2_t dx = f2_fma(sx, ww, nu);
+            const f2_t dy = f2_fma(sy, ww, nv);
+            return f2_fma(dx, dx, f2_fma(dy, dy, nthr));
+        } else {
+            const f2_t a = f2_fma(w, nu, sx);
+            const f2_t b = f2_fma(w, nv, sy);
+            const f2_t t = f2_mul(w, w);
+            if (FORM == 2) return f2_fma(a, a, f2_fma(b, b, f2_mul(t, nthr)));
+            float t0, t1;
+            f2_unpack(t, t0, t1);
+            return f2_fma(a, a, f2_fma(b, b, f2_pack(-t0, -t1)));  // the negation folds into the FFMA2 operand
+        }
+    }
 };
+
+#ifndef K3_FAST_UNROLL
+#define K3_FAST_UNROLL 4   // points per trip of the fast kernel's loop (measured: profiles/r01g_microbench_k3_forms.jsonl)
+#endif
+#ifndef K3_MIN_CTAS
+#define K3_MIN_CTAS 2
+#endif
+#ifndef K3_FAST_FORM
+#define K3_FAST_FORM 3
+#endif
 
 // models : [Q][H_stride][8] fp32 (h0..h7, h8 == 1 implied), 32-byte aligned rows; the first H of each problem are scored
 // pts    : [Q][N] PointH
 // counts : [Q][H_stride] int32, must be zeroed by the caller; each CTA adds its tile's inlier counts
 // grid   : x = ceil(H / (K3_THREADS*2*NPAIR)), y = ceil(N / tile_pts), z = Q; dynamic smem = 128 + tile_pts*16
 template <int NPAIR, bool EXACT>
-__global__ void __launch_bounds__(K3_THREADS, 2)
+__global__ void __launch_bounds__(K3_THREADS, K3_MIN_CTAS)
 k3_score_h(const float4* __restrict__ models, int H, int H_stride, const PointH* __restrict__ pts, int N, float thr,
            int* __restrict__ counts, int tile_pts) {
     models += (size_t)blockIdx.z * H_stride * 2;
@@ -137,7 +177,7 @@ k3_score_h(const float4* __restrict__ models, int H, int H_stride, const PointH*
     counts += (size_t)blockIdx.z * H_stride;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    const float4* tile = reinterpret_cast<const float4*>(smem_raw + 128);
+    float4* tile = reinterpret_cast<float4*>(smem_raw + 128);
 
     const int p_begin = blockIdx.y * tile_pts;
     const int np = min(tile_pts, N - p_begin);
@@ -169,19 +209,47 @@ k3_score_h(const float4* __restrict__ models, int H, int H_stride, const PointH*
 #pragma unroll
     for (int j = 0; j < 2 * NPAIR; ++j) cnt[j] = 0;
     const f2_t one = f2_dup(1.0f);
+    // the float above thr (a squared distance: >= 0), so that "margin < 0" is "err <= thr"; +inf stays +inf
+    const float thr_up = thr < __int_as_float(0x7f800000) ? __uint_as_float(__float_as_uint(thr) + 1u) : thr;
+    const f2_t nthr = f2_dup(-thr_up);
+    constexpr bool SCALED = !EXACT && K3_FAST_FORM == 3;
+    const float s = rsqrtf(thr_up);
+    if (SCALED) {
+        const f2_t s2 = f2_dup(s);
+#pragma unroll
+        for (int j = 0; j < NPAIR; ++j)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) h[j][k] = f2_mul(h[j][k], s2);
+    }
 
     mbar_wait(bar, 0);
+    if (SCALED) {  // every CTA scales the -u, -v of its own copy of the tile once
+        for (int p = threadIdx.x; p < np; p += K3_THREADS) {
+            float4 pt = tile[p];
+            pt.z *= s;
+            pt.w *= s;
+            tile[p] = pt;
+        }
+        __syncthreads();
+    }
 
-#pragma unroll K3_POINT_UNROLL
+    constexpr int UNROLL = EXACT ? K3_POINT_UNROLL : K3_FAST_UNROLL;  // points per trip
+#pragma unroll UNROLL
     for (int p = 0; p < np; ++p) {
         const float4 pt = tile[p];  // broadcast LDS.128
         const f2_t X = f2_dup(pt.x), Y = f2_dup(pt.y), nu = f2_dup(pt.z), nv = f2_dup(pt.w);
 #pragma unroll
         for (int j = 0; j < NPAIR; ++j) {
             float e0, e1;
-            f2_unpack(HEval<EXACT>::err(h[j], X, Y, nu, nv, one), e0, e1);
-            cnt[2 * j] += (e0 <= thr) ? 1 : 0;
-            cnt[2 * j + 1] += (e1 <= thr) ? 1 : 0;
+            if (!EXACT && K3_FAST_FORM != 0) {
+                f2_unpack(HEval<EXACT>::template margin<K3_FAST_FORM>(h[j], X, Y, nu, nv, one, nthr), e0, e1);
+                cnt[2 * j] += (int)(__float_as_uint(e0) >> 31);
+                cnt[2 * j + 1] += (int)(__float_as_uint(e1) >> 31);
+            } else {
+                f2_unpack(HEval<EXACT>::err(h[j], X, Y, nu, nv, one), e0, e1);
+                cnt[2 * j] += (e0 <= thr) ? 1 : 0;
+                cnt[2 * j + 1] += (e1 <= thr) ? 1 : 0;
+            }
         }
     }
 

@@ -110,6 +110,10 @@ k3_score_p_exact(const double* __restrict__ models, int H, int H_stride, const P
     }
 }
 
+#ifndef K3P_FAST_FORM
+#define K3P_FAST_FORM 3
+#endif
+
 // models : [Q][H][12] fp32 rows of P = K [R | R c + t] (row-major 3x4), 48-byte rows; NaN rows = no model
 // pts    : PointPF, same sharing rule as above
 template <int NPAIR>
@@ -121,7 +125,7 @@ k3_score_p_fast(const float4* __restrict__ models, int H, int H_stride, const Po
     counts += (size_t)blockIdx.z * H_stride;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    const PointPF* tile = reinterpret_cast<const PointPF*>(smem_raw + 128);
+    PointPF* tile = reinterpret_cast<PointPF*>(smem_raw + 128);
 
     const int p_begin = blockIdx.y * tile_pts;
     const int np = min(tile_pts, N - p_begin);
@@ -155,7 +159,29 @@ k3_score_p_fast(const float4* __restrict__ models, int H, int H_stride, const Po
     int cnt[2 * NPAIR];
 #pragma unroll
     for (int j = 0; j < 2 * NPAIR; ++j) cnt[j] = 0;
+    // Signed margins, as in score_h.cuh: negative <=> inlier, the sign bit is counted (one LEA.HI per evaluation), a NaN
+    // model gives the canonical NaN (sign clear): outlier.  thr_up is the float above thr, so "< thr_up" is "<= thr".
+    //   FORM 1: (x/z - u)^2 + (y/z - v)^2 - thr_up with MUFU.RCP: 13 FMA-pipe ops + 1 MUFU.
+    //   FORM 3: division-free, rows 0 and 1 of P and -u, -v pre-scaled by s = thr_up^-1/2 (hypotheses at load, the
+    //           tile once per CTA): (s x - s u z)^2 + (s y - s v z)^2 - z^2: 14 FMA-pipe ops.
+    const float thr_up = thr < __int_as_float(0x7f800000) ? __uint_as_float(__float_as_uint(thr) + 1u) : thr;
+    const f2_t nthr = f2_dup(-thr_up);
+    const float s = rsqrtf(thr_up);
+    if (K3P_FAST_FORM == 3) {
+        const f2_t s2 = f2_dup(s);
+#pragma unroll
+        for (int j = 0; j < NPAIR; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) c[j][k] = f2_mul(c[j][k], s2);
+    }
     mbar_wait(bar, 0);
+    if (K3P_FAST_FORM == 3) {
+        for (int p = threadIdx.x; p < np; p += K3_THREADS) {
+            tile[p].nu *= s;
+            tile[p].nv *= s;
+        }
+        __syncthreads();
+    }
 
 #pragma unroll 2
     for (int p = 0; p < np; ++p) {
@@ -167,14 +193,27 @@ k3_score_p_fast(const float4* __restrict__ models, int H, int H_stride, const Po
             const f2_t x = f2_fma(c[j][0], X, f2_fma(c[j][1], Y, f2_fma(c[j][2], Z, c[j][3])));
             const f2_t y = f2_fma(c[j][4], X, f2_fma(c[j][5], Y, f2_fma(c[j][6], Z, c[j][7])));
             const f2_t z = f2_fma(c[j][8], X, f2_fma(c[j][9], Y, f2_fma(c[j][10], Z, c[j][11])));
-            float z0, z1;
-            f2_unpack(z, z0, z1);
-            const f2_t iz = f2_pack(rcp_approx(z0), rcp_approx(z1));
-            const f2_t dx = f2_fma(x, iz, nu), dy = f2_fma(y, iz, nv);
             float e0, e1;
-            f2_unpack(f2_fma(dx, dx, f2_mul(dy, dy)), e0, e1);
-            cnt[2 * j] += (e0 <= thr) ? 1 : 0;
-            cnt[2 * j + 1] += (e1 <= thr) ? 1 : 0;
+            if (K3P_FAST_FORM == 3) {
+                const f2_t a = f2_fma(z, nu, x), b = f2_fma(z, nv, y);
+                float t0, t1;
+                f2_unpack(f2_mul(z, z), t0, t1);
+                f2_unpack(f2_fma(a, a, f2_fma(b, b, f2_pack(-t0, -t1))), e0, e1);  // the negation folds into the FFMA2 operand
+            } else {
+                float z0, z1;
+                f2_unpack(z, z0, z1);
+                const f2_t iz = f2_pack(rcp_approx(z0), rcp_approx(z1));
+                const f2_t dx = f2_fma(x, iz, nu), dy = f2_fma(y, iz, nv);
+                if (K3P_FAST_FORM == 0) {
+                    f2_unpack(f2_fma(dx, dx, f2_mul(dy, dy)), e0, e1);
+                    cnt[2 * j] += (e0 <= thr) ? 1 : 0;
+                    cnt[2 * j + 1] += (e1 <= thr) ? 1 : 0;
+                    continue;
+                }
+                f2_unpack(f2_fma(dx, dx, f2_fma(dy, dy, nthr)), e0, e1);
+            }
+            cnt[2 * j] += (int)(__float_as_uint(e0) >> 31);
+            cnt[2 * j + 1] += (int)(__float_as_uint(e1) >> 31);
         }
     }
 #pragma unroll

@@ -238,6 +238,20 @@ int main(int argc, char** argv) {
     };
 
     const int reps = 5;
+#ifdef K3_SWEEP_FAST
+    (void)check;
+    run_k3<1, false>("fast_p1_t1024", d_models, H, d_pts, N, thr, d_counts, 1024, reps, &got); check("fast_p1_t1024", false);
+    run_k3<2, false>("fast_p2_t512", d_models, H, d_pts, N, thr, d_counts, 512, reps, &got); check("fast_p2_t512", false);
+    run_k3<2, false>("fast_p2_t1024", d_models, H, d_pts, N, thr, d_counts, 1024, reps, nullptr);
+    run_k3<2, false>("fast_p2_t2048", d_models, H, d_pts, N, thr, d_counts, 2048, reps, nullptr);
+    run_k3<3, false>("fast_p3_t512", d_models, H, d_pts, N, thr, d_counts, 512, reps, &got); check("fast_p3_t512", false);
+    run_k3<3, false>("fast_p3_t1024", d_models, H, d_pts, N, thr, d_counts, 1024, reps, nullptr);
+    run_k3<3, false>("fast_p3_t2048", d_models, H, d_pts, N, thr, d_counts, 2048, reps, nullptr);
+#if K3_MIN_CTAS < 3
+    run_k3<4, false>("fast_p4_t512", d_models, H, d_pts, N, thr, d_counts, 512, reps, nullptr);
+    run_k3<4, false>("fast_p4_t1024", d_models, H, d_pts, N, thr, d_counts, 1024, reps, nullptr);
+#endif
+#else
     run_k3<4, true>("exact_p4_t1024", d_models, H, d_pts, N, thr, d_counts, 1024, reps, &got); check("exact_p4_t1024", true);
     run_k3<4, false>("fast_p4_t1024", d_models, H, d_pts, N, thr, d_counts, 1024, reps, &got); check("fast_p4_t1024", false);
     run_k3<2, true>("exact_p2_t1024", d_models, H, d_pts, N, thr, d_counts, 1024, reps, &got); check("exact_p2_t1024", true);
@@ -249,5 +263,6 @@ int main(int argc, char** argv) {
     run_k3<4, true>("exact_p4_t2048", d_models, H, d_pts, N, thr, d_counts, 2048, reps, nullptr);
     run_k3<6, false>("fast_p6_t1024", d_models, H, d_pts, N, thr, d_counts, 1024, reps, nullptr);
     run_k3<6, true>("exact_p6_t1024", d_models, H, d_pts, N, thr, d_counts, 1024, reps, nullptr);
+#endif
     return 0;
 }
