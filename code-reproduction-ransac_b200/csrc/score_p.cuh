@@ -110,6 +110,12 @@ k3_score_p_exact(const double* __restrict__ models, int H, int H_stride, const P
     }
 }
 
+#ifndef K3P_MIN_CTAS
+#define K3P_MIN_CTAS 2
+#endif
+#ifndef K3P_FAST_UNROLL
+#define K3P_FAST_UNROLL 2
+#endif
 #ifndef K3P_FAST_FORM
 #define K3P_FAST_FORM 3
 #endif
@@ -117,7 +123,7 @@ k3_score_p_exact(const double* __restrict__ models, int H, int H_stride, const P
 // models : [Q][H][12] fp32 rows of P = K [R | R c + t] (row-major 3x4), 48-byte rows; NaN rows = no model
 // pts    : PointPF, same sharing rule as above
 template <int NPAIR>
-__global__ void __launch_bounds__(K3_THREADS, 2)
+__global__ void __launch_bounds__(K3_THREADS, K3P_MIN_CTAS)
 k3_score_p_fast(const float4* __restrict__ models, int H, int H_stride, const PointPF* __restrict__ pts, size_t pts_q_stride,
                 int N, float thr, int* __restrict__ counts, int tile_pts) {
     models += (size_t)blockIdx.z * H_stride * 3;
@@ -183,7 +189,8 @@ k3_score_p_fast(const float4* __restrict__ models, int H, int H_stride, const Po
         __syncthreads();
     }
 
-#pragma unroll 2
+    constexpr int UNROLL = K3P_FAST_UNROLL;
+#pragma unroll UNROLL
     for (int p = 0; p < np; ++p) {
         const float4 pt = *reinterpret_cast<const float4*>(&tile[p].Xc);  // broadcast LDS.128
         const float pnv = tile[p].nv;

@@ -6,6 +6,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import ransac_b200
 from ransac_b200 import synth
+if os.environ.get("B2R_DEV_LIB"):   # development only: time a library built with other -D flags
+    import ransac_b200._build as _b
+    _b.LIB_PATH = os.path.abspath(os.environ["B2R_DEV_LIB"])
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000
