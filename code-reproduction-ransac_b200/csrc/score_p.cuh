@@ -172,7 +172,7 @@ k3_score_p_fast(const float4* __restrict__ models, int H, int H_stride, const Po
     //           tile once per CTA): (s x - s u z)^2 + (s y - s v z)^2 - z^2: 14 FMA-pipe ops.
     const float thr_up = thr < __int_as_float(0x7f800000) ? __uint_as_float(__float_as_uint(thr) + 1u) : thr;
     const f2_t nthr = f2_dup(-thr_up);
-    const float s = rsqrtf(thr_up);
+    const float s = rsqrtf(fmaxf(thr_up, 1e-30f));  // thr = 0 would scale by inf; 1e-30 px^2 is "exactly on the pixel" at fp32 accuracy
     if (K3P_FAST_FORM == 3) {
         const f2_t s2 = f2_dup(s);
 #pragma unroll

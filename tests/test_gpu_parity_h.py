@@ -134,6 +134,36 @@ def test_score_exact_counts_bit_exact(ctx, oracle, n, n_models, seed):
         assert np.abs(fast.astype(np.int64) - ref).max() <= max(3, n // 2000)
 
 
+def test_score_fast_threshold_edges(ctx, oracle):
+    """The fast kernel folds the threshold into its arithmetic (division-free signed margin, score_h.cuh): an infinite
+    threshold accepts every point of every finite model and none of a NaN model, a zero threshold accepts (almost)
+    nothing, a huge finite one behaves like the exact kernel, and a ragged point count (tile tail) is counted once."""
+    n, n_models = 2500, 700   # 2500 = two full 1024-point tiles + a tail of 452
+    s, d = _problem(n, 0.5, 77)
+    sq, dq = _quant(s), _quant(d)
+    rng = np.random.default_rng(77)
+    idx = np.stack([rng.choice(n, 4, replace=False) for _ in range(n_models)]).astype(np.int32)
+    H, ok, _ = ctx.solve_h4(sq, dq, idx)
+    models = H.reshape(-1, 9)[:, :8].astype(np.float32)
+    models[~ok] = np.nan
+    models[5] = np.nan
+    finite = ~np.isnan(models).any(axis=1)
+    for thr_sq in (np.float32(np.inf), np.float32(1e30)):
+        fast = ctx.score_h(models, sq, dq, thr_sq, ransac_b200.ARITH_FAST)
+        ref = oracle.h_count_inliers_f32(models, sq, dq, thr_sq)
+        assert (fast[~finite] == 0).all()
+        assert np.abs(fast.astype(np.int64) - ref).max() <= 1   # a point on a hypothesis' horizon (w ~ 0) may flip
+        assert (fast[finite] >= n - 1).all()
+    zero = ctx.score_h(models, sq, dq, np.float32(0.0), ransac_b200.ARITH_FAST)
+    ref0 = oracle.h_count_inliers_f32(models, sq, dq, np.float32(0.0))
+    assert zero.max() <= 4 and ref0.max() <= 4   # at most the four points the model was fitted to
+    for thr in (1e-3, 0.5, 3.0, 1000.0):
+        thr_sq = np.float32(thr * thr)
+        fast = ctx.score_h(models, sq, dq, thr_sq, ransac_b200.ARITH_FAST)
+        ref = oracle.h_count_inliers_f32(models, sq, dq, thr_sq)
+        assert np.abs(fast.astype(np.int64) - ref).max() <= 3
+
+
 @pytest.mark.parametrize("n,outliers,thr,seed", [(5, 0.0, 3.0, 20), (8, 0.2, 3.0, 21), (12, 0.3, 75.0, 22),
                                                  (64, 0.5, 3.0, 23), (300, 0.6, 10.0, 24), (1000, 0.3, 3.0, 25),
                                                  (5000, 0.5, 2.0, 26), (100000, 0.5, 3.0, 27)])

@@ -111,6 +111,32 @@ def test_score_exact_counts_bit_exact(ctx, oracle, n, n_models, seed):
         assert np.abs(fast.astype(np.int64) - ref).max() <= max(3, n // 2000)
 
 
+def test_score_fast_threshold_edges(ctx, oracle):
+    """The fast 3x4 kernel folds the threshold into its arithmetic (division-free signed margin, score_p.cuh): an
+    infinite threshold accepts every point of a finite pose and none of a NaN pose; a ragged point count (tile tail)
+    and a tiny / huge finite threshold stay within the borderline tolerance of the exact kernel."""
+    rng = np.random.default_rng(78)
+    n, n_models = 2500, 300
+    P, px, _ = synth.pnp_set(n, 0.4, rng)
+    R0, t0 = synth.look_at_pose()
+    models = np.zeros((n_models, 12))
+    for m in range(n_models):
+        rv = oracle.rodrigues_inv(R0) + rng.normal(0, 2e-3, 3)
+        models[m, :9] = oracle.rodrigues(rv).ravel()
+        models[m, 9:] = t0 + rng.normal(0, 2.0, 3)
+    models[7] = np.nan
+    finite = np.isfinite(models).all(axis=1)
+    fast = ctx.score_p(models, P, px, K, np.float32(np.inf), ransac_b200.ARITH_FAST)
+    assert (fast[~finite] == 0).all() and (fast[finite] == n).all()
+    for thr in (0.05, 8.0, 3000.0):
+        thr_sq = np.float32(thr * thr)
+        exact = ctx.score_p(models, P, px, K, thr_sq, ransac_b200.ARITH_EXACT)
+        fast = ctx.score_p(models, P, px, K, thr_sq, ransac_b200.ARITH_FAST)
+        assert np.abs(fast.astype(np.int64) - exact).max() <= 3
+    zero = ctx.score_p(models, P, px, K, np.float32(0.0), ransac_b200.ARITH_FAST)
+    assert zero.max() <= 1
+
+
 FIX = {}
 
 
