@@ -122,6 +122,25 @@ struct HEval {
             return f2_fma(dx, dx, f2_mul(dy, dy));
         }
     }
+    // EXACT, branch-free: as err(), with the reciprocal's MUFU + Newton form taken unconditionally; `ok` is cleared when
+    // a denominator lies outside the range in which that form is the correctly rounded 1/w (the caller then redoes the
+    // whole batch of points with err()).  No branch per evaluation: a batch of points is one basic block to schedule.
+    __device__ __forceinline__ static f2_t err_exact_in_range(const f2_t (&h)[8], f2_t X, f2_t Y, f2_t nu, f2_t nv, f2_t one,
+                                                              bool& ok) {
+        const f2_t zero = f2_dup(0.0f);
+        const f2_t w = f2_add(f2_add(f2_fma(h[6], X, zero), f2_fma(h[7], Y, zero)), one);
+        float w0, w1;
+        f2_unpack(w, w0, w1);
+        ok = ok && rcp_rn_fast_path_ok(w0) && rcp_rn_fast_path_ok(w1);
+        const float y0 = rcp_approx(w0), y1 = rcp_approx(w1);
+        const float e0 = __fmaf_rn(-w0, y0, 1.0f), e1 = __fmaf_rn(-w1, y1, 1.0f);
+        const f2_t ww = f2_pack(__fmaf_rn(y0, e0, y0), __fmaf_rn(y1, e1, y1));
+        const f2_t sx = f2_add(f2_add(f2_fma(h[0], X, zero), f2_fma(h[1], Y, zero)), h[2]);
+        const f2_t sy = f2_add(f2_add(f2_fma(h[3], X, zero), f2_fma(h[4], Y, zero)), h[5]);
+        const f2_t dx = f2_add(f2_fma(sx, ww, zero), nu);
+        const f2_t dy = f2_add(f2_fma(sy, ww, zero), nv);
+        return f2_add(f2_fma(dx, dx, zero), f2_fma(dy, dy, zero));
+    }
     // FAST only.  Signed margin of one point against two hypotheses: negative <=> inlier.  The caller counts sign bits
     // (one LEA.HI per evaluation instead of FSETP + two IADD3); a NaN is the canonical 0x7FFFFFFF, sign clear: outlier.
     //   FORM 1: err - thr' with MUFU.RCP, thr' = the float above thr (so "< thr'" is "<= thr"): 10 FMA-pipe ops + 1 MUFU.
@@ -154,6 +173,9 @@ struct HEval {
     }
 };
 
+#ifndef K3_EXACT_BATCHED
+#define K3_EXACT_BATCHED 1
+#endif
 #ifndef K3_FAST_UNROLL
 #define K3_FAST_UNROLL 4   // points per trip of the fast kernel's loop (measured: profiles/r01g_microbench_k3_forms.jsonl)
 #endif
@@ -234,8 +256,49 @@ k3_score_h(const float4* __restrict__ models, int H, int H_stride, const PointH*
     }
 
     constexpr int UNROLL = EXACT ? K3_POINT_UNROLL : K3_FAST_UNROLL;  // points per trip
-#pragma unroll UNROLL
-    for (int p = 0; p < np; ++p) {
+    int p0 = 0;
+    if (EXACT && K3_EXACT_BATCHED) {
+        // batches of UNROLL points without a branch inside; the tail (< UNROLL points) goes through the loop below
+        for (; p0 + UNROLL <= np; p0 += UNROLL) {
+            int c[2 * NPAIR];
+#pragma unroll
+            for (int j = 0; j < 2 * NPAIR; ++j) c[j] = 0;
+            bool ok = true;
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const float4 pt = tile[p0 + u];
+                const f2_t X = f2_dup(pt.x), Y = f2_dup(pt.y), nu = f2_dup(pt.z), nv = f2_dup(pt.w);
+#pragma unroll
+                for (int j = 0; j < NPAIR; ++j) {
+                    float e0, e1;
+                    f2_unpack(HEval<EXACT>::err_exact_in_range(h[j], X, Y, nu, nv, one, ok), e0, e1);
+                    c[2 * j] += (e0 <= thr) ? 1 : 0;
+                    c[2 * j + 1] += (e1 <= thr) ? 1 : 0;
+                }
+            }
+            if (__builtin_expect(!ok, 0)) {  // some denominator was out of range: redo the batch with the general reciprocal
+#pragma unroll
+                for (int j = 0; j < 2 * NPAIR; ++j) c[j] = 0;
+#pragma unroll 1
+                for (int u = 0; u < UNROLL; ++u) {
+                    const float4 pt = tile[p0 + u];
+                    const f2_t X = f2_dup(pt.x), Y = f2_dup(pt.y), nu = f2_dup(pt.z), nv = f2_dup(pt.w);
+#pragma unroll
+                    for (int j = 0; j < NPAIR; ++j) {
+                        float e0, e1;
+                        f2_unpack(HEval<EXACT>::err(h[j], X, Y, nu, nv, one), e0, e1);
+                        c[2 * j] += (e0 <= thr) ? 1 : 0;
+                        c[2 * j + 1] += (e1 <= thr) ? 1 : 0;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 2 * NPAIR; ++j) cnt[j] += c[j];
+        }
+    }
+    constexpr int TAIL_UNROLL = (EXACT && K3_EXACT_BATCHED) ? 1 : UNROLL;
+#pragma unroll TAIL_UNROLL
+    for (int p = p0; p < np; ++p) {
         const float4 pt = tile[p];  // broadcast LDS.128
         const f2_t X = f2_dup(pt.x), Y = f2_dup(pt.y), nu = f2_dup(pt.z), nv = f2_dup(pt.w);
 #pragma unroll
