@@ -134,6 +134,33 @@ def test_score_exact_counts_bit_exact(ctx, oracle, n, n_models, seed):
         assert np.abs(fast.astype(np.int64) - ref).max() <= max(3, n // 2000)
 
 
+def test_score_exact_reciprocal_out_of_range(ctx, oracle):
+    """Exact scoring takes the MUFU + Newton reciprocal for a whole batch of points and redoes the batch with the general
+    reciprocal when a denominator is zero, infinite, tiny or huge (score_h.cuh): hypotheses that put such denominators
+    at the start, the middle and the end of batches, in full tiles and in the tail, must still count bit-exactly."""
+    n = 2500
+    rng = np.random.default_rng(91)
+    src = rng.uniform(0.05, 0.4, (n, 2)).astype(np.float32)
+    dst = rng.uniform(0, 2000, (n, 2)).astype(np.float32)
+    special = [0, 7, 8, 1023, 1024, 1500, 2047, 2048, 2496, 2499]   # batch and tile boundaries, tail
+    src[special] = (1.0, 0.0)          # w = h6 + 1 exactly for these points
+    base = np.array([1500, 80, 600, -40, -700, 100, 0.05, -0.02], dtype=np.float32)
+    models = np.tile(base, (9, 1))
+    models[0, 6] = -1.0                      # w = 0: 1/w = inf
+    models[1, 6] = np.float32(3e38)          # w = inf for every point
+    models[2, 6] = np.float32(-1.0) + np.float32(2.0 ** -24)  # |w| = 2^-24 .. fine; kept as an in-range control
+    models[3, 6:8] = (np.float32(1e35), np.float32(-1e35))    # |w| > 2^101 for most points
+    models[4, 6] = -1.0; models[4, 0:3] = 0; models[4, 3:6] = 0   # 0 * inf = NaN at the special points
+    models[5] = np.nan
+    models[6, 6] = np.float32(-1.0 - 2.0 ** -20)              # tiny negative w at the special points
+    models[7, 6:8] = (np.float32(1e-38), np.float32(1e-38))   # denormal products
+    for thr_sq in (np.float32(9.0), np.float32(5625.0), np.float32(np.inf)):
+        with np.errstate(all="ignore"):
+            ref = oracle.h_count_inliers_f32(models, src, dst, thr_sq)
+        got = ctx.score_h(models, src, dst, thr_sq, ransac_b200.ARITH_EXACT)
+        np.testing.assert_array_equal(got, ref)
+
+
 def test_score_fast_threshold_edges(ctx, oracle):
     """The fast kernel folds the threshold into its arithmetic (division-free signed margin, score_h.cuh): an infinite
     threshold accepts every point of every finite model and none of a NaN model, a zero threshold accepts (almost)
