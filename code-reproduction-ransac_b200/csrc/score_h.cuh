@@ -18,7 +18,8 @@
 //            inlier  <=>  dx*dx + dy*dy <= thr     (NaN -> outlier)
 //          every product/sum individually rounded (mul.rn/add.rn.f32x2 are never contracted),
 //          reciprocal correctly rounded.  Bit-exact with cv2's mask by construction.
-//   FAST:  same formula with FMA contraction and MUFU.RCP (10 FMA-pipe ops + 1 MUFU per eval).
+//   FAST:  the same inequality multiplied by w^2 (no division), FMA-contracted, threshold folded into pre-scaled
+//          operands: 11 FMA-pipe ops per eval, the sign bit of the margin is the inlier flag (HEval::margin).
 #pragma once
 #include "f32x2.cuh"
 

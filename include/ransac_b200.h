@@ -46,7 +46,7 @@ extern "C" {
 #define B2R_SAMPLER_PHILOX 1    /* Philox4x32-10 counter-based sampler, fixed number of hypotheses           */
 /* arithmetic of the hypotheses x points scoring kernel */
 #define B2R_ARITH_EXACT 0 /* the reference's un-fused fp32 sequence: inlier sets bit-exact with cv2 */
-#define B2R_ARITH_FAST 1  /* FMA-contracted, MUFU reciprocal                                        */
+#define B2R_ARITH_FAST 1  /* FMA-contracted, division-free form of the same inequality               */
 /* minimal solver */
 #define B2R_SOLVER_EXACT 0 /* OpenCV's normalised DLT + Jacobi eigen-solver, fp64, bit-identical models */
 #define B2R_SOLVER_FAST 1  /* closed-form 4-point solve in registers (fp64), ~1e-12 relative agreement   */
