@@ -40,6 +40,9 @@ constexpr int K3_THREADS = 256;
 #define K3_UNROLL 8
 #endif
 constexpr int K3_POINT_UNROLL = K3_UNROLL;  // points per trip of the inner loop
+#ifndef K3_EXACT_PACKED_NEWTON
+#define K3_EXACT_PACKED_NEWTON 1
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -133,9 +136,17 @@ struct HEval {
         float w0, w1;
         f2_unpack(w, w0, w1);
         ok = ok && rcp_rn_fast_path_ok(w0) && rcp_rn_fast_path_ok(w1);
+#if K3_EXACT_PACKED_NEWTON
+        // the Newton step as two FFMA2 (the same two IEEE FMAs per half): scalar FFMA between packed instructions costs
+        // ~3 cycles per switch on sm_100 (profiles/r01_pipeprobe.jsonl: ffma2+ffma 0.31 instr/clk)
+        const f2_t y = f2_pack(rcp_approx(w0), rcp_approx(w1));
+        const f2_t e = f2_fma(f2_pack(-w0, -w1), y, one);
+        const f2_t ww = f2_fma(y, e, y);
+#else
         const float y0 = rcp_approx(w0), y1 = rcp_approx(w1);
         const float e0 = __fmaf_rn(-w0, y0, 1.0f), e1 = __fmaf_rn(-w1, y1, 1.0f);
         const f2_t ww = f2_pack(__fmaf_rn(y0, e0, y0), __fmaf_rn(y1, e1, y1));
+#endif
         const f2_t sx = f2_add(f2_add(f2_fma(h[0], X, zero), f2_fma(h[1], Y, zero)), h[2]);
         const f2_t sy = f2_add(f2_add(f2_fma(h[3], X, zero), f2_fma(h[4], Y, zero)), h[5]);
         const f2_t dx = f2_add(f2_fma(sx, ww, zero), nu);
