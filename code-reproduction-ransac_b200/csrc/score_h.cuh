@@ -135,7 +135,9 @@ struct HEval {
         const f2_t w = f2_add(f2_add(f2_fma(h[6], X, zero), f2_fma(h[7], Y, zero)), one);
         float w0, w1;
         f2_unpack(w, w0, w1);
-        ok = ok && rcp_rn_fast_path_ok(w0) && rcp_rn_fast_path_ok(w1);
+        // rcp_rn_fast_path_ok() as two unordered compares per half chained into the running predicate (FSETP.GEU/.LTU
+        // ... .AND): |w| in [2^-100, 2^101) or NaN
+        ok = ok && !(fabsf(w0) < 0x1p-100f) && !(fabsf(w0) >= 0x1p101f) && !(fabsf(w1) < 0x1p-100f) && !(fabsf(w1) >= 0x1p101f);
 #if K3_EXACT_PACKED_NEWTON
         // the Newton step as two FFMA2 (the same two IEEE FMAs per half): scalar FFMA between packed instructions costs
         // ~3 cycles per switch on sm_100 (profiles/r01_pipeprobe.jsonl: ffma2+ffma 0.31 instr/clk)
