@@ -83,6 +83,12 @@ __device__ __forceinline__ f2_t f2_sum_of_products(f2_t a, f2_t b) {
     return f2_pack(__fadd_rn(a0, b0), __fadd_rn(a1, b1));
 }
 
+// c += (e <= thr) as FSETP + one predicated IADD3 (the compiler's own form is FSETP + two IADD3; the ALU pipe shares
+// dispatch with the FMA pipe, which is what the exact kernel is bound by).  NaN compares false: outlier.
+__device__ __forceinline__ void count_le(int& c, float e, float thr) {
+    asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(c) : "f"(e), "f"(thr));
+}
+
 template <bool EXACT>
 struct HEval {
     // Returns the packed squared reprojection error of one point against two hypotheses.
@@ -286,8 +292,8 @@ k3_score_h(const float4* __restrict__ models, int H, int H_stride, const PointH*
                 for (int j = 0; j < NPAIR; ++j) {
                     float e0, e1;
                     f2_unpack(HEval<EXACT>::err_exact_in_range(h[j], X, Y, nu, nv, one, ok), e0, e1);
-                    c[2 * j] += (e0 <= thr) ? 1 : 0;
-                    c[2 * j + 1] += (e1 <= thr) ? 1 : 0;
+                    count_le(c[2 * j], e0, thr);
+                    count_le(c[2 * j + 1], e1, thr);
                 }
             }
             if (__builtin_expect(!ok, 0)) {  // some denominator was out of range: redo the batch with the general reciprocal
