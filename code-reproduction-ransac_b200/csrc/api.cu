@@ -187,7 +187,7 @@ static int score_models(b2r_ctx* c, const float4* models, int H, const PointH* p
         CU(cudaMemset2DAsync(counts + begin, sizeof(int) * (size_t)H_stride, 0, sizeof(int) * (size_t)H, (size_t)Q, c->stream));
     }
     // measured on B200 at 100k x 100k (profiles/r01g_microbench_k3_forms.jsonl): both arithmetic modes are fastest with 2
-    // hypothesis pairs per thread and 1024-point tiles (fast: 2.83e12/s with the division-free margin; exact: 1.30e12/s)
+    // hypothesis pairs per thread and 1024-point tiles (fast: 2.83e12/s with the division-free margin; exact: 1.54e12/s)
     return launch_k3<2>(c, models + 2 * (size_t)begin, H, H_stride, pts, n, thr_sq, counts + begin, Q, arith, 1024);
 }
 
