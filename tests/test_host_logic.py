@@ -32,6 +32,59 @@ def test_library_exports_every_declared_symbol():
     assert exported == declared                          # and nothing else is exported under that prefix
 
 
+def test_scoring_kernels_are_the_instruction_mix_design_md_describes():
+    """SASS of the built library (cuobjdump; no GPU needed): the fast 3x3 scoring kernel is packed fp32x2 arithmetic with
+    no reciprocal and sign-bit counting (11 FFMA2/FMUL2 per pair of hypotheses and point, LEA.HI, no MUFU in the loop),
+    it is fed by a bulk TMA copy, the exact kernel never contracts a product into its sum (every FFMA2 of its batch adds
+    RZ or belongs to the Newton step), and no scoring kernel touches the tensor pipe or spills."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    import __graft_entry__ as g
+    g.build()
+    from ransac_b200 import _lib
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.lib_path()], capture_output=True, text=True).stdout
+    funcs = {}
+    name = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            funcs[name] = []
+        elif name and re.search(r"/\*[0-9a-f]{4}\*/", line):
+            funcs[name].append(line)
+    fast = next(v for k, v in funcs.items() if "k3_score_hILi2ELb0" in k)
+    exact = next(v for k, v in funcs.items() if "k3_score_hILi2ELb1" in k)
+    pfast = next(v for k, v in funcs.items() if "k3_score_p_fastILi2" in k)
+
+    def count(lines, op):
+        return sum(1 for l in lines if re.search(r"\b" + op + r"\b", l))
+
+    def main_loop(lines):   # from the first broadcast LDS.128 to the backward branch that closes the unrolled loop
+        start = next(i for i, l in enumerate(lines) if "LDS.128" in l)
+        end = next(i for i in range(start, len(lines)) if re.search(r"\bBRA\b", lines[i]))
+        return lines[start:end]
+
+    loop = main_loop(fast)
+    n_lds = count(loop, r"LDS\.128")
+    assert n_lds == 4                                                    # unrolled by 4 points
+    assert count(loop, "FFMA2") + count(loop, "FMUL2") == 11 * 2 * n_lds  # 11 packed ops x 2 pairs per point
+    assert count(loop, r"MUFU\.RCP") == 0 and count(loop, "FSETP") == 0
+    assert count(loop, r"LEA\.HI") == 4 * n_lds                          # one per evaluation
+    for body in (fast, exact, pfast):
+        assert any("UBLKCP" in l for l in body)                           # 1-D bulk TMA copy of the point tile
+        assert not any(re.search(r"\b(HMMA|IMMA|DMMA|UTCHMMA|UTCMMA|STL|LDL)\b", l) for l in body)
+    ploop = main_loop(pfast)
+    assert count(ploop, r"MUFU\.RCP") == 0 and count(ploop, "FFMA2") + count(ploop, "FMUL2") == 14 * 2 * count(ploop, r"LDS\.128")
+    eloop = main_loop(exact)
+    n_pts = count(eloop, r"LDS\.128")
+    assert n_pts == 8
+    assert count(eloop, "FADD2") == 9 * 2 * n_pts                         # every sum is its own instruction
+    ffma2 = [l for l in eloop if re.search(r"\bFFMA2\b", l)]
+    assert len(ffma2) == 12 * 2 * n_pts                                   # 10 products (+ RZ) and the 2 FMAs of the Newton step
+    assert sum(1 for l in ffma2 if re.search(r", RZ(\.F32)? ;", l) or ", RZ ;" in l) >= 10 * 2 * n_pts
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the product path must fail loudly (and it never imports the oracle)."""
     import ransac_b200
