@@ -362,48 +362,74 @@ done:
 }
 
 /* ------------------------------------------------------------------------------------------- */
-/* A.7  refinement: cv::LMSolver (max 10 iterations, eps FLT_EPSILON) on the 8 free parameters  */
+/* A.7  refinement: cv::LMSolver (max 10 iterations, eps FLT_EPSILON) on the nine entries of H   */
 /* ------------------------------------------------------------------------------------------- */
-/* x = solve(A, b) for symmetric A through its eigen-decomposition (cv::solve DECOMP_EIG):       */
-/* Jacobi, then the SVD back-substitution with OpenCV's threshold  eps*2*sum|w|.                 */
+/* The building blocks below are pinned BIT FOR BIT against the cv2 4.13.0 binary through the functions it exposes
+ * (cv2.mulTransposed, cv2.gemm, cv2.norm, cv2.solve / cv2.invert with DECOMP_EIG, cv2.eigen): an LM assembled from those
+ * calls returns cv2.findHomography's H bit for bit, and each block here equals its cv2 call on every probe
+ * (tests/golden/make_golden_lm.py -> tests/golden/cv2_lm_blocks.json, tests/test_oracle_golden.py).  The summation
+ * orders are properties of that binary on an AVX2 host (cv::norm is dispatched; gemm / mulTransposed are not). */
+
+/* cv::gemm's inner product (GEMMSingleMul, d_size.width <= 4): FOUR interleaved partial sums over k, the tail of
+ * (n mod 4) terms into the first, combined as ((s0 + s1) + s2) + s3.  Products rounded (no FMA). */
+static double acc4_dot(const double* a, int astep, const double* b, int bstep, int n) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int k = 0;
+    for (; k <= n - 4; k += 4) {
+        s0 += a[k * astep] * b[k * bstep];
+        s1 += a[(k + 1) * astep] * b[(k + 1) * bstep];
+        s2 += a[(k + 2) * astep] * b[(k + 2) * bstep];
+        s3 += a[(k + 3) * astep] * b[(k + 3) * bstep];
+    }
+    for (; k < n; k++) s0 += a[k * astep] * b[k * bstep];
+    return ((s0 + s1) + s2) + s3;
+}
+
+/* x = solve(A, b) for symmetric A through its eigen-decomposition (cv::solve DECOMP_EIG): Jacobi, then the SVD
+ * back-substitution (SVBkSb): threshold 2 eps * sum(w) (signed sum), singular directions below it dropped,
+ * s = (v_i . b) * (1 / w_i)  — a multiplication by the reciprocal, not a division —, x += s v_i. */
 static void solve_sym_eig(const double* A, const double* b, int n, double* x) {
     double a[MAXN * MAXN], W[MAXN], V[MAXN * MAXN], thr = 0;
     int i, j;
     memcpy(a, A, sizeof(double) * n * n);
     orc_jacobi(a, n, W, V);
-    for (i = 0; i < n; i++) thr += fabs(W[i]);
+    for (i = 0; i < n; i++) thr += W[i];
     thr *= DBL_EPSILON * 2;
     for (i = 0; i < n; i++) x[i] = 0;
     for (i = 0; i < n; i++) {
         double wi = W[i], s = 0;
         if (fabs(wi) <= thr) continue;
+        wi = 1 / wi;
         for (j = 0; j < n; j++) s += V[i * n + j] * b[j];
-        s /= wi;
-        for (j = 0; j < n; j++) x[j] += s * V[i * n + j];
+        s *= wi;
+        for (j = 0; j < n; j++) x[j] = x[j] + s * V[i * n + j];
     }
 }
 
+/* diagonal of cv::invert(A, DECOMP_EIG): X[j][j] += (v_i[j] * (1 / w_i)) * v_i[j], same threshold. */
 static void invert_sym_eig_diag(const double* A, int n, double* diag) {
     double a[MAXN * MAXN], W[MAXN], V[MAXN * MAXN], thr = 0;
     int i, j;
     memcpy(a, A, sizeof(double) * n * n);
     orc_jacobi(a, n, W, V);
-    for (i = 0; i < n; i++) thr += fabs(W[i]);
+    for (i = 0; i < n; i++) thr += W[i];
     thr *= DBL_EPSILON * 2;
     for (j = 0; j < n; j++) diag[j] = 0;
     for (i = 0; i < n; i++) {
-        if (fabs(W[i]) <= thr) continue;
-        for (j = 0; j < n; j++) diag[j] += V[i * n + j] * V[i * n + j] / W[i];
+        double wi = W[i];
+        if (fabs(wi) <= thr) continue;
+        wi = 1 / wi;
+        for (j = 0; j < n; j++) diag[j] = diag[j] + (V[i * n + j] * wi) * V[i * n + j];
     }
 }
 
-/* residuals r[2k], and (optionally) A = J^T J (9x9) and v = J^T r, for the NINE parameters h[0..8].
- * OpenCV 4.13's HomographyRefineCallback refines all nine entries (w = h6 X + h7 Y + h8); an 8-parameter LM with h8 = 1
- * agrees with the binary only to 1e-9 on well-conditioned problems and not at all on ill-conditioned ones, the
- * 9-parameter one to 1e-15 (median) / 3e-8 (worst of 200 noisy problems).  Sums run over the rows of J in order (x row,
- * then y row, of each point), as cv::mulTransposed does. */
+/* residuals r[2k], and (optionally) the Jacobian J (2 count x 9, row-major), A = J^T J and v = J^T r, for the NINE
+ * parameters h[0..8].  OpenCV 4.13's HomographyRefineCallback refines all nine entries (w = h6 X + h7 Y + h8).
+ * A = cv::mulTransposed(J, aTa): every entry ONE running sum over the rows of J in order (x row, then y row, of each
+ * point).  v = cv::gemm(J, r, GEMM_1_T): the four-partial-sum inner product above over the 2 count rows. */
 static void h_refine_eval(const double* h, const float* M, const float* m, int count, double* r, double* A, double* v) {
-    if (A) { memset(A, 0, sizeof(double) * 81); memset(v, 0, sizeof(double) * 9); }
+    double* J = A ? (double*)malloc(sizeof(double) * 18 * (size_t)(count > 0 ? count : 1)) : NULL;
+    if (A) memset(A, 0, sizeof(double) * 81);
     for (int i = 0; i < count; i++) {
         double Mx = M[2 * i], My = M[2 * i + 1];
         double ww = h[6] * Mx + h[7] * My + h[8];
@@ -413,22 +439,75 @@ static void h_refine_eval(const double* h, const float* M, const float* m, int c
         r[2 * i] = xi - m[2 * i];
         r[2 * i + 1] = yi - m[2 * i + 1];
         if (A) {
-            double Jx[9] = {Mx * ww, My * ww, ww, 0, 0, 0, -Mx * ww * xi, -My * ww * xi, -ww * xi};
-            double Jy[9] = {0, 0, 0, Mx * ww, My * ww, ww, -Mx * ww * yi, -My * ww * yi, -ww * yi};
-            for (int j = 0; j < 9; j++) {
+            double* Jx = J + 18 * (size_t)i;
+            double* Jy = Jx + 9;
+            Jx[0] = Mx * ww; Jx[1] = My * ww; Jx[2] = ww; Jx[3] = Jx[4] = Jx[5] = 0;
+            Jx[6] = -Mx * ww * xi; Jx[7] = -My * ww * xi; Jx[8] = -ww * xi;
+            Jy[0] = Jy[1] = Jy[2] = 0; Jy[3] = Mx * ww; Jy[4] = My * ww; Jy[5] = ww;
+            Jy[6] = -Mx * ww * yi; Jy[7] = -My * ww * yi; Jy[8] = -ww * yi;
+            for (int j = 0; j < 9; j++)
                 for (int k = 0; k < 9; k++) {
                     A[j * 9 + k] += Jx[j] * Jx[k];
                     A[j * 9 + k] += Jy[j] * Jy[k];
                 }
-                v[j] += Jx[j] * r[2 * i];
-                v[j] += Jy[j] * r[2 * i + 1];
-            }
         }
+    }
+    if (A) {
+        for (int j = 0; j < 9; j++) v[j] = acc4_dot(J + j, 9, r, 1, 2 * count);
+        free(J);
     }
 }
 
-static double norm_l2sqr(const double* r, int n) { double s = 0; for (int i = 0; i < n; i++) s += r[i] * r[i]; return s; }
+/* cv::norm(r, NORM_L2SQR) for CV_64F as the binary's AVX2 code path computes it: 16 elements per step into four
+ * 4-lane accumulators by FUSED multiply-add, combined ((r0 + r1) + r2) + r3 lane-wise and then (l0 + l1) + (l2 + l3);
+ * the remaining elements in blocks of four ROUNDED squares added in order, the last (n mod 4) by fused multiply-add.
+ * 20 000 / 20 000 random vectors of 1 ... 129 elements equal cv2.norm bit for bit. */
+static double norm_l2sqr(const double* a, int n) {
+    double r[4][4], t[4], s = 0;
+    int j = 0, q, l;
+    for (q = 0; q < 4; q++) for (l = 0; l < 4; l++) r[q][l] = 0;
+    for (; j <= n - 16; j += 16)
+        for (q = 0; q < 4; q++)
+            for (l = 0; l < 4; l++) { double v = a[j + 4 * q + l]; r[q][l] = fma(v, v, r[q][l]); }
+    for (l = 0; l < 4; l++) t[l] = ((r[0][l] + r[1][l]) + r[2][l]) + r[3][l];
+    s += (t[0] + t[1]) + (t[2] + t[3]);
+    for (; j <= n - 4; j += 4)
+        for (l = 0; l < 4; l++) { double v = a[j + l], p = v * v; s += p; }
+    for (; j < n; j++) { double v = a[j]; s = fma(v, v, s); }
+    return s;
+}
 static double norm_inf(const double* r, int n) { double s = 0; for (int i = 0; i < n; i++) if (fabs(r[i]) > s) s = fabs(r[i]); return s; }
+
+/* cv::Mat::dot (dotProd_64f) as the binary computes it: unrolled by four,
+ *     s += a0 b0 + a1 b1 + a2 b2 + a3 b3
+ * compiled with FMA contraction: the block is fma(a3, b3, fma(a2, b2, fma(a0, b0, a1 b1))) — the SECOND product is the
+ * rounded one —, added to s by a plain add; the tail (n mod 4) is s = fma(a, b, s).  Mat::dot is not exposed by the
+ * Python binding, so this form is pinned through the whole refinement: of eight candidate forms it is the only one
+ * for which orc_h_lm_refine equals cv2.findHomography(inliers, 0) bit for bit on all 1982 probe problems (24 debug.log
+ * blocks, the 458 candidates of the repo's sweep, 1500 random sets of 5 ... 39 points); the others leave 6 ... 26
+ * problems 1e-13 ... 6e-9 away. */
+static double cv_dot(const double* a, const double* b, int n) {
+    double s = 0;
+    int i = 0;
+    for (; i <= n - 4; i += 4) s += fma(a[i + 3], b[i + 3], fma(a[i + 2], b[i + 2], fma(a[i], b[i], a[i + 1] * b[i + 1])));
+    for (; i < n; i++) s = fma(a[i], b[i], s);
+    return s;
+}
+
+/* the blocks, exported for the known-answer tests (tests/test_oracle_golden.py) */
+ORC_API double orc_cv_norm_l2sqr(const double* a, int n) { return norm_l2sqr(a, n); }
+ORC_API double orc_cv_dot(const double* a, const double* b, int n) { return cv_dot(a, b, n); }
+ORC_API void orc_cv_gemm_atb(const double* J, int rows, int cols, const double* r, double* v) {
+    for (int j = 0; j < cols; j++) v[j] = acc4_dot(J + j, cols, r, 1, rows);
+}
+ORC_API void orc_cv_gemm_axpby(const double* A, int n, const double* d, double alpha, const double* c, double beta, double* out) {
+    for (int i = 0; i < n; i++) out[i] = acc4_dot(A + i * n, 1, d, 1, n) * alpha + c[i] * beta;
+}
+ORC_API void orc_cv_solve_eig(const double* A, const double* b, int n, double* x) { solve_sym_eig(A, b, n, x); }
+ORC_API void orc_cv_invert_eig_diag(const double* A, int n, double* diag) { invert_sym_eig_diag(A, n, diag); }
+ORC_API void orc_h_refine_eval(const double* h, const float* M, const float* m, int count, double* r, double* A, double* v) {
+    h_refine_eval(h, M, m, count, r, A, v);
+}
 
 /* cv::LMSolver (max maxIters iterations, eps FLT_EPSILON) on the nine entries of H, then H *= 1/H[8] (OpenCV's
  * convertTo(..., scaleFor(H22))).  H: in = start (runKernel's output), out = refined, H[8] == 1. */
@@ -439,7 +518,7 @@ ORC_API int orc_h_lm_refine(const float* M, const float* m, int count, double* H
     double* r = (double*)malloc(sizeof(double) * 2 * (size_t)count);
     double* rd = (double*)malloc(sizeof(double) * 2 * (size_t)count);
     double lambda = 1, lc = 0.75, S;
-    int i, j, iter = 0;
+    int i, iter = 0;
     for (i = 0; i < lx; i++) x[i] = H[i];
     h_refine_eval(x, M, m, count, r, A, v);
     S = norm_l2sqr(r, 2 * count);
@@ -452,20 +531,14 @@ ORC_API int orc_h_lm_refine(const float* M, const float* m, int count, double* H
         for (i = 0; i < lx; i++) xd[i] = x[i] - d[i];
         h_refine_eval(xd, M, m, count, rd, NULL, NULL);
         Sd = norm_l2sqr(rd, 2 * count);
-        for (i = 0; i < lx; i++) {
-            double s = 0;
-            for (j = 0; j < lx; j++) s += A[i * lx + j] * d[j];
-            tmp[i] = 2 * v[i] - s;
-        }
-        dS = 0;
-        for (i = 0; i < lx; i++) dS += d[i] * tmp[i];
+        for (i = 0; i < lx; i++) tmp[i] = acc4_dot(A + i * lx, 1, d, 1, lx) * -1. + v[i] * 2.; /* gemm(A, d, -1, v, 2) */
+        dS = cv_dot(d, tmp, lx);
         R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
         if (R > Rhi) {
             lambda *= 0.5;
             if (lambda < lc) lambda = 0;
         } else if (R < Rlo) {
-            double t = 0, nu;
-            for (i = 0; i < lx; i++) t += d[i] * v[i];
+            double t = cv_dot(d, v, lx), nu;
             nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1) + 2;
             nu = nu < 2. ? 2. : nu; nu = nu > 10. ? 10. : nu;
             if (lambda == 0) {

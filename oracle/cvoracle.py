@@ -45,6 +45,15 @@ def lib():
         L.orc_h_ransac_stage.restype = C.c_int
         L.orc_h_lm_refine.argtypes = [fp, fp, C.c_int, dp, C.c_int]
         L.orc_h_lm_refine.restype = C.c_int
+        L.orc_cv_norm_l2sqr.argtypes = [dp, C.c_int]
+        L.orc_cv_norm_l2sqr.restype = C.c_double
+        L.orc_cv_dot.argtypes = [dp, dp, C.c_int]
+        L.orc_cv_dot.restype = C.c_double
+        L.orc_cv_gemm_atb.argtypes = [dp, C.c_int, C.c_int, dp, dp]
+        L.orc_cv_gemm_axpby.argtypes = [dp, C.c_int, dp, C.c_double, dp, C.c_double, dp]
+        L.orc_cv_solve_eig.argtypes = [dp, dp, C.c_int, dp]
+        L.orc_cv_invert_eig_diag.argtypes = [dp, C.c_int, dp]
+        L.orc_h_refine_eval.argtypes = [dp, fp, fp, C.c_int, dp, dp, dp]
         L.orc_find_homography.argtypes = [dp, dp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, dp, u8p, ip, u8p, dp]
         L.orc_find_homography.restype = C.c_int
         L.orc_rodrigues.argtypes = [dp, dp]
@@ -158,6 +167,65 @@ def h_lm_refine(src_inl, dst_inl, H0, max_iters=10):
     H = np.ascontiguousarray(np.asarray(H0, dtype=np.float64).reshape(9)).copy()
     it = lib().orc_h_lm_refine(_p(s, C.c_float), _p(d, C.c_float), len(s), _p(H, C.c_double), max_iters)
     return H.reshape(3, 3), it
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def cv_norm_l2sqr(r):
+    """cv2.norm(r, cv2.NORM_L2SQR) for float64 data, in the binary's summation order."""
+    r = _f64(r).ravel()
+    return lib().orc_cv_norm_l2sqr(_p(r, C.c_double), r.size)
+
+
+def cv_dot(a, b):
+    """cv::Mat::dot of two float64 vectors (not exposed by the Python binding; pinned through the LM)."""
+    a, b = _f64(a).ravel(), _f64(b).ravel()
+    return lib().orc_cv_dot(_p(a, C.c_double), _p(b, C.c_double), a.size)
+
+
+def cv_gemm_atb(J, r):
+    """cv2.gemm(J, r, 1, None, 0, flags=cv2.GEMM_1_T) for a float64 (rows x cols) J and (rows x 1) r."""
+    J, r = _f64(J), _f64(r).ravel()
+    v = np.zeros(J.shape[1])
+    lib().orc_cv_gemm_atb(_p(J, C.c_double), J.shape[0], J.shape[1], _p(r, C.c_double), _p(v, C.c_double))
+    return v
+
+
+def cv_gemm_axpby(A, d, alpha, c, beta):
+    """cv2.gemm(A, d, alpha, c, beta) for square float64 A and column vectors d, c."""
+    A, d, c = _f64(A), _f64(d).ravel(), _f64(c).ravel()
+    out = np.zeros(A.shape[0])
+    lib().orc_cv_gemm_axpby(_p(A, C.c_double), A.shape[0], _p(d, C.c_double), alpha, _p(c, C.c_double), beta,
+                            _p(out, C.c_double))
+    return out
+
+
+def cv_solve_eig(A, b):
+    """cv2.solve(A, b, flags=cv2.DECOMP_EIG) for symmetric float64 A (n <= 12)."""
+    A, b = _f64(A), _f64(b).ravel()
+    x = np.zeros(A.shape[0])
+    lib().orc_cv_solve_eig(_p(A, C.c_double), _p(b, C.c_double), A.shape[0], _p(x, C.c_double))
+    return x
+
+
+def cv_invert_eig_diag(A):
+    """np.diag(cv2.invert(A, flags=cv2.DECOMP_EIG)[1]) for symmetric float64 A."""
+    A = _f64(A)
+    d = np.zeros(A.shape[0])
+    lib().orc_cv_invert_eig_diag(_p(A, C.c_double), A.shape[0], _p(d, C.c_double))
+    return d
+
+
+def h_refine_eval(h, src_inl, dst_inl):
+    """HomographyRefineCallback::compute + the LM's A = J^T J, v = J^T r: returns (r, A, v)."""
+    s, d = _f32(src_inl, 2), _f32(dst_inl, 2)
+    h = _f64(h).ravel()
+    r, A, v = np.zeros(2 * len(s)), np.zeros((9, 9)), np.zeros(9)
+    lib().orc_h_refine_eval(_p(h, C.c_double), _p(s, C.c_float), _p(d, C.c_float), len(s), _p(r, C.c_double),
+                            _p(A, C.c_double), _p(v, C.c_double))
+    return r, A, v
 
 
 def find_homography(src, dst, thr, max_iters=2000, confidence=0.995, mask_semantics=0, details=False):

@@ -7,7 +7,11 @@ import numpy as np
 import pytest
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cv2_golden.json")
-REL_H_TOL = 1e-5   # north star tolerance; observed agreement: median 1e-10, worst 2.6e-7
+GOLD_LM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cv2_lm_blocks.json")
+REL_H_TOL = 1e-5   # north star tolerance.  It only applies from 50 RANSAC-stage inliers upwards, where the binary's
+#                    J^T r goes through OpenBLAS (cv::gemm hands matrices of >= 100 rows to LAPACK/BLAS, whose summation
+#                    order is CPU-kernel specific): observed <= 8e-11.  Below that the refined H is held to EQUALITY.
+BLAS_ROWS = 100    # cv::gemm -> cblas_dgemm from this many rows of J (= 2 x inliers), probed on the 4.13.0 binary
 
 
 @pytest.fixture(scope="module")
@@ -41,14 +45,69 @@ def test_four_point_solver_bit_exact(oracle, gold):
 
 
 def test_find_homography_random_problems(oracle, gold):
-    worst = 0.0
+    worst, exact = 0.0, 0
     for c in gold["ransac_random"]:
-        H, mask = oracle.find_homography(np.array(c["src"]), np.array(c["dst"]), c["thr"])
+        H, mask, det = oracle.find_homography(np.array(c["src"]), np.array(c["dst"]), c["thr"], details=True)
         assert (H is None) == (c["H"] is None)
         np.testing.assert_array_equal(mask.ravel(), np.array(c["mask"], dtype=np.uint8))
         if H is not None:
+            if 2 * int(det["ransac_mask"].sum()) < BLAS_ROWS:
+                np.testing.assert_array_equal(H, np.array(c["H"]))      # every bit of the refined H
+                exact += 1
             worst = max(worst, relerr(H, c["H"]))
-    assert worst < REL_H_TOL
+    assert exact >= 20 and worst < 1e-9
+
+
+def _unhex(a, shape=None):
+    v = np.array([float.fromhex(x) for x in a])
+    return v.reshape(shape) if shape else v
+
+
+@pytest.fixture(scope="module")
+def gold_lm():
+    with open(GOLD_LM) as f:
+        return json.load(f)
+
+
+def test_lm_building_blocks_bit_exact(oracle, gold_lm):
+    """cv::LMSolver's linear algebra as the 4.13.0 binary computes it (tests/golden/make_golden_lm.py): the summation
+    order of cv::norm (AVX2: fused multiply-adds in a fixed lane order), of cv::gemm's inner products (four interleaved
+    partial sums), cv::mulTransposed (one running sum per entry), and the back-substitution of cv::solve /
+    cv::invert(DECOMP_EIG) (multiplication by 1/w, threshold 2 eps sum(w))."""
+    for c in gold_lm["norm_l2sqr"]:
+        assert oracle.cv_norm_l2sqr(_unhex(c["r"])) == float.fromhex(c["out"])
+    for c in gold_lm["gemm_atb"]:
+        J, r = _unhex(c["J"], (c["rows"], 9)), _unhex(c["r"])
+        np.testing.assert_array_equal(oracle.cv_gemm_atb(J, r), _unhex(c["out"]))
+    for c in gold_lm["mul_transposed"]:
+        J = _unhex(c["J"], (c["rows"], 9))
+        A = np.zeros((9, 9))
+        for k in range(c["rows"]):
+            A += np.outer(J[k], J[k])                                   # one running sum per entry, row order
+        np.testing.assert_array_equal(A, _unhex(c["out"], (9, 9)))
+    for c in gold_lm["gemm_axpby"]:
+        out = oracle.cv_gemm_axpby(_unhex(c["A"], (9, 9)), _unhex(c["d"]), -1.0, _unhex(c["c"]), 2.0)
+        np.testing.assert_array_equal(out, _unhex(c["out"]))
+    for c in gold_lm["solve_eig"]:
+        np.testing.assert_array_equal(oracle.cv_solve_eig(_unhex(c["A"], (9, 9)), _unhex(c["b"])), _unhex(c["out"]))
+    for c in gold_lm["invert_eig_diag"]:
+        np.testing.assert_array_equal(oracle.cv_invert_eig_diag(_unhex(c["A"], (9, 9))), _unhex(c["out"]))
+
+
+def test_refit_and_lm_bit_exact_with_cv2(oracle, gold_lm):
+    """runKernel on k points + LMSolver(10) == cv2.findHomography(src, dst, 0), every bit of H, on 160 seeded problems
+    of 5 ... 39 points (noise 1e-3 ... 10, so early stops, rejected steps and the lambda == 0 branch all occur).  This
+    also pins cv::Mat::dot, which the Python binding does not expose (see cv_dot in the oracle)."""
+    cases = gold_lm["find_homography_0"]
+    assert len(cases) >= 150
+    iters = set()
+    for c in cases:
+        src, dst = _unhex(c["src"], (-1, 2)), _unhex(c["dst"], (-1, 2))
+        H0 = oracle.h_run_kernel(src, dst)
+        H, it = oracle.h_lm_refine(src, dst, H0)
+        iters.add(it)
+        np.testing.assert_array_equal(H, _unhex(c["H"], (3, 3)))
+    assert len(iters) >= 4          # the stopping rule is exercised at several iteration counts
 
 
 def test_fixture_a_sweep(oracle, gold):
@@ -67,6 +126,7 @@ def test_fixture_a_sweep(oracle, gold):
         pos2 = pipeline.candidate_pos2(pos3d, loc3ds[i])
         H, mask = oracle.find_homography(pos2, pixels, s["thr"])
         assert H is not None
+        np.testing.assert_array_equal(H, np.array(s["H"][i]))          # bit-identical to the cv2 4.13.0 binary
         worst = max(worst, relerr(H, s["H"][i]))
         np.testing.assert_array_equal(mask.ravel(), np.array(s["mask"][i], dtype=np.uint8))
         _, nm[i, 0], nm[i, 1] = pipeline._score(H, mask, pos2, pixels, s["thr"])
@@ -83,9 +143,9 @@ def test_debug_log_known_answers(oracle, gold):
     The RANSAC stage (sampler replay, degeneracy tests, 4-point solver, fp32 scoring, termination) reproduces the
     logged mask in all 24 complete blocks, and the logged matrix M = inv(refined H) to the log's printing precision
     and conditioning (<= 1e-3 relative, the same band in which the 4.13 binary reproduces it; SURVEY.md finding 5).
-    With OpenCV 4.13 semantics the oracle returns the binary's mask in 24/24 blocks; the refined H agrees to 1e-5 in
-    most blocks and to 5e-4 in all: these 28-point, 120 px problems are ill-conditioned and the 10-iteration LM
-    amplifies last-bit differences in J^T J (the restatement is not bit-identical to the binary's LM)."""
+    With OpenCV 4.13 semantics the oracle returns the binary's mask AND the binary's refined H, every bit of it, in
+    24/24 blocks (round 1: 4.2e-4 apart on the worst block, until the LM's linear algebra was pinned block by block:
+    test_lm_building_blocks_bit_exact)."""
     blocks = gold["debug_log"]
     assert len(blocks) == 24
     rel_M, rel_H = [], []
@@ -98,9 +158,10 @@ def test_debug_log_known_answers(oracle, gold):
         rel_M.append(relerr(M, b["logged_M"]))
         H413, mask413 = oracle.find_homography(pos2, p1, 120.0, mask_semantics=0)
         assert mask413.ravel().tolist() == b["cv413_mask"]
+        np.testing.assert_array_equal(H413, np.array(b["cv413_H"]))
         rel_H.append(relerr(H413, b["cv413_H"]))
     assert max(rel_M) < 1e-3 and np.median(rel_M) < 1e-6
-    assert max(rel_H) < 5e-4 and np.sum(np.array(rel_H) < REL_H_TOL) >= 18
+    assert max(rel_H) == 0.0
 
 
 def test_project_points_bit_exact(oracle, gold):
