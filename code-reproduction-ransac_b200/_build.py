@@ -19,7 +19,7 @@ TRANSLATION_UNITS = ["api.cu", "api_pnp.cu"]   # homography path, PnP path
 
 
 def _sources():
-    out = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    out = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
     out.append(os.path.join(PKG_DIR, "..", "include", "ransac_b200.h"))
     return out
 

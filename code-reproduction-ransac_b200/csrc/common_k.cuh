@@ -265,7 +265,7 @@ __device__ void solve_sym_eig(const double* A, const double* b, double* x, doubl
     for (int i = 0; i < N * N; ++i) a[i] = A[i];
     jacobi_eig<N>(a, W, V);
     double thr = 0;
-    for (int i = 0; i < N; ++i) thr += fabs(W[i]);
+    for (int i = 0; i < N; ++i) thr += W[i];   // OpenCV's SVBkSb: the SIGNED sum
     thr *= DBL_EPSILON * 2;
     for (int j = 0; j < N; ++j) {
         if (x) x[j] = 0;
@@ -273,15 +273,43 @@ __device__ void solve_sym_eig(const double* A, const double* b, double* x, doubl
     }
     for (int i = 0; i < N; ++i) {
         if (fabs(W[i]) <= thr) continue;
+        const double wi = 1 / W[i];            // ... multiplies by the reciprocal (pinned against cv2.solve / cv2.invert)
         if (x) {
             double s = 0;
             for (int j = 0; j < N; ++j) s += V[i * N + j] * b[j];
-            s /= W[i];
+            s *= wi;
             for (int j = 0; j < N; ++j) x[j] += s * V[i * N + j];
         }
         if (inv_diag)
-            for (int j = 0; j < N; ++j) inv_diag[j] += V[i * N + j] * V[i * N + j] / W[i];
+            for (int j = 0; j < N; ++j) inv_diag[j] += (V[i * N + j] * wi) * V[i * N + j];
     }
+}
+
+// The inner products of cv::LMSolver's linear algebra in the summation order of the cv2 4.13.0 binary (pinned bit for
+// bit in oracle/cv_ransac_oracle.c: acc4_dot, cv_dot; tests/golden/cv2_lm_blocks.json).
+// cv::gemm: four interleaved partial sums, the tail into the first, ((s0 + s1) + s2) + s3, products rounded.
+template <int N>
+__device__ __forceinline__ double cv_gemm_dot(const double* a, const double* b) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int k = 0;
+    for (; k <= N - 4; k += 4) {
+        s0 += a[k] * b[k];
+        s1 += a[k + 1] * b[k + 1];
+        s2 += a[k + 2] * b[k + 2];
+        s3 += a[k + 3] * b[k + 3];
+    }
+    for (; k < N; ++k) s0 += a[k] * b[k];
+    return ((s0 + s1) + s2) + s3;
+}
+// cv::Mat::dot: blocks of four with the compiler's FMA contraction — fma(a3, b3, fma(a2, b2, fma(a0, b0, a1 b1))) added
+// to the running sum — and a fused tail.
+template <int N>
+__device__ __forceinline__ double cv_mat_dot(const double* a, const double* b) {
+    double s = 0;
+    int i = 0;
+    for (; i <= N - 4; i += 4) s += fma(a[i + 3], b[i + 3], fma(a[i + 2], b[i + 2], fma(a[i], b[i], a[i + 1] * b[i + 1])));
+    for (; i < N; ++i) s = fma(a[i], b[i], s);
+    return s;
 }
 
 // solve_sym_eig executed by ONE WARP through the warp-cooperative Jacobi (jacobi_eig_warp3): same arithmetic, ~2.5x
@@ -297,19 +325,20 @@ __device__ void solve_sym_eig_warp(JacobiWarp9& jw, const double* A_src, const d
         jacobi_eig_warp3<N>(jw.A, jw.W, jw.V, jw.indR, jw.indC);
     }
     double thr = 0;
-    for (int i = 0; i < N; ++i) thr += fabs(jw.W[i]);
+    for (int i = 0; i < N; ++i) thr += jw.W[i];   // signed sum, as OpenCV's SVBkSb
     thr *= DBL_EPSILON * 2;
     if (lane < N) {
         double xj = 0, dj = 0;
         for (int i = 0; i < N; ++i) {
             if (fabs(jw.W[i]) <= thr) continue;
+            const double wi = 1 / jw.W[i];        // multiplication by the reciprocal, as OpenCV
             if (x) {
                 double s = 0;
                 for (int j = 0; j < N; ++j) s += jw.V[i * N + j] * b[j];
-                s /= jw.W[i];
+                s *= wi;
                 xj += s * jw.V[i * N + lane];
             }
-            if (inv_diag) dj += jw.V[i * N + lane] * jw.V[i * N + lane] / jw.W[i];
+            if (inv_diag) dj += (jw.V[i * N + lane] * wi) * jw.V[i * N + lane];
         }
         if (x) x[lane] = xj;
         if (inv_diag) inv_diag[lane] = dj;

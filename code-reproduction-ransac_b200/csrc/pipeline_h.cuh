@@ -643,24 +643,55 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     }
                 sh.Ac[tid] = acc;
             } else if (tid < 90) {
-                const int j = tid - 81;
-                double acc = 0;
+                // v = cv::gemm(J, r, GEMM_1_T): FOUR interleaved partial sums over the rows of the compressed J (row 2c,
+                // 2c+1 = inlier c), the (2k mod 4) tail rows into the first, combined ((s0 + s1) + s2) + s3
+                const int j = tid - 81, kfull = k & ~1;
+                double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                int c = 0;
                 for (int i = 0; i < n; ++i)
                     if (rmask[i]) {
                         const double* t = seq_tab + i * 20;
-                        acc += t[j] * t[18];
-                        acc += t[9 + j] * t[19];
+                        const double px = t[j] * t[18], py = t[9 + j] * t[19];
+                        if (c >= kfull) { s0 += px; s0 += py; }
+                        else if (c & 1) { s2 += px; s3 += py; }
+                        else { s0 += px; s1 += py; }
+                        ++c;
                     }
-                sh.vc[j] = acc;
+                sh.vc[j] = ((s0 + s1) + s2) + s3;
             } else if (tid == 90) {
-                double S = 0, rmax = 0;
+                // S = cv::norm(r, NORM_L2SQR) as the binary's AVX2 path sums it (oracle: norm_l2sqr): 16 elements per step
+                // by fused multiply-add into 4 x 4 lanes, ((r0 + r1) + r2) + r3 lane-wise, (l0 + l1) + (l2 + l3); then
+                // blocks of four rounded squares in order; the last (2k mod 4) elements fused
+                double lanes[16], S = 0, rmax = 0;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) lanes[e] = 0;
+                const int nmain = (2 * k) & ~15, n4 = (2 * k) & ~3;
+                int e = 0;
+                bool reduced = false;
                 for (int i = 0; i < n; ++i)
                     if (rmask[i]) {
                         const double rx = seq_tab[i * 20 + 18], ry = seq_tab[i * 20 + 19];
-                        S += rx * rx;
-                        S += ry * ry;
                         rmax = fmax(rmax, fmax(fabs(rx), fabs(ry)));
+                        if (e < nmain) {
+                            lanes[e & 15] = fma(rx, rx, lanes[e & 15]);
+                            lanes[(e + 1) & 15] = fma(ry, ry, lanes[(e + 1) & 15]);
+                        } else {
+                            if (!reduced) {
+                                double t4[4];
+                                for (int l = 0; l < 4; ++l) t4[l] = ((lanes[l] + lanes[4 + l]) + lanes[8 + l]) + lanes[12 + l];
+                                S += (t4[0] + t4[1]) + (t4[2] + t4[3]);
+                                reduced = true;
+                            }
+                            if (e < n4) { S += rx * rx; S += ry * ry; }
+                            else { S = fma(rx, rx, S); S = fma(ry, ry, S); }
+                        }
+                        e += 2;
                     }
+                if (!reduced) {
+                    double t4[4];
+                    for (int l = 0; l < 4; ++l) t4[l] = ((lanes[l] + lanes[4 + l]) + lanes[8 + l]) + lanes[12 + l];
+                    S += (t4[0] + t4[1]) + (t4[2] + t4[3]);
+                }
                 R.out[0] = S;
                 R.out[34] = rmax;
             }
@@ -787,10 +818,16 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                 sh.Sd = Sd;
                 sh.need_diag = 0;
                 double dS = 0;
-                for (int i = 0; i < 9; ++i) {
-                    double t = 0;
-                    for (int j = 0; j < 9; ++j) t += sh.A[i * 9 + j] * sh.d[j];
-                    dS += sh.d[i] * (2 * sh.v[i] - t);
+                if (seq) {   // cv::gemm(A, d, -1, v, 2) row by row (four partial sums), then cv::Mat::dot
+                    double tmp[9];
+                    for (int i = 0; i < 9; ++i) tmp[i] = cv_gemm_dot<9>(sh.A + i * 9, sh.d) * -1. + sh.v[i] * 2.;
+                    dS = cv_mat_dot<9>(sh.d, tmp);
+                } else {
+                    for (int i = 0; i < 9; ++i) {
+                        double t = 0;
+                        for (int j = 0; j < 9; ++j) t += sh.A[i * 9 + j] * sh.d[j];
+                        dS += sh.d[i] * (2 * sh.v[i] - t);
+                    }
                 }
                 const double Rr = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
                 if (Rr > 0.75) {
@@ -798,7 +835,8 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     if (sh.lambda < sh.lc) sh.lambda = 0;
                 } else if (Rr < 0.25) {
                     double t = 0;
-                    for (int i = 0; i < 9; ++i) t += sh.d[i] * sh.v[i];
+                    if (seq) t = cv_mat_dot<9>(sh.d, sh.v);
+                    else for (int i = 0; i < 9; ++i) t += sh.d[i] * sh.v[i];
                     double nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1) + 2;
                     nu = fmin(fmax(nu, 2.), 10.);
                     sh.nu = nu;

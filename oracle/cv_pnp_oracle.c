@@ -721,14 +721,14 @@ ORC_API int orc_pnp_refine_lm(const double* obj, const double* img, int n, const
         memcpy(Ap, A, sizeof(A));
         for (int i = 0; i < 6; i++) Ap[i * 6 + i] += lambda * D[i];
         orc_jacobi(Ap, 6, W, V); /* cv::solve(..., DECOMP_EIG) */
-        for (int i = 0; i < 6; i++) thr += fabs(W[i]);
-        thr *= DBL_EPSILON * 2;
+        for (int i = 0; i < 6; i++) thr += W[i];       /* SVBkSb: signed sum; multiplication by 1/w (pinned against */
+        thr *= DBL_EPSILON * 2;                        /* cv2.solve(DECOMP_EIG), see cv_ransac_oracle.c)             */
         for (int i = 0; i < 6; i++) d[i] = 0;
         for (int e = 0; e < 6; e++) {
             if (fabs(W[e]) <= thr) continue;
-            double s = 0;
+            double s = 0, wi = 1 / W[e];
             for (int a = 0; a < 6; a++) s += V[e * 6 + a] * v[a];
-            s /= W[e];
+            s *= wi;
             for (int a = 0; a < 6; a++) d[a] += s * V[e * 6 + a];
         }
         for (int i = 0; i < 6; i++) xd[i] = x[i] - d[i];
@@ -751,11 +751,11 @@ ORC_API int orc_pnp_refine_lm(const double* obj, const double* img, int n, const
                 double a2[36], maxval = DBL_EPSILON, th2 = 0;
                 memcpy(a2, A, sizeof(A));
                 orc_jacobi(a2, 6, W, V);
-                for (int i = 0; i < 6; i++) th2 += fabs(W[i]);
+                for (int i = 0; i < 6; i++) th2 += W[i];
                 th2 *= DBL_EPSILON * 2;
                 for (int j = 0; j < 6; j++) {
                     double dj = 0;
-                    for (int e = 0; e < 6; e++) if (fabs(W[e]) > th2) dj += V[e * 6 + j] * V[e * 6 + j] / W[e];
+                    for (int e = 0; e < 6; e++) if (fabs(W[e]) > th2) dj += (V[e * 6 + j] * (1 / W[e])) * V[e * 6 + j];
                     if (fabs(dj) > maxval) maxval = fabs(dj);
                 }
                 lambda = lc = 1. / maxval;
