@@ -68,6 +68,7 @@ SIGNATURES = {
     "b2r_h_problem_score_shard_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(HParams), C.c_void_p]),
     "b2r_h_problem_finish_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(HParams), C.c_void_p]),
     "b2r_h_problem_stage_ms": (C.c_int, [C.c_void_p, C.c_void_p, c_float_p]),
+    "b2r_h_problem_peek_hyps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, c_i32_p, c_float_p, c_i32_p]),
     "b2r_ctx_launch_count": (C.c_int, [C.c_void_p]),
     "b2r_score_h": (C.c_int, [C.c_void_p, c_float_p, C.c_int32, c_float_p, c_float_p, C.c_int32, C.c_float, C.c_int32,
                               c_i32_p]),

@@ -52,7 +52,8 @@ def make_params(thr, max_iters=2000, confidence=0.995, sampler=SAMPLER_CV_REPLAY
 
 def _info_dict(i):
     return dict(status=i.status, iters_run=i.iters_run, best_iter=i.best_iter, best_count=i.best_count,
-                sample=[int(x) for x in i.sample], n_inliers=i.n_inliers, lm_iters=i.lm_iters)
+                sample=[int(x) for x in i.sample], n_inliers=i.n_inliers, lm_iters=i.lm_iters,
+                winner_id=int(i.reserved[0]))   # PHILOX: global hypothesis id of the winner (low 31 bits), on every rank
 
 
 class _InfoSeq:
@@ -139,6 +140,16 @@ class HomographyProblem:
         self.ctx._check(self.ctx._L.b2r_h_problem_fetch(self.ctx._c, self._h, _ptr(H, C.c_double),
                                                         _ptr(mask, C.c_uint8) if want_mask else None, info))
         return H, mask, _InfoSeq(info, _info_dict)
+
+    def peek_hyps(self, first, count, q=0):
+        """Samples (count,4), fp32 models (count,8) and inlier counts (count) of hypothesis slots [first, first+count) of
+        problem q as the last run left them on the device (parity tests / diagnostics)."""
+        smp = np.zeros((count, 4), dtype=np.int32)
+        mdl = np.zeros((count, 8), dtype=np.float32)
+        cnt = np.zeros(count, dtype=np.int32)
+        self.ctx._check(self.ctx._L.b2r_h_problem_peek_hyps(self.ctx._c, self._h, int(q), int(first), int(count),
+                                                            _ptr(smp, C.c_int32), _ptr(mdl, C.c_float), _ptr(cnt, C.c_int32)))
+        return smp, mdl, cnt
 
     def stage_ms(self):
         ms = (C.c_float * 5)()

@@ -146,18 +146,17 @@ static int check_params(const b2r_h_params* p) {
     if (p->solver != B2R_SOLVER_EXACT && p->solver != B2R_SOLVER_FAST) return fail(B2R_ERR_ARG, "bad solver%s%s");
     if (p->max_iters > (1 << 30)) return fail(B2R_ERR_ARG, "max_iters too large%s%s");
     if (p->refine < B2R_REFINE_NONE || p->refine > B2R_REFINE_PARALLEL) return fail(B2R_ERR_ARG, "bad refine%s%s");
+    // the arg-max keys carry the global hypothesis id in 32 bits (count << 32 | ~id): ids beyond 2^32 would alias
+    if (p->sampler == B2R_SAMPLER_PHILOX &&
+        (p->hyp_begin < 0 || p->hyp_begin + (long long)(p->max_iters > 1 ? p->max_iters : 1) > (1LL << 32)))
+        return fail(B2R_ERR_ARG, "PHILOX hypothesis ids must lie in [0, 2^32): hyp_begin >= 0 and hyp_begin + max_iters <= 2^32%s%s");
     return B2R_OK;
 }
 
-// opt in to the 171 KB of dynamic shared memory of k_solve_h4_smem (once per process and device)
-static int k2s_prepare(b2r_ctx* c) {
-    static thread_local int done_device = -1;
-    if (done_device != c->device) {
-        CU(cudaFuncSetAttribute(k_solve_h4_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2S_SMEM));
-        done_device = c->device;
-    }
-    return B2R_OK;
-}
+// k_solve_h4_smem / k_jacobi_packed9 use K2S_SMEM = 31.5 KB of dynamic shared memory: below the 48 KB every kernel may
+// ask for without cudaFuncSetAttribute
+static_assert(K2S_SMEM <= 48 * 1024, "k_solve_h4_smem would need the dynamic shared memory opt-in");
+static int k2s_prepare(b2r_ctx*) { return B2R_OK; }
 
 template <int NPAIR>
 static int launch_k3(b2r_ctx* c, const float4* models, int H, int H_stride, const PointH* pts, int n, float thr_sq, int* counts,
@@ -432,6 +431,9 @@ static int run_finish(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p, cons
                              p->mask_semantics, p->refine, p->solver, pr->H.as<double>(), pr->mask.as<uint8_t>(),
                              pr->rmask.as<uint8_t>(), pr->info.as<int>(), nullptr, nullptr, Q, stored);
     if (rc) return rc;
+    if (n > 4 && (keys_host || keys_dev))
+        LAUNCH(c, k_patch_best_iter, (unsigned)((Q + 127) / 128), 128, 0, pr->info.as<int>(), pr->keys.as<unsigned long long>(),
+               (long long)p->hyp_begin, H, Q);
     CU(cudaGetLastError());
     CU(cudaEventRecord(pr->ev[4], c->stream));
     return B2R_OK;
@@ -521,6 +523,7 @@ int b2r_h_problem_finish(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p, c
     if (!c || !pr || !keys) return fail(B2R_ERR_ARG, "null argument%s%s");
     int rc = check_params(p);
     if (rc) return rc;
+    if (p->sampler != B2R_SAMPLER_PHILOX) return fail(B2R_ERR_ARG, "finishing from reduced keys needs the PHILOX sampler%s%s");
     CU(cudaSetDevice(c->device));
     return run_finish(c, pr, p, keys);
 }
@@ -541,6 +544,7 @@ int b2r_h_problem_finish_dev(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* 
     if (!c || !pr || !keys_dev) return fail(B2R_ERR_ARG, "null argument%s%s");
     int rc = check_params(p);
     if (rc) return rc;
+    if (p->sampler != B2R_SAMPLER_PHILOX) return fail(B2R_ERR_ARG, "finishing from reduced keys needs the PHILOX sampler%s%s");
     CU(cudaSetDevice(c->device));
     return run_finish(c, pr, p, nullptr, keys_dev);
 }
@@ -549,6 +553,22 @@ int b2r_h_problem_fetch(b2r_ctx* c, b2r_h_problem* pr, double* H_out, uint8_t* m
     if (!c || !pr) return fail(B2R_ERR_ARG, "null argument%s%s");
     CU(cudaSetDevice(c->device));
     return fetch(c, pr, H_out, mask_out, info_out);
+}
+
+int b2r_h_problem_peek_hyps(b2r_ctx* c, b2r_h_problem* pr, int32_t q, int32_t first, int32_t count, int32_t* samples_out,
+                            float* models8_out, int32_t* counts_out) {
+    if (!c || !pr || q < 0 || q >= pr->Q || first < 0 || count < 1 || (long long)first + count > pr->H_last)
+        return fail(B2R_ERR_ARG, "peek_hyps: slots [first, first + count) must lie inside the last run's hypotheses%s%s");
+    CU(cudaSetDevice(c->device));
+    const size_t slot = (size_t)q * pr->H_last + first;
+    if (samples_out)
+        CU(cudaMemcpyAsync(samples_out, pr->samples.as<int>() + 4 * slot, sizeof(int) * 4 * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
+    if (models8_out)
+        CU(cudaMemcpyAsync(models8_out, pr->models.as<float>() + 8 * slot, sizeof(float) * 8 * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
+    if (counts_out)
+        CU(cudaMemcpyAsync(counts_out, pr->counts.as<int>() + slot, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2R_OK;
 }
 
 int b2r_h_problem_stage_ms(b2r_ctx* c, b2r_h_problem* pr, float ms_out[5]) {
@@ -802,7 +822,6 @@ int b2r_jacobi_eig(b2r_ctx* c, const double* A, int32_t n_mat, int32_t n, int32_
     int rc = B2R_OK;
     if (form == 2) {
         if ((rc = k2s_prepare(c))) return rc;
-        CU(cudaFuncSetAttribute(k_jacobi_packed9, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2S_SMEM));
         LAUNCH(c, k_jacobi_packed9, (unsigned)((n_mat + K2S_THREADS - 1) / K2S_THREADS), K2S_THREADS, K2S_SMEM, dA, n_mat, dW, dV);
     } else {
         switch (n) {

@@ -43,6 +43,10 @@ static int check_p_params(const b2r_p_params* p) {
     if (p->arith != B2R_ARITH_EXACT && p->arith != B2R_ARITH_FAST) return fail(B2R_ERR_ARG, "bad arith%s%s");
     if (p->solver != B2R_SOLVER_EXACT && p->solver != B2R_SOLVER_FAST) return fail(B2R_ERR_ARG, "bad solver%s%s");
     if (p->max_iters > (1 << 30)) return fail(B2R_ERR_ARG, "iterationsCount too large%s%s");
+    // the arg-max keys carry the global hypothesis id in 32 bits (count << 32 | ~id): ids beyond 2^32 would alias
+    if (p->sampler == B2R_SAMPLER_PHILOX &&
+        (p->hyp_begin < 0 || p->hyp_begin + (long long)(p->max_iters > 1 ? p->max_iters : 1) > (1LL << 32)))
+        return fail(B2R_ERR_ARG, "PHILOX hypothesis ids must lie in [0, 2^32): hyp_begin >= 0 and hyp_begin + iterationsCount <= 2^32%s%s");
     return B2R_OK;
 }
 
@@ -285,6 +289,9 @@ static int p_run_finish(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p, co
                             (const double*)(pr->rt_valid && !keys_host && !keys_dev ? pr->rt.as<double>() : nullptr), pr->rmask.as<uint8_t>(),
                             pr->pose.as<double>(), pr->info_i.as<int>(), pr->info_d.as<double>());
     if (rc) return rc;
+    if (n > PNP_MP && (keys_host || keys_dev))
+        LAUNCH(c, k_patch_best_iter, (unsigned)((Q + 127) / 128), 128, 0, pr->info_i.as<int>(), pr->keys.as<unsigned long long>(),
+               (long long)p->hyp_begin, H, Q);
     LAUNCH(c, k_compact_inliers, (unsigned)Q, 1024, 0, pr->rmask.as<uint8_t>(), n, pr->inliers.as<int>(), pr->ninl.as<int>());
     CU(cudaGetLastError());
     CU(cudaEventRecord(pr->ev[4], c->stream));
@@ -419,6 +426,7 @@ int b2r_p_problem_finish(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p, c
     if (!c || !pr || !keys) return fail(B2R_ERR_ARG, "null argument%s%s");
     int rc = check_p_params(p);
     if (rc) return rc;
+    if (p->sampler != B2R_SAMPLER_PHILOX) return fail(B2R_ERR_ARG, "finishing from reduced keys needs the PHILOX sampler%s%s");
     CU(cudaSetDevice(c->device));
     return p_run_finish(c, pr, p, keys);
 }
@@ -439,6 +447,7 @@ int b2r_p_problem_finish_dev(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* 
     if (!c || !pr || !keys_dev) return fail(B2R_ERR_ARG, "null argument%s%s");
     int rc = check_p_params(p);
     if (rc) return rc;
+    if (p->sampler != B2R_SAMPLER_PHILOX) return fail(B2R_ERR_ARG, "finishing from reduced keys needs the PHILOX sampler%s%s");
     CU(cudaSetDevice(c->device));
     return p_run_finish(c, pr, p, nullptr, keys_dev);
 }

@@ -117,7 +117,7 @@ static __global__ void k_select_from_keys(const unsigned long long* __restrict__
     s.best = count > model_points - 1 ? (int)(gid - (id_base & 0xFFFFFFFFull)) : -1;
     s.best_count = count > model_points - 1 ? count : 0;
     s.iters_run = H;
-    s.pad = 0;
+    s.pad = (int)(gid & 0x7fffffff);   // info.reserved[0]: the winner's global id (low 31 bits), as after a keyed finish
     sel[q] = s;
 }
 
@@ -454,3 +454,14 @@ __device__ void cholesky_solve_warp(const double* L, const double* b, double* x)
 }
 
 }  // namespace b2r
+
+// sharded finish: info.best_iter = winning hypothesis id - hyp_begin, or -1 when the winner lives on another rank's shard
+static __global__ void k_patch_best_iter(int* __restrict__ info, const unsigned long long* __restrict__ keys, long long hyp_begin,
+                                  int H, int Q) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    if (info[(size_t)q * 12 + 2] < 0) return;   // no model
+    const long long gid = (long long)(0xFFFFFFFFull - (keys[q] & 0xFFFFFFFFull)) - hyp_begin;
+    info[(size_t)q * 12 + 2] = (gid >= 0 && gid < H) ? (int)gid : -1;
+}
+

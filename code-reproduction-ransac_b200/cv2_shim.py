@@ -46,7 +46,10 @@ def findHomography(srcPoints, dstPoints, method=0, ransacReprojThreshold=3.0, ma
         exc = cv2.error if cv2 is not None else error
         raise exc("findHomography: need >= 4 corresponding points (OpenCV asserts in fundam.cpp)")
     ctx = _ctx or api.default_context()
-    H, m, _ = ctx.find_homography(src, dst, float(ransacReprojThreshold), int(maxIters), float(confidence), **b2r_kw)
+    thr = float(ransacReprojThreshold)
+    if not thr > 0:      # OpenCV substitutes its default (fundam.cpp: `if (ransacReprojThreshold <= 0) ... = 3`);
+        thr = 3.0        # probed on the 4.13.0 binary: thr = 0, -1, -5.5 all return the thr = 3 result
+    H, m, _ = ctx.find_homography(src, dst, thr, int(maxIters), float(confidence), **b2r_kw)
     return H, m
 
 

@@ -89,7 +89,9 @@ def find_homographies(recs, camera_locations, im=None, show=False, ransacbound=7
                     raise np.linalg.LinAlgError(f"findHomography returned no model for candidate {i} "
                                                 "(the reference fails at main_v1.py:314)")
                 Ms[i], num_matches[i] = res["M"][i], res["scores"][i]
-        best = res["best"]
+        # The device arg-min (res["best"]) runs over all Q candidates; the reference's rule is applied to the scores the
+        # host loop kept (candidates below grid_code_min stay 0 -> 1e6; np.argmin returns the first NaN): Q doubles.
+        best = best_location(num_matches)
     else:
         pos2 = candidate_pos2(pos3ds[None, good, :], loc3ds[:, None, :])          # (Q, n, 2)
         H, ok, mask, infos = ctx.find_homography_batch(pos2, pixels[good], ransacbound, **ransac_kw)

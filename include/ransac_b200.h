@@ -72,7 +72,8 @@ typedef struct {
     int32_t arith;       /* B2R_ARITH_*                                                                      */
     int32_t mask_semantics; /* B2R_MASK_*                                                                    */
     int32_t refine;      /* B2R_REFINE_* : 1 refit on inliers + 10 Levenberg-Marquardt iterations, as cv2 does; 0 skip */
-    /* hypothesis-id shard of this rank (PHILOX only): ids [hyp_begin, hyp_begin + max_iters) are scored.   */
+    /* hypothesis-id shard of this rank (PHILOX only): ids [hyp_begin, hyp_begin + max_iters) are scored.  Ids must lie
+     * in [0, 2^32) (the arg-max key carries the id in 32 bits): hyp_begin < 0 or hyp_begin + max_iters > 2^32 -> B2R_ERR_ARG */
     int64_t hyp_begin;
     int32_t solver;      /* B2R_SOLVER_*                                                                     */
     int32_t reserved;
@@ -81,12 +82,14 @@ typedef struct {
 typedef struct {
     int32_t status;       /* B2R_OK / B2R_NO_MODEL                                          */
     int32_t iters_run;    /* RANSAC iterations executed (CV_REPLAY) / hypotheses scored      */
-    int32_t best_iter;    /* 0-based iteration (CV_REPLAY) or hypothesis id - hyp_begin      */
+    int32_t best_iter;    /* 0-based iteration (CV_REPLAY) or hypothesis id - hyp_begin; -1 after a sharded
+                             finish whose winner lies in another rank's shard                 */
     int32_t best_count;   /* RANSAC-stage inlier count of the winning hypothesis             */
     int32_t sample[4];    /* its minimal sample (point indices)                              */
     int32_t n_inliers;    /* number of ones in the returned mask                             */
     int32_t lm_iters;     /* LM iterations executed by the refinement                        */
-    int32_t reserved[2];
+    int32_t reserved[2];  /* [0]: PHILOX sampler: global hypothesis id of the winner, low 31 bits (the same on
+                             every rank of a sharded run)                                     */
 } b2r_h_info;
 
 /* ---- life cycle -------------------------------------------------------------------------------------- */
@@ -148,6 +151,11 @@ int b2r_h_problem_finish(b2r_ctx* ctx, b2r_h_problem* prob, const b2r_h_params* 
  * stream: a collective library can reduce them in place (NCCL all-reduce enqueued on that stream) without a host round trip. */
 int b2r_h_problem_score_shard_dev(b2r_ctx* ctx, b2r_h_problem* prob, const b2r_h_params* params, uint64_t* keys_dev_out);
 int b2r_h_problem_finish_dev(b2r_ctx* ctx, b2r_h_problem* prob, const b2r_h_params* params, const uint64_t* keys_dev);
+/* Diagnostics / parity tests: copies hypothesis slots [first, first + count) of problem q as the LAST run left them on the
+ * device — minimal samples (count,4) int32, fp32 models (count,8) as K3 scored them (NaN: rejected), inlier counts (count)
+ * int32.  Any output may be NULL.  Slot i holds hypothesis id hyp_begin + i (PHILOX) / iteration i (CV_REPLAY). */
+int b2r_h_problem_peek_hyps(b2r_ctx* ctx, b2r_h_problem* prob, int32_t q, int32_t first, int32_t count, int32_t* samples_out,
+                            float* models8_out, int32_t* counts_out);
 /* Device time (ms, CUDA events on the context stream) of the stages of the last run:
  * [0] sample+solve, [1] scoring kernel, [2] select, [3] finalize (mask/refit/LM), [4] total. */
 int b2r_h_problem_stage_ms(b2r_ctx* ctx, b2r_h_problem* prob, float ms_out[5]);

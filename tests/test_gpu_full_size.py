@@ -6,7 +6,9 @@ Properties: (a) the returned mask is exactly the reference's fp32 un-fused error
 returned H — recomputed here with NumPy float32 arithmetic, which rounds every operation like the reference's scalar
 code; (b) the winner of a hypothesis-sharded run equals the winner of the unsharded run (counter-based sampler);
 (c) the best count is the maximum of the per-hypothesis counts and the lowest id attaining it; (d) fast arithmetic
-finds the same consensus set up to threshold-borderline points."""
+finds the same consensus set up to threshold-borderline points; and (e) a direct ORACLE comparison that stays cheap at
+any size: the per-hypothesis inlier counts of 64 random hypotheses + the winner, read back from the device after the
+full-size launch (b2r_h_problem_peek_hyps), equal the CPU oracle's counts of those fp32 models over all points."""
 import numpy as np
 import pytest
 
@@ -31,7 +33,7 @@ def reference_mask_f32(H, src, dst, thr):
 
 
 @pytest.mark.parametrize("cfg,shards", [(2, 4), (3, 8)])
-def test_large_single_problem_properties(ctx, cfg, shards):
+def test_large_single_problem_properties(ctx, oracle, cfg, shards):
     c = synth.CONFIGS[cfg]
     src, dst = synth.config_homography(cfg)
     n, Htot, thr = c["n_points"], c["hypotheses"], 3.0
@@ -43,6 +45,18 @@ def test_large_single_problem_properties(ctx, cfg, shards):
     H0, m0, i0 = prob.fetch()
     assert i0[0]["status"] == 0 and i0[0]["best_count"] > 0.9 * (1 - c["outliers"]) * n * 0.9
     np.testing.assert_array_equal(m0[0], reference_mask_f32(H0[0], src, dst, thr))                      # (a)
+    # (e) ORACLE comparison at full size: the counts K3 left on the device for 64 random hypotheses + the winner, against
+    # the CPU oracle's count of the very fp32 models the kernel scored (exact arithmetic: equality)
+    ids = np.unique(np.r_[np.random.default_rng(cfg).integers(0, Htot, 64), i0[0]["best_iter"]])
+    peek = [prob.peek_hyps(int(g), 1) for g in ids]
+    models0 = np.concatenate([p[1] for p in peek])
+    counts0 = np.concatenate([p[2] for p in peek])
+    valid = ~np.isnan(models0).any(axis=1)
+    assert valid.sum() >= 48
+    want = oracle.h_count_inliers_f32(models0[valid], src, dst, np.float32(thr * thr))
+    np.testing.assert_array_equal(counts0[valid], want)
+    assert (counts0[~valid] == 0).all()
+    assert counts0[list(ids).index(i0[0]["best_iter"])] == i0[0]["best_count"]
     # sharded by hypothesis id (what 8 ranks do), MAX of the packed keys
     per = Htot // shards
     keys = [prob.score_shard(ransac_b200.make_params(thr, per, arith=ransac_b200.ARITH_EXACT, hyp_begin=r * per, **kw)) for r in range(shards)]
@@ -58,6 +72,12 @@ def test_large_single_problem_properties(ctx, cfg, shards):
     prob.run(ransac_b200.make_params(thr, Htot, arith=ransac_b200.ARITH_FAST, **kw))
     Hf, mf, i_f = prob.fetch()
     assert abs(i_f[0]["best_count"] - i0[0]["best_count"]) <= max(3, n // 20000)                       # (d)
+    # fast arithmetic against the oracle on the same 65 hypotheses: FMA margins may flip threshold-borderline points only
+    peek = [prob.peek_hyps(int(g), 1) for g in ids]
+    models_f = np.concatenate([p[1] for p in peek])
+    counts_f = np.concatenate([p[2] for p in peek])
+    np.testing.assert_array_equal(models_f[valid], models0[valid])       # the same hypotheses (sampler + solver are shared)
+    assert np.abs(counts_f[valid].astype(np.int64) - want).max() <= max(3, n // 20000)
     if i_f[0]["sample"] == i0[0]["sample"]:
         assert np.abs(Hf - H0).max() / np.abs(H0).max() < 1e-5
     np.testing.assert_array_equal(mf[0], reference_mask_f32(Hf[0], src, dst, thr))                      # the final mask is always exact

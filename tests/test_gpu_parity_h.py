@@ -322,3 +322,42 @@ def test_refine_building_block(ctx, oracle, n, seed):
     assert iters == it_ref
     assert np.abs(H - Href).max() / np.abs(Href).max() < 1e-8
     assert np.abs(H - Hr).max() / np.abs(Hr).max() < 1e-8          # = what the whole call returns
+
+
+@pytest.mark.parametrize("n,seed,hyp_begin", [(12, 70, 0), (500, 71, 0), (500, 72, 2**31 + 12345), (9, 73, 2**32 - 600)])
+def test_philox_sampler_matches_restatement(ctx, oracle, n, seed, hyp_begin):
+    """North-star kernel 1 (b2r_sample_philox -> k_philox_sample_solve_h): the samples of 600 hypothesis ids equal the
+    NumPy restatement (oracle/philox.py: Philox4x32-10 pinned by Random123's known answers, the rejection-free distinct-
+    index map, OpenCV's checkSubset from the C oracle, at most 16 attempts), for ids at 0, above 2^31 and up to 2^32 - 1;
+    every sample has 4 distinct in-range indices; splitting the id range anywhere returns the same samples; ids beyond
+    2^32 are refused (the arg-max key carries the id in 32 bits)."""
+    from oracle import philox
+    if n == 9:   # lattice: most subsets contain three collinear points, so later attempts are exercised
+        s = np.array([(100.0 * (i % 3), 100.0 * (i // 3)) for i in range(9)])
+        d = s * 1.1 + 7.0
+    else:
+        s, d = _problem(n, 0.4, seed)
+    sq, dq = _quant(s), _quant(d)
+    n_hyp, key = 600, 0x1234_5678_9ABC_DEF0 + seed
+    got = ctx.sample_philox(sq, dq, key, hyp_begin, n_hyp)
+    want = philox.sample_h(sq, dq, key, hyp_begin, n_hyp, oracle.h_check_subset)
+    np.testing.assert_array_equal(got, want)
+    ok = got[:, 0] >= 0
+    assert ok.sum() >= (n_hyp // 4 if n == 9 else n_hyp - 2)
+    assert (got[ok] >= 0).all() and (got[ok] < n).all()
+    assert all(len(set(row)) == 4 for row in got[ok].tolist())
+    if n == 9:
+        assert (~ok).sum() == (want[:, 0] < 0).sum()
+    for cut in (1, 257, 599):
+        a = ctx.sample_philox(sq, dq, key, hyp_begin, cut)
+        b = ctx.sample_philox(sq, dq, key, hyp_begin + cut, n_hyp - cut)
+        np.testing.assert_array_equal(np.concatenate([a, b]), got)
+
+
+def test_philox_id_range_is_checked(ctx):
+    s, d = _problem(100, 0.3, 80)
+    for bad in (dict(hyp_begin=-1, max_iters=10), dict(hyp_begin=2**32 - 5, max_iters=10)):
+        with pytest.raises(ransac_b200.RansacB200Error):
+            ctx.find_homography(s, d, 3.0, sampler=ransac_b200.SAMPLER_PHILOX, seed=1, **bad)
+    H, m, info = ctx.find_homography(s, d, 3.0, sampler=ransac_b200.SAMPLER_PHILOX, seed=1, hyp_begin=2**32 - 10, max_iters=10)
+    assert info["iters_run"] == 10

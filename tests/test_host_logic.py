@@ -215,3 +215,25 @@ def test_two_rank_key_reduce_over_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"ok {r}" in o
+
+
+def test_philox_known_answers():
+    """Philox4x32-10 (north-star kernel 1) against the three known-answer vectors of Random123's kat_vectors; the GPU
+    sampler is compared with this restatement in tests/test_gpu_parity_h.py::test_philox_sampler_matches_restatement."""
+    from oracle import philox
+    for ctr, key, want in philox.KNOWN_ANSWERS:
+        got = philox.philox4x32_10(*ctr, *key)
+        assert [int(x) for x in got] == list(want)
+    # vectorised form == scalar form
+    ids = np.arange(5, dtype=np.uint64) + np.uint64(0xFFFFFFFE)
+    v = philox.philox4x32_10(ids & np.uint64(0xFFFFFFFF), ids >> np.uint64(32), 3, 0, 7, 0)
+    for i, g in enumerate(ids):
+        s = philox.philox4x32_10(int(g) & 0xFFFFFFFF, int(g) >> 32, 3, 0, 7, 0)
+        assert [int(x[i]) for x in v] == [int(x) for x in s]
+    # distinct(): k distinct indices in range, uniform mapping of the words
+    rng = np.random.default_rng(0)
+    for n in (4, 5, 12, 1000):
+        for _ in range(200):
+            idx = philox.distinct(rng.integers(0, 2**32, 4).tolist(), n)
+            assert len(set(idx)) == 4 and min(idx) >= 0 and max(idx) < n
+    assert philox.distinct([0, 0, 0, 0], 4) == [0, 1, 2, 3] and philox.distinct([2**32 - 1] * 4, 4) == [3, 2, 1, 0]
