@@ -15,7 +15,7 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
 ]
-TRANSLATION_UNITS = ["api.cu", "api_pnp.cu"]   # homography path, PnP path
+TRANSLATION_UNITS = ["api.cu", "api_pnp.cu", "api_geo.cu"]   # homography path, PnP path, DEM ray-march
 
 
 def _sources():

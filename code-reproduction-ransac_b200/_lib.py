@@ -105,6 +105,14 @@ SIGNATURES = {
     "b2r_pnp_minimal_models": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, c_double_p, c_i32_p, C.c_int32,
                                          C.c_int32, c_double_p, c_double_p, c_double_p, c_u8_p]),
     "b2r_sample_cv_p": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_i32_p]),
+    # ---- DEM ray-march (row f4)
+    "b2r_dem_upload": (C.c_void_p, [C.c_void_p, c_double_p, C.c_int32, c_double_p, C.c_int32, c_double_p]),
+    "b2r_dem_free": (None, [C.c_void_p, C.c_void_p]),
+    "b2r_ray_march_dem": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_int32, c_double_p, C.c_int32, c_double_p, C.c_double,
+                                    C.c_double, C.c_int32, c_double_p, c_i32_p, c_i32_p]),
+    "b2r_pixels_to_geo": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p,
+                                    c_double_p, C.c_int32, c_double_p, C.c_double, C.c_double, C.c_int32, c_double_p, c_i32_p,
+                                    c_i32_p, c_double_p]),
 }
 
 _lib = None

@@ -277,6 +277,37 @@ class PnPProblem:
             pass
 
 
+class Dem:
+    """A DEM grid resident in HBM (b2r_dem)."""
+
+    def __init__(self, ctx, grid_y, grid_x, values):
+        gy = np.asarray(grid_y, dtype=np.float64).ravel()
+        gx = np.asarray(grid_x, dtype=np.float64).ravel()
+        v = np.asarray(values, dtype=np.float64)
+        if v.shape != (len(gy), len(gx)):
+            raise ValueError("values must be (len(grid_y), len(grid_x))")
+        if len(gy) > 1 and gy[1] < gy[0]:      # scipy's RegularGridInterpolator flips descending axes (and the values)
+            gy, v = gy[::-1], v[::-1, :]
+        if len(gx) > 1 and gx[1] < gx[0]:
+            gx, v = gx[::-1], v[:, ::-1]
+        gy, gx, v = np.ascontiguousarray(gy), np.ascontiguousarray(gx), np.ascontiguousarray(v)
+        self.ctx, self.shape = ctx, v.shape
+        self._h = ctx._L.b2r_dem_upload(ctx._c, _ptr(gy, C.c_double), len(gy), _ptr(gx, C.c_double), len(gx), _ptr(v, C.c_double))
+        if not self._h:
+            raise RansacB200Error(_lib.last_error())
+
+    def free(self):
+        if self._h:
+            self.ctx._L.b2r_dem_free(self.ctx._c, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Context:
     """One GPU context (own CUDA stream and workspaces).  Not thread-safe."""
 
@@ -491,6 +522,50 @@ class Context:
         self._check(self._L.b2r_refine_h(self._c, _ptr(s, C.c_float), _ptr(d, C.c_float), len(s), _ptr(m, C.c_uint8),
                                          _ptr(H, C.c_double), C.byref(it)))
         return H.reshape(3, 3), it.value
+
+    # ---- row f4: the DEM ray-march (main_v1.py:635-684, :765-785) --------------------------------------------------
+    def upload_dem(self, grid_y, grid_x, values):
+        """DEM resident in HBM: the grid of RegularGridInterpolator((dem_y, dem_x), dem_array), main_v1.py:454.
+        Descending axes are flipped (with the values), as scipy does at construction."""
+        return Dem(self, grid_y, grid_x, values)
+
+    def ray_march_dem(self, dem, origins, dirs, max_search_dist=10000, step=1, min_steps=150):
+        """ray_intersect_dem (main_v1.py:635-658) for m rays in one launch.  origins (3,) or (m,3); dirs (m,3).
+        Returns (geo (m,3), hit_step (m,), status (m,): 0 hit, 1 no intersection, 2 left the DEM)."""
+        from . import geo
+        o = np.ascontiguousarray(np.asarray(origins, dtype=np.float64))
+        d = np.ascontiguousarray(np.asarray(dirs, dtype=np.float64).reshape(-1, 3))
+        m = len(d)
+        shared = o.ndim == 1
+        if not shared and o.shape != (m, 3):
+            raise ValueError("origins must be (3,) or (m,3)")
+        out, hit, st = np.zeros((m, 3)), np.zeros(m, dtype=np.int32), np.zeros(m, dtype=np.int32)
+        u = geo.utm_series_constants()
+        self._check(self._L.b2r_ray_march_dem(self._c, dem._h, _ptr(o, C.c_double), 1 if shared else 0, _ptr(d, C.c_double), m,
+                                              _ptr(u, C.c_double), float(max_search_dist), float(step), int(min_steps),
+                                              _ptr(out, C.c_double), _ptr(hit, C.c_int32), _ptr(st, C.c_int32)))
+        return out, hit, st
+
+    def pixels_to_geo(self, dem, pixels, Kinv, R, ray_origin, ctrl_pixels, ctrl_factors, max_search_dist=10000, step=1,
+                      min_steps=150):
+        """pixel_to_geo (main_v1.py:661-684) for m pixels in one launch sequence.  Returns (geo, hit_step, status, dirs)."""
+        from . import geo
+        px = np.ascontiguousarray(np.asarray(pixels, dtype=np.float64).reshape(-1, 2))
+        cp = np.ascontiguousarray(np.asarray(ctrl_pixels, dtype=np.float64).reshape(-1, 2))
+        cf = np.ascontiguousarray(np.asarray(ctrl_factors, dtype=np.float64).reshape(-1, 3))
+        if len(cp) != len(cf):
+            raise ValueError("every control point needs its optimisation factors (np.average raises in the reference otherwise)")
+        Ki = np.ascontiguousarray(np.asarray(Kinv, dtype=np.float64).reshape(3, 3))
+        Rm = np.ascontiguousarray(np.asarray(R, dtype=np.float64).reshape(3, 3))
+        o = np.ascontiguousarray(np.asarray(ray_origin, dtype=np.float64).reshape(3))
+        m = len(px)
+        out, hit, st, dirs = np.zeros((m, 3)), np.zeros(m, dtype=np.int32), np.zeros(m, dtype=np.int32), np.zeros((m, 3))
+        u = geo.utm_series_constants()
+        self._check(self._L.b2r_pixels_to_geo(self._c, dem._h, _ptr(px, C.c_double), m, _ptr(Ki, C.c_double), _ptr(Rm, C.c_double),
+                                              _ptr(o, C.c_double), _ptr(cp, C.c_double), _ptr(cf, C.c_double), len(cp),
+                                              _ptr(u, C.c_double), float(max_search_dist), float(step), int(min_steps),
+                                              _ptr(out, C.c_double), _ptr(hit, C.c_int32), _ptr(st, C.c_int32), _ptr(dirs, C.c_double)))
+        return out, hit, st, dirs
 
     def jacobi_eig(self, A, form=1):
         """Eigenvalues (descending) and eigenvectors (rows) of symmetric matrices A (n_mat, n, n), 2 <= n <= 9, by the

@@ -278,6 +278,33 @@ int b2r_pnp_minimal_models(b2r_ctx* ctx, const double* obj_host, const double* i
 /* K1: the first n_iters 5-point subsets OpenCV's RANSAC draws for n points.  idx_out (n_iters,5). */
 int b2r_sample_cv_p(b2r_ctx* ctx, int32_t n, int32_t n_iters, int32_t* idx_out);
 
+/* ---- downstream georeferencing: the DEM ray-march -------------------------------------------
+ * Replaces the per-vertex Python loops of the reference:
+ *   ray_intersect_dem        /root/reference/main_v1.py:635-658  (10 000 x [pyproj UTM->WGS84, DEM bilinear lookup, test])
+ *   pixel_to_geo             /root/reference/main_v1.py:661-684  (weights :577-596, weighted factors :627-632, pixel_to_ray :547-574)
+ *   convert_boundary_to_geo  /root/reference/main_v1.py:765-785  (every polygon vertex of the annotation JSON)
+ * A DEM is the grid of scipy's RegularGridInterpolator((dem_y, dem_x), dem_array) (main_v1.py:454): strictly ASCENDING
+ * axes grid_y (latitude, ny) and grid_x (longitude, nx) in degrees — scipy flips descending axes, pass them flipped —
+ * and values (ny, nx) float64, row-major.  utm_series16 = {k0 A, lon0 [rad], FE, FN, beta[6], delta[6]}: the constants of
+ * the inverse transverse Mercator series (host layer: geo.utm_series_constants(), EPSG:32650).
+ * Outputs per ray: status 0 = hit (geo_out = E, N, height of the first step s >= min_steps with height <= DEM;
+ * the reference's rule with min_steps = 150), 1 = no intersection within int(max_search_dist / step) steps, 2 = a step
+ * left the DEM (the interpolator raises; the reference returns None in both cases); hit_step_out = that step. */
+typedef struct b2r_dem b2r_dem;
+b2r_dem* b2r_dem_upload(b2r_ctx* ctx, const double* grid_y, int32_t ny, const double* grid_x, int32_t nx, const double* values);
+void b2r_dem_free(b2r_ctx* ctx, b2r_dem* dem);
+/* ray_intersect_dem for m rays: origins (m,3) or one shared origin (origin_shared != 0), unit directions (m,3), UTM metres. */
+int b2r_ray_march_dem(b2r_ctx* ctx, const b2r_dem* dem, const double* origins, int32_t origin_shared, const double* dirs, int32_t m,
+                      const double* utm_series16, double max_search_dist, double step, int32_t min_steps, double* geo_out,
+                      int32_t* hit_step_out, int32_t* status_out);
+/* pixel_to_geo for m pixels (m,2): Kinv = inverse camera matrix (3,3), R = world->camera rotation (3,3), ray_origin (3),
+ * n_ctrl control points with their pixels (n_ctrl,2) and optimisation factors (n_ctrl,3).  dirs_out (m,3), optional: the
+ * corrected unit ray directions. */
+int b2r_pixels_to_geo(b2r_ctx* ctx, const b2r_dem* dem, const double* pixels, int32_t m, const double* Kinv, const double* R,
+                      const double* ray_origin, const double* ctrl_pixels, const double* ctrl_factors, int32_t n_ctrl,
+                      const double* utm_series16, double max_search_dist, double step, int32_t min_steps, double* geo_out,
+                      int32_t* hit_step_out, int32_t* status_out, double* dirs_out);
+
 #ifdef __cplusplus
 }
 #endif
