@@ -5,9 +5,9 @@ main_v1.py:312 and cv2.solvePnPRansac at main_v1.py:497) and for the Python loop
 name contains hyphens, so it is imported through the alias module `ransac_b200.py` at the repo root.
 """
 from . import _build  # noqa: F401
-from .api import (ARITH_EXACT, ARITH_FAST, MASK_CV413, MASK_LEGACY, REFINE_CV, REFINE_NONE, REFINE_PARALLEL, SAMPLER_CV_REPLAY, SAMPLER_PHILOX, SOLVER_EXACT, SOLVER_FAST, Context,
+from .api import (ARITH_EXACT, ARITH_EXACT_UNFILTERED, ARITH_FAST, MASK_CV413, MASK_LEGACY, REFINE_CV, REFINE_NONE, REFINE_PARALLEL, SAMPLER_CV_REPLAY, SAMPLER_PHILOX, SOLVER_EXACT, SOLVER_FAST, Context,
                   HomographyProblem, PnPProblem, RansacB200Error, default_context, make_p_params, make_params)
 
-__all__ = ["Context", "HomographyProblem", "RansacB200Error", "default_context", "make_params", "make_p_params", "PnPProblem", "ARITH_EXACT", "ARITH_FAST",
+__all__ = ["Context", "HomographyProblem", "RansacB200Error", "default_context", "make_params", "make_p_params", "PnPProblem", "ARITH_EXACT", "ARITH_EXACT_UNFILTERED", "ARITH_FAST",
            "MASK_CV413", "MASK_LEGACY", "SAMPLER_CV_REPLAY", "SAMPLER_PHILOX", "SOLVER_EXACT", "SOLVER_FAST", "REFINE_NONE", "REFINE_CV", "REFINE_PARALLEL"]
 __version__ = "0.1.0"

@@ -11,7 +11,7 @@ from . import _lib
 from ._lib import HInfo, HParams, PInfo, PParams
 
 SAMPLER_CV_REPLAY, SAMPLER_PHILOX = 0, 1
-ARITH_EXACT, ARITH_FAST = 0, 1
+ARITH_EXACT, ARITH_FAST, ARITH_EXACT_UNFILTERED = 0, 1, 2
 MASK_CV413, MASK_LEGACY = 0, 1
 SOLVER_EXACT, SOLVER_FAST, SOLVER_EXACT_WARP = 0, 1, 2
 REFINE_NONE, REFINE_CV, REFINE_PARALLEL = 0, 1, 2

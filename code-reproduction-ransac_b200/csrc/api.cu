@@ -3,6 +3,7 @@
 // fallback: each entry point fails with B2R_ERR_CUDA when no device is usable.
 #include "host_common.h"
 #include "sweep.cuh"
+#include "score_h_filt.cuh"
 
 using namespace b2r;
 
@@ -142,7 +143,8 @@ static int check_params(const b2r_h_params* p) {
     if (!p) return fail(B2R_ERR_ARG, "null params%s%s");
     if (!(p->thr >= 0)) return fail(B2R_ERR_ARG, "thr must be >= 0%s%s");
     if (p->sampler != B2R_SAMPLER_CV_REPLAY && p->sampler != B2R_SAMPLER_PHILOX) return fail(B2R_ERR_ARG, "bad sampler%s%s");
-    if (p->arith != B2R_ARITH_EXACT && p->arith != B2R_ARITH_FAST) return fail(B2R_ERR_ARG, "bad arith%s%s");
+    if (p->arith != B2R_ARITH_EXACT && p->arith != B2R_ARITH_FAST && p->arith != B2R_ARITH_EXACT_UNFILTERED)
+        return fail(B2R_ERR_ARG, "bad arith%s%s");
     if (p->solver != B2R_SOLVER_EXACT && p->solver != B2R_SOLVER_FAST) return fail(B2R_ERR_ARG, "bad solver%s%s");
     if (p->max_iters > (1 << 30)) return fail(B2R_ERR_ARG, "max_iters too large%s%s");
     if (p->refine < B2R_REFINE_NONE || p->refine > B2R_REFINE_PARALLEL) return fail(B2R_ERR_ARG, "bad refine%s%s");
@@ -168,7 +170,15 @@ static int launch_k3(b2r_ctx* c, const float4* models, int H, int H_stride, cons
     if (tile > n) tile = ((n + 7) / 8) * 8;
     const size_t smem = 128 + (size_t)tile * 16;
     dim3 grid((unsigned)hyp_blocks, (unsigned)((n + tile - 1) / tile), (unsigned)Q);
-    if (arith == B2R_ARITH_EXACT)
+    if (arith == B2R_ARITH_EXACT) {   // the same counts as the un-fused sequence, through the filtered predicate (score_h_filt.cuh)
+        static bool optin[64] = {false};   // > 48 KB of dynamic shared memory: once per device
+        if (c->device < 64 && !optin[c->device]) {
+            CU(cudaFuncSetAttribute(k3_score_h_filt<NPAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_filt_smem(1024, NPAIR)));
+            optin[c->device] = true;
+        }
+        LAUNCH(c, (k3_score_h_filt<NPAIR>), grid, K3_THREADS, k3_filt_smem(tile, NPAIR), models, H, H_stride, pts, n, thr_sq, counts,
+               tile);
+    } else if (arith == B2R_ARITH_EXACT_UNFILTERED)
         LAUNCH(c, (k3_score_h<NPAIR, true>), grid, K3_THREADS, smem, models, H, H_stride, pts, n, thr_sq, counts, tile);
     else
         LAUNCH(c, (k3_score_h<NPAIR, false>), grid, K3_THREADS, smem, models, H, H_stride, pts, n, thr_sq, counts, tile);

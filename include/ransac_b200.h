@@ -47,6 +47,9 @@ extern "C" {
 /* arithmetic of the hypotheses x points scoring kernel */
 #define B2R_ARITH_EXACT 0 /* the reference's un-fused fp32 sequence: inlier sets bit-exact with cv2 */
 #define B2R_ARITH_FAST 1  /* FMA-contracted, division-free form of the same inequality               */
+#define B2R_ARITH_EXACT_UNFILTERED 2 /* the un-fused sequence for EVERY evaluation.  B2R_ARITH_EXACT returns the same counts:
+                                        it takes the sign of the division-free margin where a proved error bound allows and
+                                        runs this sequence elsewhere; this value exists so that tests can hold the two equal */
 /* minimal solver */
 #define B2R_SOLVER_EXACT 0 /* OpenCV's normalised DLT + Jacobi eigen-solver, fp64, bit-identical models */
 #define B2R_SOLVER_FAST 1  /* closed-form 4-point solve in registers (fp64), ~1e-12 relative agreement   */

@@ -1,0 +1,134 @@
+"""The filtered exact predicate of the scoring kernels (csrc/score_h_filt.cuh, csrc/score_p_filt.cuh).
+
+B2R_ARITH_EXACT takes the sign of a division-free FMA margin wherever a proved error bound separates it from OpenCV's own
+comparison and runs OpenCV's un-fused sequence elsewhere.  It must return the SAME integers as that sequence run on every
+evaluation (B2R_ARITH_EXACT_UNFILTERED) and as the CPU oracle (HomographyEstimatorCallback::computeError / findInliers,
+SURVEY.md A.5; reference call site main_v1.py:312) — also when the threshold is put exactly on an evaluation's error, one
+float below it, one above it, when hypotheses are degenerate, huge, tiny, NaN or infinite, when a
+denominator changes sign inside the point range, and when points are not finite.  All comparisons are equalities."""
+import numpy as np
+import pytest
+
+import ransac_b200
+from ransac_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(n, outliers, seed, noise=1.0):
+    rng = np.random.default_rng(seed)
+    s, d, _ = synth.homography_set(n, outliers, rng, noise_px=noise)
+    return np.asarray(s, dtype=np.float32), np.asarray(d, dtype=np.float32)
+
+
+def _models_from_samples(ctx, sq, dq, n_models, seed):
+    rng = np.random.default_rng(seed)
+    idx = np.stack([rng.choice(len(sq), 4, replace=False) for _ in range(n_models)]).astype(np.int32)
+    H, ok, _ = ctx.solve_h4(sq, dq, idx)
+    m = H.reshape(-1, 9)[:, :8].astype(np.float32)
+    m[~ok] = np.nan
+    return m
+
+
+def _errors_f32(models, src, dst):
+    """OpenCV's un-fused fp32 sequence in numpy (every operation rounded to float32), [H, N]."""
+    m = models.astype(np.float32)[:, None, :]
+    X, Y = src[None, :, 0], src[None, :, 1]
+    u, v = dst[None, :, 0], dst[None, :, 1]
+    one = np.float32(1.0)
+    with np.errstate(all="ignore"):
+        ww = one / ((m[..., 6] * X + m[..., 7] * Y) + one)
+        dx = ((m[..., 0] * X + m[..., 1] * Y) + m[..., 2]) * ww - u
+        dy = ((m[..., 3] * X + m[..., 4] * Y) + m[..., 5]) * ww - v
+        return dx * dx + dy * dy
+
+
+def _check(ctx, oracle, models, src, dst, thr_sq):
+    with np.errstate(all="ignore"):
+        ref = oracle.h_count_inliers_f32(models, src, dst, thr_sq)
+    got = ctx.score_h(models, src, dst, thr_sq, ransac_b200.ARITH_EXACT)
+    unf = ctx.score_h(models, src, dst, thr_sq, ransac_b200.ARITH_EXACT_UNFILTERED)
+    np.testing.assert_array_equal(unf, ref)
+    np.testing.assert_array_equal(got, ref)
+    return ref
+
+
+def test_threshold_on_below_and_above_an_evaluation(ctx, oracle):
+    """thr = the fp32 error of one (hypothesis, point), the float below it and the float above it: the count of that
+    hypothesis changes by exactly that point between the three, and every count equals the oracle's."""
+    sq, dq = _problem(3000, 0.5, 301)
+    models = _models_from_samples(ctx, sq, dq, 1200, 302)
+    e = _errors_f32(models, sq, dq)
+    rng = np.random.default_rng(303)
+    finite = np.isfinite(e)
+    near = np.argwhere(finite & (e > 0.5) & (e < 200.0))
+    picks = near[rng.choice(len(near), 24, replace=False)]
+    for (k, p) in picks:
+        t = np.float32(e[k, p])
+        counts = []
+        for thr_sq in (np.nextafter(t, np.float32(0)), t, np.nextafter(t, np.float32(np.inf))):
+            counts.append(_check(ctx, oracle, models, sq, dq, np.float32(thr_sq))[k])
+        assert counts[1] >= counts[0] + 1 and counts[2] >= counts[1]   # the point itself enters at thr = its error
+
+
+def test_equal_on_mixed_hypotheses(ctx, oracle):
+    """Near-truth hypotheses (dense near the threshold), sample hypotheses, and pathological rows: NaN, one NaN
+    coefficient, infinities, 1e20 / 1e-20 scales, all zeros, denominators that vanish inside the point range."""
+    n = 5000 + 37   # full tiles + a ragged tail
+    sq, dq = _problem(n, 0.4, 311)
+    models = _models_from_samples(ctx, sq, dq, 3000, 312)
+    good = np.argwhere(~np.isnan(models).any(axis=1)).ravel()
+    e = _errors_f32(models[good], sq, dq)
+    best = good[np.argsort((e <= 9.0).sum(axis=1))[-40:]]
+    rng = np.random.default_rng(313)
+    near = np.concatenate([models[best] * (1 + 1e-4 * rng.standard_normal((40, 8)).astype(np.float32)) for _ in range(20)])
+    odd = np.tile(models[best[0]], (16, 1)).astype(np.float32)
+    odd[0] = np.nan
+    odd[1, 3] = np.nan
+    odd[2, 0] = np.inf
+    odd[3, 7] = -np.inf
+    odd[4] *= np.float32(1e20)
+    odd[5, :6] *= np.float32(1e-20)
+    odd[6] = 0
+    odd[7, 6:8] = (np.float32(-1.0 / sq[:, 0].mean()), 0)        # w = 0 near the middle of the X range
+    odd[8, 6:8] = (0, np.float32(-1.0 / sq[:, 1].mean()))
+    odd[9, 6:8] = (np.float32(3e38), np.float32(3e38))
+    odd[10, :6] = 0
+    odd[11, 2] = np.float32(2.0 ** 41)
+    odd[12, 6] = np.float32(2.0 ** 41)
+    odd[13, 0] = np.float32(1e-42)                                  # a denormal coefficient
+    allm = np.concatenate([models, near.astype(np.float32), odd])
+    for thr in (0.7, 3.0, 75.0):
+        _check(ctx, oracle, allm, sq, dq, np.float32(thr * thr))
+
+
+@pytest.mark.parametrize("thr_sq", [0.0, 1e-45, 2.0 ** -41, 2.0 ** -39, 2.0 ** 39, 2.0 ** 41, 3e38, np.inf])
+def test_threshold_range(ctx, oracle, thr_sq):
+    """Thresholds inside and outside the guards of the bound (2^-40 .. 2^40): the counts do not depend on the route."""
+    sq, dq = _problem(2100, 0.5, 321)
+    models = _models_from_samples(ctx, sq, dq, 600, 322)
+    _check(ctx, oracle, models, sq, dq, np.float32(thr_sq))
+
+
+def test_non_finite_and_huge_points(ctx, oracle):
+    """A NaN / infinite / 2^41 coordinate in a tile sends that tile through the un-fused sequence; the other tiles
+    stay filtered; counts are the oracle's."""
+    sq, dq = _problem(3100, 0.5, 331)
+    models = _models_from_samples(ctx, sq, dq, 900, 332)
+    for where, value in ((5, np.nan), (1500, np.inf), (3099, -np.inf), (2047, np.float32(2.0 ** 41))):
+        for arr in (0, 1):
+            s2, d2 = sq.copy(), dq.copy()
+            (s2 if arr == 0 else d2)[where, arr] = value
+            _check(ctx, oracle, models, s2, d2, np.float32(9.0))
+
+
+def test_full_size_equals_unfiltered(ctx):
+    """BASELINE configs[2] shape (100k x 100k): every one of the 100 000 counts equal between the two routes."""
+    src, dst = synth.config_homography(2)
+    sq, dq = np.asarray(src, dtype=np.float32), np.asarray(dst, dtype=np.float32)
+    models = _models_from_samples(ctx, sq, dq, 100_000, 342)
+    thr_sq = np.float32(9.0)
+    a = ctx.score_h(models, sq, dq, thr_sq, ransac_b200.ARITH_EXACT)
+    b = ctx.score_h(models, sq, dq, thr_sq, ransac_b200.ARITH_EXACT_UNFILTERED)
+    np.testing.assert_array_equal(a, b)
+    assert a.max() > 40_000
