@@ -3,6 +3,7 @@
 // runs in the kernels of pipeline_p.cuh / score_p.cuh / pnp_solver.cuh.  No CPU fallback.
 #include "host_common.h"
 #include "pipeline_p.cuh"
+#include "score_p_filt.cuh"
 
 using namespace b2r;
 
@@ -40,7 +41,8 @@ static int check_p_params(const b2r_p_params* p) {
     if (!p) return fail(B2R_ERR_ARG, "null params%s%s");
     if (!(p->thr >= 0)) return fail(B2R_ERR_ARG, "reprojectionError must be >= 0%s%s");
     if (p->sampler != B2R_SAMPLER_CV_REPLAY && p->sampler != B2R_SAMPLER_PHILOX) return fail(B2R_ERR_ARG, "bad sampler%s%s");
-    if (p->arith != B2R_ARITH_EXACT && p->arith != B2R_ARITH_FAST) return fail(B2R_ERR_ARG, "bad arith%s%s");
+    if (p->arith != B2R_ARITH_EXACT && p->arith != B2R_ARITH_FAST && p->arith != B2R_ARITH_EXACT_UNFILTERED)
+        return fail(B2R_ERR_ARG, "bad arith%s%s");
     if (p->solver != B2R_SOLVER_EXACT && p->solver != B2R_SOLVER_FAST) return fail(B2R_ERR_ARG, "bad solver%s%s");
     if (p->max_iters > (1 << 30)) return fail(B2R_ERR_ARG, "iterationsCount too large%s%s");
     // the arg-max keys carry the global hypothesis id in 32 bits (count << 32 | ~id): ids beyond 2^32 would alias
@@ -121,11 +123,28 @@ static int zero_counts(b2r_ctx* c, int* counts, int Q, int H, int H_stride, int 
 }
 
 // score hypotheses [begin, begin+H) of every problem; mx/counts are [Q][H_stride] arrays
+// pf / centre != nullptr: the filtered predicate (score_p_filt.cuh: the same counts); nullptr: OpenCV's sequence for every evaluation
 static int score_p_exact(b2r_ctx* c, const double* mx, int H, const PointPX* px, size_t stride, int n, const double* Kq,
-                         float thr_sq, int* counts, int Q, int H_stride = 0, int begin = 0) {
+                         float thr_sq, int* counts, int Q, int H_stride = 0, int begin = 0, const PointPF* pf = nullptr,
+                         const double* centre = nullptr, size_t centre_stride = 0) {
     if (H_stride == 0) H_stride = H;
     int rc = zero_counts(c, counts, Q, H, H_stride, begin);
     if (rc) return rc;
+    if (pf && centre) {
+        constexpr int NP = 2;
+        const long long hb = (H + K3_THREADS * 2 * NP - 1) / (K3_THREADS * 2 * NP);
+        const int tile = pick_tile(c, hb, n, Q, 1024);
+        static bool optin[64] = {false};   // > 48 KB of dynamic shared memory: once per device
+        if (c->device < 64 && !optin[c->device]) {
+            CU(cudaFuncSetAttribute(k3_score_p_filt<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3p_filt_smem(1024, NP)));
+            optin[c->device] = true;
+        }
+        dim3 grid((unsigned)hb, (unsigned)((n + tile - 1) / tile), (unsigned)Q);
+        LAUNCH(c, (k3_score_p_filt<NP>), grid, K3_THREADS, k3p_filt_smem(tile, NP), mx + 12 * (size_t)begin, H, H_stride, px, pf, stride, n, Kq,
+               centre, centre_stride, thr_sq, counts + begin, tile);
+        CU(cudaGetLastError());
+        return B2R_OK;
+    }
     const bool two = (long long)H * Q > 1024LL * c->sm_count;
     const int per_cta = K3P_THREADS * (two ? 2 : 1);
     const long long hb = (H + per_cta - 1) / per_cta;
@@ -163,7 +182,8 @@ static int p_run_score(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p) {
     const int Q = pr->Q, n = pr->n;
     int H = p->max_iters > 1 ? p->max_iters : 1;
     if (n == PNP_MP) H = 1;  // OpenCV solves the only possible subset once
-    const bool exact = p->arith == B2R_ARITH_EXACT;
+    const bool exact = p->arith != B2R_ARITH_FAST;
+    const bool filt = p->arith == B2R_ARITH_EXACT;
     int rc = p_reserve(pr, Q, n, H, exact);
     if (rc) return rc;
     pr->H_last = H;
@@ -181,7 +201,8 @@ static int p_run_score(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p) {
                mf, (double*)nullptr, (uint8_t*)nullptr, (int)p->solver);
         CU(cudaGetLastError());
         CU(cudaEventRecord(pr->ev[1], c->stream));
-        if (exact) rc = score_p_exact(c, mx, H, pr->px.as<PointPX>(), pr->pts_stride(), n, pr->Kq.as<double>(), thr_sq, pr->counts.as<int>(), Q);
+        if (exact) rc = score_p_exact(c, mx, H, pr->px.as<PointPX>(), pr->pts_stride(), n, pr->Kq.as<double>(), thr_sq, pr->counts.as<int>(), Q, 0, 0,
+                                      filt ? pr->pf.as<PointPF>() : nullptr, pr->centre.as<double>(), cstride);
         else rc = score_p_fast(c, mf, H, pr->pf.as<PointPF>(), pr->pts_stride(), n, thr_sq, pr->counts.as<int>(), Q);
         if (rc) return rc;
         CU(cudaEventRecord(pr->ev[2], c->stream));
@@ -207,7 +228,8 @@ static int p_run_score(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p) {
                pr->Kq.as<double>(), pr->centre.as<double>(), cstride, 0, 0LL, (uint64_t)0, pr->samples.as<int>(), mx, mf,
                pr->rt.as<double>(), (uint8_t*)nullptr, (int)p->solver);
         CU(cudaGetLastError());
-        if (exact) rc = score_p_exact(c, mx, len, pr->px.as<PointPX>(), pr->pts_stride(), n, pr->Kq.as<double>(), thr_sq, pr->counts.as<int>(), Q, H, begin);
+        if (exact) rc = score_p_exact(c, mx, len, pr->px.as<PointPX>(), pr->pts_stride(), n, pr->Kq.as<double>(), thr_sq, pr->counts.as<int>(), Q, H, begin,
+                                      filt ? pr->pf.as<PointPF>() : nullptr, pr->centre.as<double>(), cstride);
         else rc = score_p_fast(c, mf, len, pr->pf.as<PointPF>(), pr->pts_stride(), n, thr_sq, pr->counts.as<int>(), Q, H, begin);
         if (rc) return rc;
         LAUNCH(c, k_select_cv_chunk, (unsigned)((Q + 127) / 128), 128, 0, pr->counts.as<int>(), H, begin, len, n, p->confidence, PNP_MP,
@@ -549,9 +571,9 @@ int b2r_score_p(b2r_ctx* c, const double* models_Rt, int32_t n_models, const dou
     CU(c->scratch1.reserve(sizeof(double) * 12 * (size_t)n_models));
     CU(c->scratch2.reserve(sizeof(int) * (size_t)n_models));
     CU(cudaMemcpyAsync(c->scratch1.p, models_Rt, sizeof(double) * 12 * (size_t)n_models, cudaMemcpyHostToDevice, c->stream));
-    if (arith == B2R_ARITH_EXACT) {
+    if (arith != B2R_ARITH_FAST) {
         rc = score_p_exact(c, c->scratch1.as<double>(), n_models, pr->px.as<PointPX>(), 0, n, pr->Kq.as<double>(), thr_sq,
-                           c->scratch2.as<int>(), 1);
+                           c->scratch2.as<int>(), 1, 0, 0, arith == B2R_ARITH_EXACT ? pr->pf.as<PointPF>() : nullptr, pr->centre.as<double>(), 0);
     } else {
         CU(c->scratch3.reserve(sizeof(float) * 12 * (size_t)n_models));
         LAUNCH(c, k_fast_models_from_rt, (unsigned)((n_models + 127) / 128), 128, 0, c->scratch1.as<double>(), n_models,

@@ -85,7 +85,7 @@ __device__ __forceinline__ bool h_inlier_exact(const float4 a0, const float4 a1,
 }
 
 // the un-fused sequence for hypothesis hh on the points flagged in `um` (bit 2i: the point i before `newest`): inlier count
-__device__ __noinline__ int k3_filt_resolve(const float4* __restrict__ models, int H, int hh, const float4* tile, uint32_t um, int newest,
+static __device__ __noinline__ int k3_filt_resolve(const float4* __restrict__ models, int H, int hh, const float4* tile, uint32_t um, int newest,
                                             float thr) {
     if (hh >= H) return 0;
     const float4 a0 = __ldg(models + 2 * hh), a1 = __ldg(models + 2 * hh + 1);

@@ -132,3 +132,144 @@ def test_full_size_equals_unfiltered(ctx):
     b = ctx.score_h(models, sq, dq, thr_sq, ransac_b200.ARITH_EXACT_UNFILTERED)
     np.testing.assert_array_equal(a, b)
     assert a.max() > 40_000
+
+
+# ---- 3x4 models (cv2.solvePnPRansac, main_v1.py:497-502): csrc/score_p_filt.cuh ---------------------------------------------
+
+K = synth.K_1898
+
+
+def _pnp_errors(models, P32, px32, K):
+    """cv::projectPoints (fp64, un-fused) + the fp32 error, as csrc/score_p.cuh::p_inlier_exact runs them, [H, N]."""
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    X, Y, Z = (P32[:, i].astype(np.float64)[None, :] for i in range(3))
+    m = models[:, None, :]
+    with np.errstate(all="ignore"):
+        x = ((m[..., 0] * X + m[..., 1] * Y) + m[..., 2] * Z) + m[..., 9]
+        y = ((m[..., 3] * X + m[..., 4] * Y) + m[..., 5] * Z) + m[..., 10]
+        z = ((m[..., 6] * X + m[..., 7] * Y) + m[..., 8] * Z) + m[..., 11]
+        z = np.where(z != 0, 1.0 / z, 1.0)
+        pu = ((x * z) * fx + cx).astype(np.float32)
+        pv = ((y * z) * fy + cy).astype(np.float32)
+        dx, dy = px32[None, :, 0] - pu, px32[None, :, 1] - pv
+        return dx * dx + dy * dy
+
+
+def _pnp_check(ctx, models, P, px, thr_sq, ref=None):
+    got = ctx.score_p(models, P, px, K, thr_sq, ransac_b200.ARITH_EXACT)
+    unf = ctx.score_p(models, P, px, K, thr_sq, ransac_b200.ARITH_EXACT_UNFILTERED)
+    np.testing.assert_array_equal(got, unf)
+    if ref is not None:
+        np.testing.assert_array_equal(unf, ref)
+    return unf
+
+
+def _poses(oracle, rng, n_near, n_wild):
+    """Poses around the true one (the rotation is perturbed about the CAMERA, t = -R cam: errors of a few pixels, dense
+    near the threshold) and wild ones (cameras inside and around the cloud: the depth changes sign among the points)."""
+    R0, _ = synth.look_at_pose()
+    rv0 = oracle.rodrigues_inv(R0)
+    out = []
+    for k in range(n_near):
+        R = oracle.rodrigues(rv0 + rng.normal(0, 2e-4 if k % 2 else 2e-3, 3))
+        cam = synth.CAMERA_ORIGIN + rng.normal(0, 0.3 if k % 2 else 3.0, 3)
+        out.append(np.concatenate([R.ravel(), -R @ cam]))
+    centre = 0.5 * (synth.BOX_LO + synth.BOX_HI)
+    for k in range(n_wild):
+        R = oracle.rodrigues(rng.normal(0, 2.0, 3))
+        cam = centre + rng.normal(0, 150.0 if k % 2 else 600.0, 3)
+        out.append(np.concatenate([R.ravel(), -R @ cam]))
+    return np.array(out)
+
+
+def test_pnp_equal_on_mixed_hypotheses(ctx, oracle):
+    rng = np.random.default_rng(401)
+    n = 5000 + 37
+    P, px, _ = synth.pnp_set(n, 0.4, rng)
+    models = _poses(oracle, rng, 900, 1200)
+    odd = np.tile(models[0], (10, 1))
+    odd[0] = np.nan
+    odd[1, 4] = np.nan
+    odd[2, 9] = np.inf
+    odd[3, 11] = 1e20
+    odd[4, :9] *= 1e20
+    odd[5, 9:] = 0
+    odd[6, :9] = 0
+    odd[7, 6:9] = 0; odd[7, 11] = 0          # z == 0 for every point: OpenCV takes z = 1
+    odd[8, 6:9] = 0; odd[8, 11] = 1e-300     # 1/z overflows
+    odd[9, 11] = -odd[9, 11]
+    allm = np.concatenate([models, odd])
+    P32, px32 = P.astype(np.float32), px.astype(np.float32)
+    e = _pnp_errors(allm, P32, px32, K)
+    for thr in (1.0, 8.0, 30.0):
+        thr_sq = np.float32(thr * thr)
+        with np.errstate(all="ignore"):
+            ref = (e <= thr_sq).sum(axis=1)
+        _pnp_check(ctx, allm, P, px, thr_sq, ref)
+    k = 17   # spot check of the numpy restatement against the C oracle
+    assert oracle.pnp_count_inliers(allm[k, :9], allm[k, 9:], K, P32, px32, 8.0)[0] == (e[k] <= np.float32(64.0)).sum()
+
+
+def test_pnp_threshold_on_below_and_above_an_evaluation(ctx, oracle):
+    rng = np.random.default_rng(411)
+    P, px, _ = synth.pnp_set(3000, 0.4, rng)
+    models = _poses(oracle, rng, 500, 300)
+    P32, px32 = P.astype(np.float32), px.astype(np.float32)
+    e = _pnp_errors(models, P32, px32, K)
+    near = np.argwhere(np.isfinite(e) & (e > 0.5) & (e < 2000.0))
+    picks = near[rng.choice(len(near), 16, replace=False)]
+    for (k, p) in picks:
+        t = np.float32(e[k, p])
+        counts = []
+        for thr_sq in (np.nextafter(t, np.float32(0)), t, np.nextafter(t, np.float32(np.inf))):
+            with np.errstate(all="ignore"):
+                ref = (e <= np.float32(thr_sq)).sum(axis=1)
+            counts.append(_pnp_check(ctx, models, P, px, np.float32(thr_sq), ref)[k])
+        assert counts[1] >= counts[0] + 1 and counts[2] >= counts[1]
+
+
+def test_pnp_depth_exactly_zero(ctx, oracle):
+    """Planar object points (Z = 0) under R = I, t = (tx, ty, 0): the fp64 depth is exactly 0 for every point and
+    OpenCV's `z != 0 ? 1/z : 1` takes z = 1, so pixels u = fx (X + tx) + cx ARE inliers.  The margin's form assumes the
+    first branch: the depth guard must send these evaluations to OpenCV's sequence."""
+    rng = np.random.default_rng(421)
+    n = 1500
+    P = np.zeros((n, 3))
+    P[:, :2] = rng.uniform(-0.3, 0.3, (n, 2))
+    tx, ty = 0.05, -0.02
+    px = np.stack([K[0, 0] * (P[:, 0].astype(np.float32) + tx) + K[0, 2], K[1, 1] * (P[:, 1].astype(np.float32) + ty) + K[1, 2]], axis=1)
+    px[::3] += rng.normal(0, 40.0, (len(px[::3]), 2))
+    models = np.zeros((6, 12))
+    for k in range(6):
+        models[k, :9] = np.eye(3).ravel()
+        models[k, 9:] = (tx + 1e-4 * k, ty, 0.0)
+    models[4, 11] = 1e-7      # a tiny non-zero depth
+    models[5, 11] = 1.0
+    P32, px32 = P.astype(np.float32), px.astype(np.float32)
+    e = _pnp_errors(models, P32, px32, K)
+    for thr_sq in (np.float32(4.0), np.float32(64.0)):
+        ref = (e <= thr_sq).sum(axis=1)
+        assert ref[0] > n // 2
+        _pnp_check(ctx, models, P, px, thr_sq, ref)
+
+
+@pytest.mark.parametrize("thr_sq", [0.0, 2.0 ** -41, 2.0 ** 41, np.inf])
+def test_pnp_threshold_range(ctx, oracle, thr_sq):
+    rng = np.random.default_rng(431)
+    P, px, _ = synth.pnp_set(2100, 0.4, rng)
+    models = _poses(oracle, rng, 200, 200)
+    _pnp_check(ctx, models, P, px, np.float32(thr_sq))
+
+
+def test_pnp_full_size_equals_unfiltered(ctx, oracle):
+    """100k points x 100k poses: every count equal between the two routes."""
+    rng = np.random.default_rng(441)
+    P, px, _ = synth.pnp_set(100_000, 0.5, rng)
+    models = _poses(oracle, rng, 2000, 3000)
+    models = np.tile(models, (20, 1))
+    models[:, 9:] += rng.normal(0, 0.05, (len(models), 3))
+    models[7::1000] = np.nan
+    a = ctx.score_p(models, P, px, K, np.float32(64.0), ransac_b200.ARITH_EXACT)
+    b = ctx.score_p(models, P, px, K, np.float32(64.0), ransac_b200.ARITH_EXACT_UNFILTERED)
+    np.testing.assert_array_equal(a, b)
+    assert a.max() > 40_000
