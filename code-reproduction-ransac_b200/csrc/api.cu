@@ -386,7 +386,9 @@ static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samp
     }
     // a big batch of mid-size problems is bound by the sequential part of each problem (one thread's small linear algebra):
     // 64-thread CTAs keep eight problems per SM in flight instead of four
-    const int threads = n >= 2048 ? 1024 : ((Q >= 4 * c->sm_count && n >= 256) ? 64 : 128);
+    // measured (tools/perf_cfg1.py): one 128-thread CTA finalizes 2000 points in 0.20 ms, a 1024-thread CTA in 0.25 ms — the LM's
+    // sequential linear algebra and the depth of the reductions, not the passes over the points, bound a mid-size problem
+    const int threads = n >= 4096 ? 1024 : ((Q >= 4 * c->sm_count && n >= 256) ? 64 : 128);
     const int csize = n >= 32768 ? 8 : (n >= 8192 ? 2 : 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(Q * csize));
