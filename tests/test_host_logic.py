@@ -83,6 +83,41 @@ def test_scoring_kernels_are_the_instruction_mix_design_md_describes():
     ffma2 = [l for l in eloop if re.search(r"\bFFMA2\b", l)]
     assert len(ffma2) == 12 * 2 * n_pts                                   # 10 products (+ RZ) and the 2 FMAs of the Newton step
     assert sum(1 for l in ffma2 if re.search(r", RZ(\.F32)? ;", l) or ", RZ ;" in l) >= 10 * 2 * n_pts
+    # the filtered exact kernels (score_h_filt.cuh, score_p_filt.cuh): the fast kernels' packed arithmetic, ONE funnel shift per
+    # evaluation that files sign and band bit (no per-evaluation compare, min or count), no reciprocal, no fp64 and no local
+    # memory in the loop; the 3x4 kernel adds the depth guard (one FMUL2 per pair, one FMNMX per evaluation)
+    hfilt = next(v for k, v in funcs.items() if "k3_score_h_filtILi2" in k)
+    pfilt = next(v for k, v in funcs.items() if "k3_score_p_filtILi2" in k)
+
+    def unrolled_loop(lines, per_point):   # the longest run of instructions between two branches that holds packed arithmetic
+        best, cur = [], []
+        for l in lines:
+            if re.search(r"\b(BRA|EXIT|RET|CALL)\b", l):
+                if count(cur, "FFMA2") > count(best, "FFMA2"):
+                    best = cur
+                cur = []
+            else:
+                cur.append(l)
+        assert count(best, "FFMA2") >= per_point
+        return best
+
+    floop = unrolled_loop(hfilt, 20)
+    n_pts = count(floop, r"LDS\.128")
+    assert n_pts >= 4
+    assert count(floop, "FFMA2") + count(floop, "FMUL2") == 11 * 2 * n_pts
+    assert count(floop, r"SHF\.L\.W\.U32\.HI") == 4 * n_pts             # one per evaluation: (sg << 2) | (margin >> 30)
+    for op in (r"MUFU\.\w+", "FSETP", "FMNMX3?", r"LEA\.HI", "POPC", "DFMA", "DADD", "DMUL", "STL", "LDL", r"ATOMS?\.\w+", "BAR"):
+        assert count(floop, op) == 0, op
+    ploop2 = unrolled_loop(pfilt, 26)
+    n_pts = count(ploop2, r"LDS\.128")
+    assert n_pts >= 2
+    assert count(ploop2, "FFMA2") + count(ploop2, "FMUL2") == 15 * 2 * n_pts   # 14 of the margin + the depth guard's product
+    assert count(ploop2, r"SHF\.L\.W\.U32\.HI") == 4 * n_pts and count(ploop2, "FMNMX") == 4 * n_pts
+    for op in (r"MUFU\.\w+", "FSETP", r"LEA\.HI", "DFMA", "DADD", "DMUL", "STL", "LDL", r"ATOMS?\.\w+", "BAR"):
+        assert count(ploop2, op) == 0, op
+    for body in (hfilt, pfilt):
+        assert any("UBLKCP" in l for l in body)
+        assert not any(re.search(r"\b(HMMA|IMMA|DMMA|UTCHMMA|UTCMMA)\b", l) for l in body)
 
 
 def test_no_cpu_fallback():
