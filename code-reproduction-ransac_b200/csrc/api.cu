@@ -170,6 +170,8 @@ static int launch_k3(b2r_ctx* c, const float4* models, int H, int H_stride, cons
     if (tile > n) tile = ((n + 7) / 8) * 8;
     const size_t smem = 128 + (size_t)tile * 16;
     dim3 grid((unsigned)hyp_blocks, (unsigned)((n + tile - 1) / tile), (unsigned)Q);
+    // a handful of points (the reference's 12) cannot repay the per-hypothesis set-up of the filter: the un-fused kernel then
+    if (arith == B2R_ARITH_EXACT && n < 64) arith = B2R_ARITH_EXACT_UNFILTERED;
     if (arith == B2R_ARITH_EXACT) {   // the same counts as the un-fused sequence, through the filtered predicate (score_h_filt.cuh)
         static bool optin[64] = {false};   // > 48 KB of dynamic shared memory: once per device
         if (c->device < 64 && !optin[c->device]) {

@@ -130,7 +130,7 @@ static int score_p_exact(b2r_ctx* c, const double* mx, int H, const PointPX* px,
     if (H_stride == 0) H_stride = H;
     int rc = zero_counts(c, counts, Q, H, H_stride, begin);
     if (rc) return rc;
-    if (pf && centre) {
+    if (pf && centre && n >= 64) {   // fewer points cannot repay the per-hypothesis set-up of the filter
         constexpr int NP = 2;
         const long long hb = (H + K3_THREADS * 2 * NP - 1) / (K3_THREADS * 2 * NP);
         const int tile = pick_tile(c, hb, n, Q, 1024);
