@@ -247,15 +247,15 @@ static int run_score(b2r_ctx* c, b2r_h_problem* pr, const b2r_h_params* p) {
         dim3 grid((unsigned)((H + 127) / 128), (unsigned)Q);
         if (p->solver == B2R_SOLVER_EXACT) {
             // sample only, then the shared-memory Jacobi kernel (7x the throughput of solving in the sampling thread)
-            LAUNCH(c, k_philox_sample_solve_h, grid, 128, 0, pr->pts.as<PointH>(), n, H, (long long)p->hyp_begin, p->seed,
-                   pr->samples.as<int>(), (float4*)nullptr, 0, 0);
+            LAUNCH(c, k_philox_sample_solve_h<false>, grid, 128, 0, pr->pts.as<PointH>(), n, H, (long long)p->hyp_begin, p->seed,
+                   pr->samples.as<int>(), (float4*)nullptr);
             if ((rc = k2s_prepare(c))) return rc;
             dim3 g2((unsigned)((H + K2S_THREADS - 1) / K2S_THREADS), (unsigned)Q);
             LAUNCH(c, k_solve_h4_smem, g2, K2S_THREADS, K2S_SMEM, pr->pts.as<PointH>(), n, pr->samples.as<int>(), H, 0, H,
                    (const RansacState*)nullptr, pr->models.as<float4>(), (double*)nullptr, (uint8_t*)nullptr, (uint8_t*)nullptr);
         } else {
-            LAUNCH(c, k_philox_sample_solve_h, grid, 128, 0, pr->pts.as<PointH>(), n, H, (long long)p->hyp_begin, p->seed,
-                   pr->samples.as<int>(), pr->models.as<float4>(), 1, p->solver);
+            LAUNCH(c, k_philox_sample_solve_h<true>, grid, 128, 0, pr->pts.as<PointH>(), n, H, (long long)p->hyp_begin, p->seed,
+                   pr->samples.as<int>(), pr->models.as<float4>());
         }
         CU(cudaGetLastError());
         CU(cudaEventRecord(pr->ev[1], c->stream));
@@ -390,8 +390,13 @@ static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samp
     // 64-thread CTAs keep eight problems per SM in flight instead of four
     // measured (tools/perf_cfg1.py): one 128-thread CTA finalizes 2000 points in 0.20 ms, a 1024-thread CTA in 0.25 ms — the LM's
     // sequential linear algebra and the depth of the reductions, not the passes over the points, bound a mid-size problem
-    const int threads = n >= 4096 ? 1024 : ((Q >= 4 * c->sm_count && n >= 256) ? 64 : 128);
-    const int csize = n >= 32768 ? 8 : (n >= 8192 ? 2 : 1);
+    // ... and 512-thread CTAs (127 registers: the 1024-thread instantiation is capped at 64 and spilled 1.8 KB per thread) take
+    // over at 512 points with the closed-form solver, at 4096 with the exact one (tools/perf_cfg1.py: 5000 points 0.28 -> 0.17 ms,
+    // 20 000 points 0.34 -> 0.19 ms, 2000 points 0.21 -> 0.17 ms)
+    const bool many = Q >= 4 * c->sm_count && n >= 256 && n < 4096;
+    const int big_n = solver == B2R_SOLVER_EXACT ? 4096 : 512;
+    const int threads = many ? 64 : (n >= big_n ? 512 : 128);
+    const int csize = n >= 32768 ? 8 : (n >= 8192 ? 4 : (n >= 4096 ? 2 : 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(Q * csize));
     cfg.blockDim = dim3((unsigned)threads);
@@ -405,8 +410,8 @@ static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samp
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     double* no_scratch = nullptr;
-    if (threads == 1024)
-        CU(cudaLaunchKernelEx(&cfg, k_finalize_h<1024, false>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
+    if (threads == 512)
+        CU(cudaLaunchKernelEx(&cfg, k_finalize_h<512, false>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
                               mask_out, rmask_out, info, ext_mask, ext_H, no_scratch, models, seq));
     else if (threads == 64)
         CU(cudaLaunchKernelEx(&cfg, k_finalize_h<64, false>, pts, n, samples, Hs, sel, thr_sq, mask_semantics, refine, solver, H_out,
@@ -756,8 +761,8 @@ int b2r_sample_philox(b2r_ctx* c, const float* src, const float* dst, int32_t n,
     int rc = upload_f32_points(c, src, dst, n, c->scratch0);
     if (rc) return rc;
     CU(c->scratch1.reserve(sizeof(int) * 4 * (size_t)n_hyp));
-    LAUNCH(c, k_philox_sample_solve_h, dim3((unsigned)((n_hyp + 127) / 128), 1), 128, 0, c->scratch0.as<PointH>(), n, n_hyp,
-           (long long)hyp_begin, seed, c->scratch1.as<int>(), (float4*)nullptr, 0, 0);
+    LAUNCH(c, k_philox_sample_solve_h<false>, dim3((unsigned)((n_hyp + 127) / 128), 1), 128, 0, c->scratch0.as<PointH>(), n, n_hyp,
+           (long long)hyp_begin, seed, c->scratch1.as<int>(), (float4*)nullptr);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(idx_out, c->scratch1.p, sizeof(int) * 4 * (size_t)n_hyp, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

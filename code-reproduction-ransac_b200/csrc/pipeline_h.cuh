@@ -62,9 +62,13 @@ __device__ __forceinline__ void store_model(float4* __restrict__ models, size_t 
 
 // ---- K1 (Philox) + K2 fused: one thread per (problem, hypothesis) ----------------------------------------
 // samples : [Q][H][4] int32 (all -1: no acceptable subset in PHILOX_MAX_ATTEMPTS attempts)
+// SOLVE: false = sample only (the exact solver runs in k_solve_h4_smem), true = the closed-form solver in the same thread.
+// A template, not a flag: with the exact solver compiled in as well the kernel carried its 1.4 KB stack frame and 166
+// registers (12 resident warps per SM) through every launch.
+template <bool SOLVE>
 __global__ void __launch_bounds__(128)
 k_philox_sample_solve_h(const PointH* __restrict__ pts, int n, int H, long long hyp_begin, uint64_t seed,
-                        int* __restrict__ samples, float4* __restrict__ models, int solve, int fast_solver) {
+                        int* __restrict__ samples, float4* __restrict__ models) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int q = blockIdx.y;
     if (g >= H) return;
@@ -83,9 +87,9 @@ k_philox_sample_solve_h(const PointH* __restrict__ pts, int n, int H, long long 
     const size_t slot = (size_t)q * H + g;
     if (!found) idx[0] = idx[1] = idx[2] = idx[3] = -1;
     reinterpret_cast<int4*>(samples)[slot] = make_int4(idx[0], idx[1], idx[2], idx[3]);
-    if (solve) {
+    if (SOLVE) {
         double Hm[9];
-        const bool ok = found && (fast_solver ? h_solve4_fast(ms1, ms2, Hm) : h_solve4(ms1, ms2, Hm)) > 0;
+        const bool ok = found && h_solve4_fast(ms1, ms2, Hm) > 0;
         store_model(models, slot, Hm, ok);
     }
 }
