@@ -11,6 +11,7 @@ struct b2r_p_problem {
     int Q = 0, n = 0, P = 0;  // Q problems (intrinsics), n points, P point sets (1 = shared by all problems, else Q)
     DevBuf raw_obj, raw_img;  // [P][n][3], [P][n][2] fp64 as the caller passed them
     DevBuf px, pf, centre;    // [P][n] PointPX, PointPF; [P][3] fp64
+    DevBuf win;               // [Q][6] fp64: the winner's minimal model (k_winner_model_p)
     DevBuf Kq;                // [Q][4] fx, fy, cx, cy
     DevBuf samples;           // [Q][H][5] int32
     DevBuf mx, mf;            // [Q][H][12] fp64 / fp32 models
@@ -22,7 +23,7 @@ struct b2r_p_problem {
     float stage_ms[5] = {0, 0, 0, 0, 0};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     void release() {
-        raw_obj.release(); raw_img.release(); px.release(); pf.release(); centre.release(); Kq.release();
+        raw_obj.release(); raw_img.release(); px.release(); pf.release(); centre.release(); Kq.release(); win.release();
         samples.release(); mx.release(); mf.release(); rt.release(); counts.release(); state.release(); keys.release(); sel.release();
         rmask.release(); pose.release(); info_i.release(); info_d.release(); inliers.release(); ninl.release();
         for (auto& e : ev)
@@ -196,9 +197,14 @@ static int p_run_score(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p) {
     pr->rt_valid = false;
     if (philox) {
         dim3 grid((unsigned)((H + 63) / 64), (unsigned)Q);
-        LAUNCH(c, k_epnp_solve_p, grid, 64, 0, pr->px.as<PointPX>(), pr->pts_stride(), n, H, 0, H, (const RansacState*)nullptr,
-               pr->Kq.as<double>(), pr->centre.as<double>(), cstride, 1, (long long)p->hyp_begin, p->seed, pr->samples.as<int>(), mx,
-               mf, (double*)nullptr, (uint8_t*)nullptr, (int)p->solver);
+        if (p->solver)
+            LAUNCH(c, k_epnp_solve_p<true>, grid, 64, 0, pr->px.as<PointPX>(), pr->pts_stride(), n, H, 0, H, (const RansacState*)nullptr,
+                   pr->Kq.as<double>(), pr->centre.as<double>(), cstride, 1, (long long)p->hyp_begin, p->seed, pr->samples.as<int>(), mx,
+                   mf, (double*)nullptr, (uint8_t*)nullptr);
+        else
+            LAUNCH(c, k_epnp_solve_p<false>, grid, 64, 0, pr->px.as<PointPX>(), pr->pts_stride(), n, H, 0, H, (const RansacState*)nullptr,
+                   pr->Kq.as<double>(), pr->centre.as<double>(), cstride, 1, (long long)p->hyp_begin, p->seed, pr->samples.as<int>(), mx,
+                   mf, (double*)nullptr, (uint8_t*)nullptr);
         CU(cudaGetLastError());
         CU(cudaEventRecord(pr->ev[1], c->stream));
         if (exact) rc = score_p_exact(c, mx, H, pr->px.as<PointPX>(), pr->pts_stride(), n, pr->Kq.as<double>(), thr_sq, pr->counts.as<int>(), Q, 0, 0,
@@ -224,9 +230,14 @@ static int p_run_score(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p) {
         CU(cudaMemsetAsync(not_done, 0, sizeof(int), c->stream));
         LAUNCH(c, k_cv_sample_p, (unsigned)Q, 32, 0, n, H, begin, len, pr->samples.as<int>(), st, Q);
         dim3 grid((unsigned)((len + 63) / 64), (unsigned)Q);
-        LAUNCH(c, k_epnp_solve_p, grid, 64, 0, pr->px.as<PointPX>(), pr->pts_stride(), n, H, begin, len, (const RansacState*)st,
-               pr->Kq.as<double>(), pr->centre.as<double>(), cstride, 0, 0LL, (uint64_t)0, pr->samples.as<int>(), mx, mf,
-               pr->rt.as<double>(), (uint8_t*)nullptr, (int)p->solver);
+        if (p->solver)
+            LAUNCH(c, k_epnp_solve_p<true>, grid, 64, 0, pr->px.as<PointPX>(), pr->pts_stride(), n, H, begin, len, (const RansacState*)st,
+                   pr->Kq.as<double>(), pr->centre.as<double>(), cstride, 0, 0LL, (uint64_t)0, pr->samples.as<int>(), mx, mf,
+                   pr->rt.as<double>(), (uint8_t*)nullptr);
+        else
+            LAUNCH(c, k_epnp_solve_p<false>, grid, 64, 0, pr->px.as<PointPX>(), pr->pts_stride(), n, H, begin, len, (const RansacState*)st,
+                   pr->Kq.as<double>(), pr->centre.as<double>(), cstride, 0, 0LL, (uint64_t)0, pr->samples.as<int>(), mx, mf,
+                   pr->rt.as<double>(), (uint8_t*)nullptr);
         CU(cudaGetLastError());
         if (exact) rc = score_p_exact(c, mx, len, pr->px.as<PointPX>(), pr->pts_stride(), n, pr->Kq.as<double>(), thr_sq, pr->counts.as<int>(), Q, H, begin,
                                       filt ? pr->pf.as<PointPF>() : nullptr, pr->centre.as<double>(), cstride);
@@ -296,19 +307,30 @@ static int p_run_finish(b2r_ctx* c, b2r_p_problem* pr, const b2r_p_params* p, co
     CU(cudaEventRecord(pr->ev[3], c->stream));
     const int csize = n >= 32768 ? 8 : (n >= 8192 ? 2 : 1);
     int rc;
+    CU(pr->win.reserve(sizeof(double) * 6 * (size_t)Q));
+    const double* rt_kept = pr->rt_valid && !keys_host && !keys_dev ? pr->rt.as<double>() : nullptr;
+    if (p->solver)
+        LAUNCH(c, k_winner_model_p<true>, (unsigned)((Q + 31) / 32), 32, 0, (const PointPX*)pr->px.as<PointPX>(), pr->pts_stride(),
+               (const int*)pr->samples.as<int>(), Hs, (const HSelect*)pr->sel.as<HSelect>(), (const double*)pr->Kq.as<double>(), rt_kept,
+               pr->win.as<double>(), Q);
+    else
+        LAUNCH(c, k_winner_model_p<false>, (unsigned)((Q + 31) / 32), 32, 0, (const PointPX*)pr->px.as<PointPX>(), pr->pts_stride(),
+               (const int*)pr->samples.as<int>(), Hs, (const HSelect*)pr->sel.as<HSelect>(), (const double*)pr->Kq.as<double>(), rt_kept,
+               pr->win.as<double>(), Q);
+    CU(cudaGetLastError());
     if (n >= 1024)
         rc = launch_cluster(c, k_finalize_p<512>, Q, csize, 512, (const PointPX*)pr->px.as<PointPX>(), pr->pts_stride(),
                             (const double*)pr->raw_obj.as<double>(), (const double*)pr->raw_img.as<double>(), pr->pts_stride(), n,
                             (const int*)pr->samples.as<int>(), Hs, (const HSelect*)pr->sel.as<HSelect>(),
-                            (const double*)pr->Kq.as<double>(), thr_sq, (int)p->refine, (int)(n == PNP_MP), (int)p->solver,
-                            (const double*)(pr->rt_valid && !keys_host && !keys_dev ? pr->rt.as<double>() : nullptr), pr->rmask.as<uint8_t>(),
+                            (const double*)pr->Kq.as<double>(), thr_sq, (int)p->refine, (int)(n == PNP_MP),
+                            (const double*)pr->win.as<double>(), pr->rmask.as<uint8_t>(),
                             pr->pose.as<double>(), pr->info_i.as<int>(), pr->info_d.as<double>());
     else
         rc = launch_cluster(c, k_finalize_p<128>, Q, csize, 128, (const PointPX*)pr->px.as<PointPX>(), pr->pts_stride(),
                             (const double*)pr->raw_obj.as<double>(), (const double*)pr->raw_img.as<double>(), pr->pts_stride(), n,
                             (const int*)pr->samples.as<int>(), Hs, (const HSelect*)pr->sel.as<HSelect>(),
-                            (const double*)pr->Kq.as<double>(), thr_sq, (int)p->refine, (int)(n == PNP_MP), (int)p->solver,
-                            (const double*)(pr->rt_valid && !keys_host && !keys_dev ? pr->rt.as<double>() : nullptr), pr->rmask.as<uint8_t>(),
+                            (const double*)pr->Kq.as<double>(), thr_sq, (int)p->refine, (int)(n == PNP_MP),
+                            (const double*)pr->win.as<double>(), pr->rmask.as<uint8_t>(),
                             pr->pose.as<double>(), pr->info_i.as<int>(), pr->info_d.as<double>());
     if (rc) return rc;
     if (n > PNP_MP && (keys_host || keys_dev))
@@ -602,9 +624,14 @@ int b2r_pnp_minimal_models(b2r_ctx* c, const double* obj, const double* img, int
     CU(cudaMemcpyAsync(c->scratch1.p, idx, sizeof(int) * PNP_MP * (size_t)n_samples, cudaMemcpyHostToDevice, c->stream));
     double* mx = c->scratch2.as<double>();
     double* rt = mx + 12 * (size_t)n_samples;
-    LAUNCH(c, k_epnp_solve_p, dim3((unsigned)((n_samples + 63) / 64), 1), 64, 0, pr->px.as<PointPX>(), (size_t)0, n, n_samples, 0,
-           n_samples, (const RansacState*)nullptr, pr->Kq.as<double>(), pr->centre.as<double>(), (size_t)0, 0, 0LL, (uint64_t)0,
-           c->scratch1.as<int>(), mx, (float4*)nullptr, rt, c->scratch3.as<uint8_t>(), (int)(solver == B2R_SOLVER_FAST));
+    if (solver == B2R_SOLVER_FAST)
+        LAUNCH(c, k_epnp_solve_p<true>, dim3((unsigned)((n_samples + 63) / 64), 1), 64, 0, pr->px.as<PointPX>(), (size_t)0, n, n_samples, 0,
+               n_samples, (const RansacState*)nullptr, pr->Kq.as<double>(), pr->centre.as<double>(), (size_t)0, 0, 0LL, (uint64_t)0,
+               c->scratch1.as<int>(), mx, (float4*)nullptr, rt, c->scratch3.as<uint8_t>());
+    else
+        LAUNCH(c, k_epnp_solve_p<false>, dim3((unsigned)((n_samples + 63) / 64), 1), 64, 0, pr->px.as<PointPX>(), (size_t)0, n, n_samples, 0,
+               n_samples, (const RansacState*)nullptr, pr->Kq.as<double>(), pr->centre.as<double>(), (size_t)0, 0, 0LL, (uint64_t)0,
+               c->scratch1.as<int>(), mx, (float4*)nullptr, rt, c->scratch3.as<uint8_t>());
     CU(cudaGetLastError());
     std::vector<double> h(18 * (size_t)n_samples);
     CU(cudaMemcpyAsync(h.data(), mx, sizeof(double) * 18 * (size_t)n_samples, cudaMemcpyDeviceToHost, c->stream));

@@ -195,12 +195,15 @@ __device__ __forceinline__ void store_fast_model(float4* __restrict__ mf, size_t
 #ifndef K2P_MIN_BLOCKS
 #define K2P_MIN_BLOCKS 4
 #endif
+// FAST: the closed 5-point solver instead of EPnP — a template, not a flag: with EPnP compiled in as well every launch carried its
+// 3.4 KB stack frame and 255 registers
+template <bool FAST>
 __global__ void __launch_bounds__(64, K2P_MIN_BLOCKS)
 k_epnp_solve_p(const PointPX* __restrict__ pts, size_t pts_q_stride, int n, int H, int begin, int len,
                const RansacState* __restrict__ state, const double* __restrict__ Kq,
                const double* __restrict__ centre, size_t centre_q_stride, int sampler_philox, long long hyp_begin,
                uint64_t seed, int* __restrict__ samples, double* __restrict__ mx, float4* __restrict__ mf,
-               double* __restrict__ rt, uint8_t* __restrict__ ok_out, int fast_solver) {
+               double* __restrict__ rt, uint8_t* __restrict__ ok_out) {
     const int q = blockIdx.y;
     if ((int)(blockIdx.x * blockDim.x + threadIdx.x) >= len) return;
     const int g = begin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,8 +224,8 @@ k_epnp_solve_p(const PointPX* __restrict__ pts, size_t pts_q_stride, int n, int 
     bool ok = state == nullptr || g < state[q].gen;
     if (ok) {
         gather5(P, idx, obj5, img5);
-        ok = fast_solver ? pnp_minimal_model_fast(obj5, img5, K4[0], K4[1], K4[2], K4[3], rvec, tvec)
-                         : pnp_minimal_model(obj5, img5, K4[0], K4[1], K4[2], K4[3], rvec, tvec);
+        ok = FAST ? pnp_minimal_model_fast(obj5, img5, K4[0], K4[1], K4[2], K4[3], rvec, tvec)
+                  : pnp_minimal_model(obj5, img5, K4[0], K4[1], K4[2], K4[3], rvec, tvec);
     }
     if (ok) rodrigues_vec2mat(rvec, R);
     if (mx) {
@@ -556,12 +559,43 @@ __device__ void pnp_refine_lm(ClusterRed& R, PnpLsqShared& sh, JacobiWarp9& jw, 
 //   pose_out    : [Q][6] returned pose (seeded LM on the quantised inliers when refine != 0)
 //   info_i      : [Q][12] int32, info_d : [Q][8] fp64 = RANSAC model rvec|tvec, mean inlier reprojection error of the
 //                 returned pose on the caller's un-quantised points (testpro-K.py:32-36, 80-82), final |r|^2
+// The winner's minimal model (rvec | tvec) of every problem, [Q][6]: copied from the solve kernel's output when the replay path
+// kept it (rt != nullptr), re-derived from the winning sample otherwise (Philox runs do not store 6 doubles per hypothesis, and
+// under hypothesis sharding the winner may come from another rank).  All zeros = no model.  A kernel of its own so that the
+// minimal solvers' stack frames (EPnP: 3.4 KB) stay out of k_finalize_p, which used to spill 2.8 KB per thread around them.
+template <bool FAST>
+__global__ void __launch_bounds__(32)
+k_winner_model_p(const PointPX* __restrict__ pts, size_t pts_q_stride, const int* __restrict__ samples, int Hs,
+                 const HSelect* __restrict__ sel, const double* __restrict__ Kq, const double* __restrict__ rt, double* __restrict__ win, int Q) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const HSelect s = sel[q];
+    double model[6] = {0, 0, 0, 0, 0, 0};
+    if (s.best >= 0) {
+        if (rt) {
+            const double* m = rt + ((size_t)q * Hs + s.best) * 6;
+            for (int i = 0; i < 6; ++i) model[i] = m[i];
+        } else {
+            int smp[PNP_MP];
+            double obj5[15], img5[10];
+            for (int i = 0; i < PNP_MP; ++i) smp[i] = samples[((size_t)q * Hs + s.best) * PNP_MP + i];
+            gather5(pts + (size_t)q * pts_q_stride, smp, obj5, img5);
+            const double* K4 = Kq + (size_t)q * 4;
+            const bool ok = FAST ? pnp_minimal_model_fast(obj5, img5, K4[0], K4[1], K4[2], K4[3], model, model + 3)
+                                 : pnp_minimal_model(obj5, img5, K4[0], K4[1], K4[2], K4[3], model, model + 3);
+            if (!ok)
+                for (int i = 0; i < 6; ++i) model[i] = 0;
+        }
+    }
+    for (int i = 0; i < 6; ++i) win[(size_t)q * 6 + i] = model[i];
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 1)
 k_finalize_p(const PointPX* __restrict__ pts, size_t pts_q_stride, const double* __restrict__ obj_raw,
              const double* __restrict__ img_raw, size_t raw_q_stride, int n, const int* __restrict__ samples, int Hs,
              const HSelect* __restrict__ sel, const double* __restrict__ Kq, float thr_sq, int refine, int all_inliers,
-             int fast_solver, const double* __restrict__ rt, uint8_t* __restrict__ rmask_out, double* __restrict__ pose_out, int* __restrict__ info_i,
+             const double* __restrict__ win, uint8_t* __restrict__ rmask_out, double* __restrict__ pose_out, int* __restrict__ info_i,
              double* __restrict__ info_d) {
     __shared__ PnpLsqShared sh;
     __shared__ ClusterRed R;
@@ -584,21 +618,14 @@ k_finalize_p(const PointPX* __restrict__ pts, size_t pts_q_stride, const double*
     if (tid == 0) {
         have_model = 0;
         if (s.best >= 0) {
-            double obj5[15], img5[10];
             for (int i = 0; i < PNP_MP; ++i) smp[i] = samples[((size_t)q * Hs + s.best) * PNP_MP + i];
-            if (rt) {
-                const double* m = rt + ((size_t)q * Hs + s.best) * 6;
-                bool any = false;
-                for (int i = 0; i < 6; ++i) {
-                    model[i] = m[i];
-                    any |= m[i] != 0;
-                }
-                have_model = any ? 1 : 0;   // the solve kernel stores zeros when the minimal solver produced no model
-            } else {
-            gather5(P, smp, obj5, img5);
-            have_model = (fast_solver ? pnp_minimal_model_fast(obj5, img5, K4[0], K4[1], K4[2], K4[3], model, model + 3)
-                                      : pnp_minimal_model(obj5, img5, K4[0], K4[1], K4[2], K4[3], model, model + 3)) ? 1 : 0;
+            const double* m = win + (size_t)q * 6;   // k_winner_model_p: zeros when the minimal solver produced no model
+            bool any = false;
+            for (int i = 0; i < 6; ++i) {
+                model[i] = m[i];
+                any |= m[i] != 0;
             }
+            have_model = any ? 1 : 0;
         }
     }
     __syncthreads();
