@@ -1,3 +1,9 @@
+// The product's eigen-solvers come from csrc/solver_h.cuh (#include below): k_warp / k_warp3 / k_thread2 time exactly what the
+// library runs.  Two kinds of code are defined HERE: (1) earlier forms that the product no longer contains (the strided thread
+// form, warp2), kept as baselines; (2) *_prof variants — jacobi_eig_warp / _warp3 with clock64() reads between their sections.
+// An instrumented function cannot be the product function, so main() holds every *_prof variant to the product form's result
+// bit for bit on the matrices it times ("*_prof_vs_product_bit_differences" must print 0): if the product kernel changes and
+// the instrumented text is not updated with it, this probe says so instead of silently timing something else.
 // Probe: where the time of one 9x9 Jacobi eigen-decomposition (OpenCV's pivot order, fp64) goes on an SM, and the fp64
 // dependent-issue latencies that bound it.  One warp per decomposition (jacobi_eig_warp), one thread per decomposition
 // (jacobi_eig_strided), and the section cycle counts of the warp form.
@@ -896,6 +902,26 @@ int main() {
         printf("{\"probe\": \"warp3_sections\", \"matrix\": %d, \"rotations\": %d, \"cycles_total\": %lld, \"per_rotation\": {\"install_pivot\": %.0f, \"prefetch_refresh\": %.0f, \"arith\": %.0f, \"rotate_sync\": %.0f}}\n",
                r, pf.rotations, pf.total, (double)pf.pivot / pf.rotations, (double)pf.ind / pf.rotations, (double)pf.arith / pf.rotations,
                (double)pf.rotate / pf.rotations);
+    }
+    {   // drift check: the instrumented variants against the product forms on the same matrices
+        size_t bad = 0;
+        for (int r = 0; r < 8; ++r) {
+            double wp[9], wq[9];
+            k_warp3<<<1, 32>>>(dm + 81 * r, 1, dW2, dV2);
+            CK(cudaMemcpy(wq, dW2, sizeof(wq), cudaMemcpyDeviceToHost));
+            k_warp3_prof<<<1, 32>>>(dm + 81 * r, dW, dpf);
+            CK(cudaMemcpy(wp, dW, sizeof(wp), cudaMemcpyDeviceToHost));
+            bad += memcmp(wp, wq, sizeof(wp)) != 0;
+            k_warp_prof<<<1, 32>>>(dm + 81 * r, dW, dpf);
+            CK(cudaMemcpy(wp, dW, sizeof(wp), cudaMemcpyDeviceToHost));
+            bad += memcmp(wp, wq, sizeof(wp)) != 0;
+            k_warp2_prof<<<1, 32>>>(dm + 81 * r, dW, dpf);
+            CK(cudaMemcpy(wp, dW, sizeof(wp), cudaMemcpyDeviceToHost));
+            bad += memcmp(wp, wq, sizeof(wp)) != 0;
+        }
+        CK(cudaGetLastError());
+        printf("{\"probe\": \"prof_variants_vs_product_bit_differences\", \"count\": %zu}\n", bad);
+        if (bad) { fprintf(stderr, "an instrumented variant no longer computes what csrc/solver_h.cuh computes\n"); return 1; }
     }
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     auto time_it = [&](const char* name, int nmat, auto launch) {
