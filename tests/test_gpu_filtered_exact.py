@@ -273,3 +273,22 @@ def test_pnp_full_size_equals_unfiltered(ctx, oracle):
     b = ctx.score_p(models, P, px, K, np.float32(64.0), ransac_b200.ARITH_EXACT_UNFILTERED)
     np.testing.assert_array_equal(a, b)
     assert a.max() > 40_000
+
+
+def test_pnp_non_finite_points_and_huge_intrinsics(ctx, oracle):
+    """A NaN / infinite object point or pixel sends its tile through OpenCV's sequence (the other tiles stay filtered); an
+    intrinsics matrix beyond the guards (2^41) sends every tile there: the two routes return the same counts."""
+    rng = np.random.default_rng(451)
+    P, px, _ = synth.pnp_set(3100, 0.4, rng)
+    models = _poses(oracle, rng, 150, 150)
+    for where, value in ((5, np.nan), (1500, np.inf), (3099, -np.inf)):
+        P2, px2 = P.copy(), px.copy()
+        P2[where, 1] = value
+        _pnp_check(ctx, models, P2, px, np.float32(64.0))
+        px2[where, 0] = value
+        _pnp_check(ctx, models, P, px2, np.float32(64.0))
+    Kbig = K.copy()
+    Kbig[0, 0] = 2.0 ** 41
+    got = ctx.score_p(models, P, px, Kbig, np.float32(64.0), ransac_b200.ARITH_EXACT)
+    unf = ctx.score_p(models, P, px, Kbig, np.float32(64.0), ransac_b200.ARITH_EXACT_UNFILTERED)
+    np.testing.assert_array_equal(got, unf)
