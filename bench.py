@@ -481,6 +481,17 @@ def extras(ctx, args, rank, world, device, src, dst):
         pnp[name] = {"k3_evals_per_s": float(N) * H / (best["score"] * 1e-3), "step_evals_per_s": float(N) * H / (best["total"] * 1e-3),
                      "stage_ms": best}
     pnp["fast"]["k3_tflops_at_26_flop_per_eval"] = pnp["fast"]["k3_evals_per_s"] * 26.0 / 1e12
+    # bit-exact scoring goes through the filtered predicate (csrc/score_p_filt.cuh); OpenCV's sequence on EVERY evaluation must
+    # give the same answer
+    _, _, _, info_f = pp.fetch(want_inliers=False)
+    par_u = ransac_b200.make_p_params(8.0, H, 0.99, sampler=ransac_b200.SAMPLER_PHILOX, seed=5, arith=ransac_b200.ARITH_EXACT_UNFILTERED,
+                                      solver=ransac_b200.SOLVER_EXACT)
+    pp.run(par_u)
+    _, _, _, info_u = pp.fetch(want_inliers=False)
+    same = all(info_f[0][k] == info_u[0][k] for k in ("best_count", "n_inliers", "sample"))
+    pnp["exact"]["unfiltered"] = {"k3_evals_per_s": float(N) * H / (pp.stage_ms()["score"] * 1e-3), "same_winner_and_counts": bool(same)}
+    if not same:
+        raise SystemExit("bench.py: filtered and un-filtered exact PnP scoring disagree: " + json.dumps([info_f[0], info_u[0]], default=str))
     pp.free()
     out["pnp_model"] = pnp
     # ---- homography model in parity arithmetic (OpenCV's DLT + Jacobi solver, un-fused fp32 scoring), same shape ------------------
@@ -494,7 +505,22 @@ def extras(ctx, args, rank, world, device, src, dst):
         ms = prob.stage_ms()
         best = ms if best is None or ms["total"] < best["total"] else best
     out["h_model_exact"] = {"k3_evals_per_s": float(N) * H / (best["score"] * 1e-3), "step_evals_per_s": float(N) * H / (best["total"] * 1e-3),
-                            "stage_ms": best, "what": "bit-exact models and inlier counts for the given samples (Philox sampler)"}
+                            "stage_ms": best, "what": "bit-exact models and inlier counts for the given samples (Philox sampler); "
+                                                      "scoring through the filtered exact predicate (csrc/score_h_filt.cuh)"}
+    # the same step with OpenCV's un-fused sequence on EVERY evaluation: the filter must not change the answer
+    _, _, info_f = prob.fetch(want_mask=False)
+    par_u = ransac_b200.make_params(THR_PX, H, sampler=ransac_b200.SAMPLER_PHILOX, seed=3, arith=ransac_b200.ARITH_EXACT_UNFILTERED,
+                                    solver=ransac_b200.SOLVER_EXACT)
+    best_u = None
+    for _ in range(2):
+        prob.run(par_u)
+        _, _, info_u = prob.fetch(want_mask=False)
+        ms = prob.stage_ms()
+        best_u = ms if best_u is None or ms["score"] < best_u["score"] else best_u
+    same = all(info_f[0][k] == info_u[0][k] for k in ("best_count", "n_inliers", "sample"))
+    out["h_model_exact"]["unfiltered"] = {"k3_evals_per_s": float(N) * H / (best_u["score"] * 1e-3), "same_winner_and_counts": bool(same)}
+    if not same:
+        raise SystemExit("bench.py: filtered and un-filtered exact scoring disagree: " + json.dumps([info_f[0], info_u[0]], default=str))
     prob.free()
     # ---- other BASELINE configs (homography model, fast arithmetic, Philox) -----------------------------------------------------
     other = {}
