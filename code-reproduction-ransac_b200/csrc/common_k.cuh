@@ -388,7 +388,7 @@ __device__ __forceinline__ void cholesky_solve(const double* L, const double* b,
 // dot products of the serial forms become N dependent column steps (one thread walking a 9x9 factorisation in local
 // memory was the longest sequential stretch of the finalize kernel's throughput mode).
 template <int N>
-__device__ bool cholesky_warp(const double* A, double* L) {
+__device__ __noinline__ bool cholesky_warp(const double* A, double* L) {   // one copy per kernel: inlined at four call sites it (and its fp64 divisions) bloated k_finalize_h to 39 584 instructions, and the serial part of the kernel waited on instruction fetches
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int i = lane < N ? lane : N - 1;   // idle lanes shadow the last row (results discarded)
@@ -417,7 +417,7 @@ __device__ bool cholesky_warp(const double* A, double* L) {
 
 // x = (L L^T)^-1 b
 template <int N>
-__device__ void cholesky_solve_warp(const double* L, const double* b, double* x) {
+__device__ __noinline__ void cholesky_solve_warp(const double* L, const double* b, double* x) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int i = lane < N ? lane : N - 1;

@@ -308,7 +308,7 @@ struct JacobiWarp9 {
 };
 
 template <int N>
-__device__ void jacobi_eig_warp(double* A, double* W, double* V, int* indR, int* indC) {
+__device__ __noinline__ void jacobi_eig_warp(double* A, double* W, double* V, int* indR, int* indC) {
     const int lane = threadIdx.x & 31;
     for (int e = lane; e < N * N; e += 32) V[e] = (e / N == e % N) ? 1. : 0.;
     if (lane < N) {
@@ -445,7 +445,7 @@ __device__ void jacobi_eig_warp(double* A, double* W, double* V, int* indR, int*
 // Same IEEE operations on every element: bit-identical to jacobi_eig<N> for finite matrices (others go to
 // jacobi_eig_warp).  indR / indC: shared-memory scratch of the fall-back only.
 template <int N>
-__device__ void jacobi_eig_warp3(double* A, double* W, double* V, int* indR, int* indC) {
+__device__ __noinline__ void jacobi_eig_warp3(double* A, double* W, double* V, int* indR, int* indC) {
     static_assert(N >= 2 && N <= 9, "lane layout");
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int BIG = 0x7fffffff;
