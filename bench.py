@@ -376,8 +376,8 @@ def run_b200(args):
         "flop_per_eval": F_ALG, "k3_evals_per_s": k3_evals_per_s, "k3_ms": k3_ms, "k3_share_of_step": k3_ms / stage_mean["total"],
         "ffma2_peak_tflops": 2.0 * fma_packed / 1e12,
         # dram__bytes_read + write of ONE k3_score_h launch at this shape from the committed ncu --set full capture
-        # (profiles/r01g_k3_score_h_fast_ncu_full.json); other shapes were not captured
-        "traffic": 5.311e6 if (N == 100_000 and Hper == 100_000 and args.arith == "fast") else None,
+        # (profiles/r02n_k3_score_h_fast_ncu_full.json: 5.21 MB read, 0 written); other shapes were not captured
+        "traffic": 5.2106e6 if (N == 100_000 and Hper == 100_000 and args.arith == "fast") else None,
         "hbm": {"algorithmic_bytes_per_launch": 16.0 * N + 36.0 * Hper, "achieved_GBps": (16.0 * N + 36.0 * Hper) / (k3_ms * 1e-3) / 1e9,
                 "peak_GBps": measured_peaks().get("hbm_gbs")},
     }
