@@ -7,6 +7,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 // the library is built with -fvisibility=hidden; exactly the symbols of the public header are exported
 #pragma GCC visibility push(default)

@@ -169,6 +169,22 @@ struct HEval {
     //           in shared memory): (s sx - s u w)^2 + (s sy - s v w)^2 - w^2: 11 FMA-pipe ops.
     // MUFU.RCP and FFMA2 do not overlap freely on sm_100 (profiles/r01_pipeprobe.jsonl: 4 FFMA2 + 1 MUFU take 12.4
     // cycles, not 8): the reciprocal costs more issue time than the one or two extra FFMA2 that replace it.
+    // FORM 4: FORM 3's margin with the last operation as two scalar FFMA.SAT on the NEGATED margin: the result is the
+    // inlier flag itself (1.0f / +0), which one FADD2 per pair accumulates.  10 FFMA2 + 2 FFMA.SAT + 1 FADD2 per pair
+    // and point instead of 11 FFMA2 + 2 LEA.HI.
+    __device__ __forceinline__ static f2_t inlier_flag_sat(const f2_t (&h)[8], f2_t X, f2_t Y, f2_t nu, f2_t nv, f2_t k) {
+        const f2_t w = f2_fma(h[6], X, f2_fma(h[7], Y, k));
+        const f2_t sx = f2_fma(h[0], X, f2_fma(h[1], Y, h[2]));
+        const f2_t sy = f2_fma(h[3], X, f2_fma(h[4], Y, h[5]));
+        const f2_t a = f2_fma(w, nu, sx);
+        const f2_t b = f2_fma(w, nv, sy);
+        const f2_t t = f2_mul(w, w);
+        float t0, t1, a0, a1, q0, q1;
+        f2_unpack(t, t0, t1);
+        f2_unpack(f2_fma(b, b, f2_pack(-t0, -t1)), q0, q1);
+        f2_unpack(a, a0, a1);
+        return f2_pack(__saturatef(__fmaf_rn(-a0, a0, -q0)), __saturatef(__fmaf_rn(-a1, a1, -q1)));
+    }
     template <int FORM>
     __device__ __forceinline__ static f2_t margin(const f2_t (&h)[8], f2_t X, f2_t Y, f2_t nu, f2_t nv, f2_t one, f2_t nthr) {
         const f2_t w = f2_fma(h[6], X, f2_fma(h[7], Y, one));
@@ -254,7 +270,8 @@ k3_score_h(const float4* __restrict__ models, int H, int H_stride, const PointH*
     // the float above thr (a squared distance: >= 0), so that "margin < 0" is "err <= thr"; +inf stays +inf
     const float thr_up = thr < __int_as_float(0x7f800000) ? __uint_as_float(__float_as_uint(thr) + 1u) : thr;
     const f2_t nthr = f2_dup(-thr_up);
-    constexpr bool SCALED = !EXACT && K3_FAST_FORM == 3;
+    constexpr bool SCALED = !EXACT && K3_FAST_FORM >= 3;
+    constexpr bool SATCNT = !EXACT && K3_FAST_FORM == 4;  // inlier flag = FFMA.SAT of the margin, counted by packed float adds
     const float s = rsqrtf(fmaxf(thr_up, 1e-30f));  // thr = 0 would scale by inf; 1e-30 px^2 is "exactly on the pixel" at fp32 accuracy
     if (SCALED) {
         const f2_t s2 = f2_dup(s);
@@ -262,6 +279,19 @@ k3_score_h(const float4* __restrict__ models, int H, int H_stride, const PointH*
         for (int j = 0; j < NPAIR; ++j)
 #pragma unroll
             for (int k = 0; k < 6; ++k) h[j][k] = f2_mul(h[j][k], s2);
+    }
+    // FORM 4: every coefficient (the implied h8 = 1 included) times 2^32, i.e. the margin times 2^64: sat(-margin) is 1.0f
+    // for every margin below -2^-64 w^2 and +0 for every margin >= 0 (NaN -> +0)
+    const f2_t one_k = SATCNT ? f2_dup(0x1p32f) : one;
+    f2_t cntf[NPAIR];
+    if (SATCNT) {
+        const f2_t k2 = f2_dup(0x1p32f);
+#pragma unroll
+        for (int j = 0; j < NPAIR; ++j) {
+            cntf[j] = f2_dup(0.0f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) h[j][k] = f2_mul(h[j][k], k2);
+        }
     }
 
     mbar_wait(bar, 0);
@@ -324,7 +354,9 @@ k3_score_h(const float4* __restrict__ models, int H, int H_stride, const PointH*
 #pragma unroll
         for (int j = 0; j < NPAIR; ++j) {
             float e0, e1;
-            if (!EXACT && K3_FAST_FORM != 0) {
+            if (SATCNT) {
+                cntf[j] = f2_add(cntf[j], HEval<EXACT>::inlier_flag_sat(h[j], X, Y, nu, nv, one_k));
+            } else if (!EXACT && K3_FAST_FORM != 0) {
                 f2_unpack(HEval<EXACT>::template margin<K3_FAST_FORM>(h[j], X, Y, nu, nv, one, nthr), e0, e1);
                 cnt[2 * j] += (int)(__float_as_uint(e0) >> 31);
                 cnt[2 * j + 1] += (int)(__float_as_uint(e1) >> 31);
@@ -336,6 +368,15 @@ k3_score_h(const float4* __restrict__ models, int H, int H_stride, const PointH*
         }
     }
 
+    if (SATCNT) {  // a tile holds far fewer than 2^24 points: the float sums are exact integers
+#pragma unroll
+        for (int j = 0; j < NPAIR; ++j) {
+            float c0, c1;
+            f2_unpack(cntf[j], c0, c1);
+            cnt[2 * j] = __float2int_rn(c0);
+            cnt[2 * j + 1] = __float2int_rn(c1);
+        }
+    }
 #pragma unroll
     for (int j = 0; j < 2 * NPAIR; ++j) {
         const int hh = h_base + j * K3_THREADS;
