@@ -948,3 +948,16 @@ int b2r_probe_fp32_peak(b2r_ctx* c, double* fma_per_s_out, double* ffma2_per_s_o
 }
 
 }  // extern "C"
+
+#ifdef B2R_FIN_PROFILE
+// development probe (see FINCLK in pipeline_h.cuh): read (and optionally clear) the per-section cycle counters
+extern "C" __attribute__((visibility("default"))) int b2r_debug_fin_clocks(unsigned long long* out, int reset) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (out && cudaMemcpyFromSymbol(out, b2r::g_fin_clk, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[32] = {0};
+        if (cudaMemcpyToSymbol(b2r::g_fin_clk, z, sizeof(z)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif

@@ -175,35 +175,87 @@ __device__ __forceinline__ void cluster_reduce(ClusterRed& R, double (&v)[NV]) {
     __syncthreads();
 }
 
-// Same reduction with the LAST NMAX of the NV values combined by max instead of + (one cluster barrier for a set of
-// sums plus a max-norm).
+// ---- warp reduction of NV values per lane ------------------------------------------------------------------------------
+// The butterfly-per-value form above costs NV x 5 64-bit shuffles per warp; with 35 values and sixteen warps the
+// shuffle unit, not the passes over the points, was the bulk of an LM evaluation (tools/prof_finalize_sections.py).
+// Transpose-reduce instead: in the step with lane offset o every lane keeps one half of its values and hands the other
+// half to lane ^ o, so M = 2^m values take M - 1 shuffles (+ the plain butterfly over the lane bits that are left when
+// M < 32), and lane L ends up with the warp total of value (L mod M) of its group.  Groups of 32 / 16 / 8 / 4 first; the
+// last NV mod 4 values (and the NMAX max-combined ones, which must be among them) go through the plain butterfly.
+// Fixed order: every warp, CTA and run produces the same bits.  Results: R.warp[warp * NV + value].
+template <int M, int OFF>
+__device__ __forceinline__ void warp_transpose_reduce_group(double* v, double* dst, int lane) {
+    constexpr unsigned FULL = 0xffffffffu;
+    // v[OFF .. OFF + M) are this group's values (static register indices throughout)
+#pragma unroll
+    for (int h = M / 2, o = 16; h >= 1; h >>= 1, o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const double send = up ? v[OFF + i] : v[OFF + i + h];
+            const double keep = up ? v[OFF + i + h] : v[OFF + i];
+            v[OFF + i] = keep + __shfl_xor_sync(FULL, send, o);
+        }
+    }
+    // lane bits below 32 / M have not been folded yet
+#pragma unroll
+    for (int o = 16 / M; o >= 1; o >>= 1) v[OFF] += __shfl_xor_sync(FULL, v[OFF], o);
+    // value index held by this lane: the lane bits 16, 8, ... consumed by the halving steps, most significant first
+    if constexpr (M == 32) { dst[OFF + lane] = v[OFF]; }
+    else if ((lane & (32 / M - 1)) == 0) { dst[OFF + (lane / (32 / M))] = v[OFF]; }
+}
+
+template <int NV, int NMAX>
+__device__ __forceinline__ void warp_reduce_multi(double (&v)[NV], double* dst) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    constexpr int NS = NV - NMAX;                 // values combined by +
+    constexpr int G32 = (NS / 32) * 32;
+    constexpr int G16 = G32 + (((NS - G32) / 16) * 16);
+    constexpr int G8 = G16 + (((NS - G16) / 8) * 8);
+    constexpr int G4 = G8 + (((NS - G8) / 4) * 4);
+    if constexpr (G32 > 0) warp_transpose_reduce_group<32, 0>(v, dst, lane);
+    static_assert(G32 <= 32, "one group of 32 at most");
+    if constexpr (G16 > G32) warp_transpose_reduce_group<16, G32>(v, dst, lane);
+    if constexpr (G8 > G16) warp_transpose_reduce_group<8, G16>(v, dst, lane);
+    if constexpr (G4 > G8) warp_transpose_reduce_group<4, G8>(v, dst, lane);
+#pragma unroll
+    for (int i = G4; i < NV; ++i) {
+        double x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_xor_sync(FULL, x, o);
+            x = i >= NS ? fmax(x, y) : x + y;
+        }
+        if (lane == 0) dst[i] = x;
+    }
+}
+
+// Cluster-wide reduction with the LAST NMAX of the NV values combined by max instead of + (one cluster barrier for a set
+// of sums plus a max-norm).
 template <int THREADS, int NV, int NMAX>
 __device__ __forceinline__ void cluster_reduce_tail_max(ClusterRed& R, double (&v)[NV]) {
     static_assert(NV <= RED_MAX && NMAX <= NV, "too many values");
     cg::cluster_group cluster = cg::this_cluster();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        double x = v[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double y = __shfl_down_sync(0xffffffffu, x, o);
-            x = i >= NV - NMAX ? fmax(x, y) : x + y;
-        }
-        if (lane == 0) R.warp[warp * NV + i] = x;
-    }
+    warp_reduce_multi<NV, NMAX>(v, R.warp + (threadIdx.x >> 5) * NV);
     __syncthreads();
     const int ph = R.phase;
+    const unsigned nb = cluster.num_blocks();
     if (threadIdx.x < NV) {
         const bool is_max = (int)threadIdx.x >= NV - NMAX;
         double s = R.warp[threadIdx.x];
+#pragma unroll
         for (int w = 1; w < THREADS / 32; ++w) s = is_max ? fmax(s, R.warp[w * NV + threadIdx.x]) : s + R.warp[w * NV + threadIdx.x];
-        R.part[ph][threadIdx.x] = s;
+        if (nb == 1) R.out[threadIdx.x] = s;   // a single CTA: no exchange
+        else R.part[ph][threadIdx.x] = s;
+    }
+    if (nb == 1) {
+        __syncthreads();
+        return;
     }
     cluster.sync();
     if (threadIdx.x < NV) {
         const bool is_max = (int)threadIdx.x >= NV - NMAX;
-        const unsigned nb = cluster.num_blocks();
         double s = 0;
         for (unsigned r = 0; r < nb; ++r) {
             const double* remote = cluster.map_shared_rank(&R.part[ph][0], r);
@@ -215,43 +267,46 @@ __device__ __forceinline__ void cluster_reduce_tail_max(ClusterRed& R, double (&
     __syncthreads();
 }
 
-// The same deterministic all-to-all reduction over a whole cooperative GRID (one big problem on all SMs): every CTA
-// publishes its partials in global memory, one grid barrier, every CTA sums all partials in CTA order.  gscratch holds
-// 2 x gridDim.x x RED_MAX doubles (double-buffered like ClusterRed::part).  The LAST NMAX values are combined by max.
+// The same deterministic all-to-all reduction over a whole cooperative GRID (one big problem on many SMs): every CTA
+// publishes its partials in global memory, one grid barrier, every CTA combines all partials in the same fixed order —
+// one warp per value, lane r takes the partials of CTAs r, r + 32, ... (the loads of a value are issued together: one L2
+// round trip instead of gridDim.x / 4), then a butterfly over the lanes.  gscratch holds 2 x gridDim.x x RED_MAX doubles
+// (double-buffered like ClusterRed::part).  The LAST NMAX values are combined by max.
 template <int THREADS, int NV, int NMAX>
 __device__ __forceinline__ void grid_reduce_tail_max(ClusterRed& R, double (&v)[NV], double* __restrict__ gscratch) {
     static_assert(NV <= RED_MAX && NMAX <= NV, "too many values");
+    constexpr unsigned FULL = 0xffffffffu;
     cg::grid_group grid = cg::this_grid();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        double x = v[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double y = __shfl_down_sync(0xffffffffu, x, o);
-            x = i >= NV - NMAX ? fmax(x, y) : x + y;
-        }
-        if (lane == 0) R.warp[warp * NV + i] = x;
-    }
+    warp_reduce_multi<NV, NMAX>(v, R.warp + warp * NV);
     __syncthreads();
     const int ph = R.phase;
     double* buf = gscratch + (size_t)ph * gridDim.x * RED_MAX;
     if (threadIdx.x < NV) {
         const bool is_max = (int)threadIdx.x >= NV - NMAX;
         double s = R.warp[threadIdx.x];
+#pragma unroll
         for (int w = 1; w < THREADS / 32; ++w) s = is_max ? fmax(s, R.warp[w * NV + threadIdx.x]) : s + R.warp[w * NV + threadIdx.x];
         buf[(size_t)blockIdx.x * RED_MAX + threadIdx.x] = s;
     }
     __threadfence();
     grid.sync();
-    if (threadIdx.x < NV) {
-        const bool is_max = (int)threadIdx.x >= NV - NMAX;
+    for (int val = warp; val < NV; val += THREADS / 32) {
+        const bool is_max = val >= NV - NMAX;
         double s = 0;
-        for (unsigned r = 0; r < gridDim.x; ++r) {
-            const double x = __ldcg(buf + (size_t)r * RED_MAX + threadIdx.x);
-            s = r == 0 ? x : (is_max ? fmax(s, x) : s + x);
+        bool have = false;
+        for (unsigned r = lane; r < gridDim.x; r += 32) {
+            const double x = __ldcg(buf + (size_t)r * RED_MAX + val);
+            s = !have ? x : (is_max ? fmax(s, x) : s + x);
+            have = true;
         }
-        R.out[threadIdx.x] = s;
+        // lanes without a partial contribute the neutral element (a max over non-negative norms / a sum)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_xor_sync(FULL, s, o);
+            s = is_max ? fmax(s, y) : s + y;
+        }
+        if (lane == 0) R.out[val] = s;
     }
     if (threadIdx.x == 0) R.phase = ph ^ 1;
     __syncthreads();
@@ -451,6 +506,108 @@ __device__ __noinline__ void cholesky_solve_warp(const double* L, const double* 
     }
     if (lane < N) x[i] = xi;
     __syncwarp();
+}
+
+// ---- register-resident Cholesky of a 9x9 SPD system (throughput paths of the finalize kernel) ---------------------------
+// Lane i (< N; the others shadow lane N-1) owns row i of L, column i of L and 1/L[i][i] in registers; nothing passes
+// through shared memory between the factorisation and the substitutions.  Right-looking: column j costs one broadcast
+// of the pivot, one rsqrt (L[j][j] = a rs, L[i][j] = a[i][j] rs: no square root followed by a division), the N-1-j
+// broadcasts of the new column (independent shuffles) and one FMA per trailing entry; the substitutions multiply by
+// the stored reciprocal.  ~2.5k cycles for factorisation + solve against ~11k for cholesky_warp + cholesky_solve_warp
+// through shared memory (tools/prof_finalize_sections.py).  Not bit-identical to cholesky<N> (rsqrt, reciprocals): used
+// only where the iterates are not pinned to OpenCV's bits (parallel-sum refinement, throughput mode).
+template <int N>
+struct CholRegs {
+    double row[N];   // L[i][k], k <= i
+    double col[N];   // L[k][i], k > i
+    double rinv;     // 1 / L[i][i]
+    bool ok;
+};
+
+// a[k] = A[i][k] (k <= i is what is read).  Every lane of the warp calls.
+template <int N>
+__device__ __forceinline__ void chol_regs_factor(double (&a)[N], double dmax, CholRegs<N>& F) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    F.ok = true;
+    F.rinv = 1;
+#pragma unroll
+    for (int k = 0; k < N; ++k) { F.row[k] = 0; F.col[k] = 0; }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const double ajj = __shfl_sync(FULL, a[j], j);
+        if (!(ajj > dmax * 1e-14)) F.ok = false;               // warp-uniform; the garbage that follows is discarded by the caller
+        const double rs = rsqrt(ajj);
+        const double lij = lane == j ? ajj * rs : a[j] * rs;   // lanes i < j: unused
+        F.row[j] = lij;
+        if (lane == j) F.rinv = rs;
+#pragma unroll
+        for (int m = 0; m < N; ++m) {                          // fixed bounds: both loops unroll, every index is static
+            if (m > j) {
+                const double vm = __shfl_sync(FULL, lij, m);   // L[m][j]
+                if (lane == j) F.col[m] = vm;
+                a[m] -= lij * vm;                              // a[i][m] -= L[i][j] L[m][j], meaningful for i >= m
+            }
+        }
+    }
+}
+
+// x_i = ((L L^T)^-1 b)_i; b_i is this lane's entry
+template <int N>
+__device__ __forceinline__ double chol_regs_solve(const CholRegs<N>& F, double b_i) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    double t = b_i, y = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double q = t * F.rinv;
+        const double yk = __shfl_sync(FULL, q, k);
+        if (lane == k) y = q;
+        t -= F.row[k] * yk;          // meaningful for lanes > k
+    }
+    double u = y, x = 0;
+#pragma unroll
+    for (int r = N - 1; r >= 0; --r) {
+        const double q = u * F.rinv;
+        const double xr = __shfl_sync(FULL, q, r);
+        if (lane == r) x = q;
+        u -= F.col[r] * xr;          // meaningful for lanes < r
+    }
+    return x;
+}
+
+// diag((L L^T)^-1)_i: the rows of M = L^-1 by forward substitution on the identity (lane i owns row i), then column sums
+// of squares through `scratch` (N x N doubles of shared memory).
+template <int N>
+__device__ __forceinline__ double chol_regs_inv_diag(const CholRegs<N>& F, double* scratch) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int i = lane < N ? lane : N - 1;
+    double acc[N], fin[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) { acc[j] = j == i ? 1. : 0.; fin[j] = 0; }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            if (j <= k) {
+                const double mkj = __shfl_sync(FULL, acc[j] * F.rinv, k);   // M[k][j]
+                if (lane == k) fin[j] = mkj;
+                acc[j] -= F.row[k] * mkj;                                    // meaningful for lanes > k
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < N) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) scratch[lane * N + j] = fin[j];
+    }
+    __syncwarp();
+    double d = 0;
+#pragma unroll
+    for (int r = 0; r < N; ++r) d += scratch[r * N + i] * scratch[r * N + i];
+    __syncwarp();
+    return d;
 }
 
 }  // namespace b2r

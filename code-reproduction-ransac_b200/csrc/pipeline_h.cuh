@@ -327,45 +327,63 @@ __device__ __forceinline__ float h_err_exact(const float* Hf, float X, float Y, 
 }
 
 // Eigenvector of the smallest eigenvalue of the symmetric PSD 9x9 L^T L by shifted inverse iteration
-// (fast-solver mode; the exact mode runs OpenCV's Jacobi).  One warp; LtL (upper triangle filled), A, L, b, x in shared
-// memory; the result is left in b.  false -> caller falls back to Jacobi.
-__device__ __forceinline__ bool smallest_eigvec9_warp(const double* LtL, double* A, double* L, double* b, double* x) {
+// (fast-solver mode; the exact mode runs OpenCV's Jacobi).  One warp; LtL in shared memory (upper triangle filled); lane i
+// keeps row i of the Cholesky factor and entry i of the iterate in registers (chol_regs_*); the result is written to
+// out[0..9).  false -> caller falls back to Jacobi.
+__device__ __forceinline__ bool smallest_eigvec9_warp(const double* LtL, double* out) {
+    constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    for (int e = lane; e < 81; e += 32) {
-        const int j = e / 9, k = e % 9;
-        A[e] = j <= k ? LtL[j * 9 + k] : LtL[k * 9 + j];
-    }
-    __syncwarp();
-    double tr = 0;
-    for (int j = 0; j < 9; ++j) tr += A[j * 9 + j];
+    const int i = lane < 9 ? lane : 8;
+    double tr = 0, dmax = 0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { tr += LtL[j * 10]; dmax = fmax(dmax, fabs(LtL[j * 10])); }
     const double mu = tr * 1e-13;
-    __syncwarp();
-    if (lane < 9) A[lane * 10] += mu;
-    __syncwarp();
-    if (!cholesky_warp<9>(A, L)) return false;
-    if (lane < 9) b[lane] = 1. / 3.;
-    __syncwarp();
+    double a[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a[k] = (k <= i ? LtL[k * 9 + i] : LtL[i * 9 + k]) + (k == i ? mu : 0.);
+    CholRegs<9> F;
+    chol_regs_factor<9>(a, dmax + mu, F);
+    if (!F.ok) return false;
+    double b = 1. / 3.;
     for (int it = 0; it < 16; ++it) {
-        cholesky_solve_warp<9>(L, b, x);
-        double nrm = 0;
-        for (int j = 0; j < 9; ++j) nrm += x[j] * x[j];
-        nrm = 1. / sqrt(nrm);
-        double diff = 0;
-        for (int j = 0; j < 9; ++j) diff = fmax(diff, fabs(x[j] * nrm - b[j]));
-        __syncwarp();
-        if (lane < 9) b[lane] = x[lane] * nrm;
-        __syncwarp();
+        const double x = chol_regs_solve<9>(F, b);
+        double n2 = lane < 9 ? x * x : 0.;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(FULL, n2, o);
+        const double xn = x * (1. / sqrt(n2));
+        double diff = lane < 9 ? fabs(xn - b) : 0.;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) diff = fmax(diff, __shfl_xor_sync(FULL, diff, o));
+        b = xn;
         if (it > 1 && diff < 1e-15) break;
     }
+    if (lane < 9) out[lane] = b;
+    __syncwarp();
     return true;
 }
+
+// Development probe (tools/prof_finalize_sections.py builds a copy of the library with -DB2R_FIN_PROFILE): clock64() deltas
+// of thread 0 of CTA 0 accumulated per section of k_finalize_h.  Compiled out of the product.
+#ifdef B2R_FIN_PROFILE
+__device__ unsigned long long g_fin_clk[32];
+#define FINCLK(sec)                                                                  \
+    do {                                                                             \
+        if (threadIdx.x == 0 && blockIdx.x == 0) {                                   \
+            const long long now_ = clock64();                                        \
+            atomicAdd(&g_fin_clk[sec], (unsigned long long)(now_ - fin_last_));      \
+            fin_last_ = now_;                                                        \
+        }                                                                            \
+    } while (0)
+#else
+#define FINCLK(sec) do { } while (0)
+#endif
 
 struct HFinalizeShared {
     double H[9];          // current model (fp64)
     double x[9], xd[9];   // LM parameter vectors (all nine entries of H, as OpenCV 4.13 refines them)
     double A[81], v[9], D[9], d[9];
     double Ap[81], diag[9];
-    double L[81];          // Cholesky factor of the damped / regularised J^T J
+    double L[81], Lrinv[9];  // rows of the Cholesky factor of the regularised J^T J (lambda == 0 step) and 1 / its diagonal
     double Ac[81], vc[9];  // J^T J and J^T r at the trial point (become A, v when the step is accepted)
     double S, Sd, lambda, lc, rmax, nu;
     float Hf[8];
@@ -416,6 +434,9 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
     uint8_t* mask = mask_out + (size_t)q * n;
     const HSelect s = sel[q];
     int* inf = info + (size_t)q * 12;
+#ifdef B2R_FIN_PROFILE
+    long long fin_last_ = clock64();
+#endif
     if (tid == 0) R.phase = 0;
 
     if (s.best < 0) {  // no model: cv2 returns (None, zeros)
@@ -473,6 +494,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
         double kv[1] = {(double)k_local};
         TEAM_REDUCE(1, 0, kv);
     }
+    FINCLK(0);   // RANSAC-stage mask + count
     const int k = (int)R.out[0];
     const bool refit = refine && n > 4 && k >= 4;
     if (stored_model && !refit) minimal_model64();   // the minimal model is what is returned
@@ -526,6 +548,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
             TEAM_REDUCE(4, 0, a);
             nm.smx = R.out[0]; nm.smy = R.out[1]; nm.sMx = R.out[2]; nm.sMy = R.out[3];
         }
+        FINCLK(1);   // normalisation statistics (two passes)
         const bool degenerate = fabs(nm.smx) < DBL_EPSILON || fabs(nm.smy) < DBL_EPSILON ||
                                 fabs(nm.sMx) < DBL_EPSILON || fabs(nm.sMy) < DBL_EPSILON;
         if (degenerate && stored_model) minimal_model64();   // runKernel fails on the inliers: the LM starts from the minimal model
@@ -577,6 +600,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     }
                 }
             if (!seq) TEAM_REDUCE(24, 0, L);
+            FINCLK(2);   // L^T L pass + reduction
             if (tid < 32) {  // warp 0
                 // index of (a,b), a<=b, in the packed symmetric 3x3: (0,0)=0 (0,1)=1 (0,2)=2 (1,1)=3 (1,2)=4 (2,2)=5
                 const int sym[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
@@ -599,7 +623,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                 __syncwarp();
                 double Hm[9], vec[9];
                 bool done = false;
-                if (fast_solver && smallest_eigvec9_warp(LtL, jw.V, sh.L, sh.diag, sh.d)) {
+                if (fast_solver && smallest_eigvec9_warp(LtL, sh.diag)) {
                     for (int i = 0; i < 9; ++i) vec[i] = sh.diag[i];
                     h_from_eigvec(vec, nm, Hm);
                     done = true;
@@ -609,6 +633,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     for (int i = 0; i < 9; ++i) sh.H[i] = Hm[i];
             }
             __syncthreads();
+            FINCLK(3);   // eigenvector of L^T L
         }
 
         // ---- Levenberg-Marquardt, max 10 iterations, eps = FLT_EPSILON (cv::LMSolver) ---------------------
@@ -737,142 +762,177 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                         acc[31 + u] += a[u] * rr;
                     }
                 }
+            FINCLK(11);  // eval: pass over the points
             TEAM_REDUCE(35, 1, acc);
+            FINCLK(12);  // eval: reduction (block + team barrier + partials)
             const double S = R.out[0], rmax = R.out[34];
-            if (tid == 0) {
+            for (int e = tid; e < 90; e += THREADS) {   // one thread per entry of J^T J (81) and J^T r (9)
                 const double* o = R.out;
-                const int sym[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
-                for (int j = 0; j < 81; ++j) sh.Ac[j] = 0;
-                for (int u = 0; u < 3; ++u) {
-                    for (int w = 0; w < 3; ++w) {
-                        const int e = sym[u][w];
-                        sh.Ac[u * 9 + w] = o[1 + e];
-                        sh.Ac[(3 + u) * 9 + 3 + w] = o[1 + e];
-                        sh.Ac[u * 9 + 6 + w] = sh.Ac[(6 + w) * 9 + u] = -o[7 + e];
-                        sh.Ac[(3 + u) * 9 + 6 + w] = sh.Ac[(6 + w) * 9 + 3 + u] = -o[13 + e];
-                        sh.Ac[(6 + u) * 9 + 6 + w] = o[19 + e];
-                    }
-                    sh.vc[u] = o[25 + u];
-                    sh.vc[3 + u] = o[28 + u];
-                    sh.vc[6 + u] = -o[31 + u];
+                if (e < 81) {
+                    const int r = e / 9, c = e % 9, br = r / 3, bc = c / 3, u = r % 3, w = c % 3;
+                    const int lo = u < w ? u : w, hi = u < w ? w : u;
+                    const int se = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);   // packed symmetric 3x3: (0,0)=0 (0,1)=1 (0,2)=2 (1,1)=3 (1,2)=4 (2,2)=5
+                    double val = 0;
+                    if (br == bc) val = br == 2 ? o[19 + se] : o[1 + se];
+                    else if (br + bc == 2 && br != 1) val = -o[7 + se];        // blocks (0,2), (2,0)
+                    else if (br + bc == 3) val = -o[13 + se];                 // blocks (1,2), (2,1)
+                    sh.Ac[e] = val;
+                } else {
+                    const int j = e - 81;
+                    sh.vc[j] = j < 3 ? o[25 + j] : (j < 6 ? o[28 + j - 3] : -o[31 + j - 6]);
                 }
             }
             __syncthreads();
+            FINCLK(13);  // eval: J^T J assembled by thread 0
             return make_double2(S, rmax);
         };
-        auto accept_candidate = [&]() {   // thread 0
-            for (int j = 0; j < 81; ++j) sh.A[j] = sh.Ac[j];
-            for (int j = 0; j < 9; ++j) sh.v[j] = sh.vc[j];
+        auto accept_candidate = [&]() {   // all threads; the caller's next barrier publishes it
+            for (int e = tid; e < 90; e += THREADS) {
+                if (e < 81) sh.A[e] = sh.Ac[e];
+                else sh.v[e - 81] = sh.vc[e - 81];
+            }
         };
 
         if (tid == 0)
             for (int i = 0; i < 9; ++i) sh.x[i] = sh.H[i];
         __syncthreads();
         {
+            FINCLK(4);
             const double2 e0 = eval(sh.x);
+            accept_candidate();
             if (tid == 0) {
-                accept_candidate();
                 sh.S = e0.x; sh.rmax = e0.y;
-                for (int i = 0; i < 9; ++i) sh.D[i] = sh.A[i * 9 + i];
+                for (int i = 0; i < 9; ++i) sh.D[i] = sh.Ac[i * 9 + i];
                 sh.lambda = 1; sh.lc = 0.75;
             }
             __syncthreads();
         }
         for (int iter = 0;;) {
+            FINCLK(5);   // loop control / first accept
             if (tid < 32) {   // warp 0
                 // J^T J is singular along h itself (the projection is scale-invariant): with lambda == 0 only the
                 // eigen-decomposition solve with OpenCV's cut-off is meaningful; with lambda > 0 the matrix is SPD
                 double* Ap = sh.Ap;
                 const double lambda = sh.lambda;
-                for (int e = tid; e < 81; e += 32) Ap[e] = sh.A[e];
-                __syncwarp();
-                if (tid < 9) Ap[tid * 10] += lambda * sh.D[tid];
-                __syncwarp();
                 bool solved = false;
-                if (seq) {
-                    // cv::solve(DECOMP_EIG) for every step, as OpenCV
-                } else if (lambda > 0) {
-                    solved = cholesky_warp<9>(Ap, sh.L);
-                } else if (fast_solver) {
-                    // throughput mode: the null direction is known (n = x/|x|, J n = 0, hence n.v = 0), so the
-                    // minimum-norm solution is that of the SPD system (A + s n n^T) d = v
-                    double nn = 0, tr = 0;
-                    for (int i = 0; i < 9; ++i) { nn += sh.x[i] * sh.x[i]; tr += sh.A[i * 9 + i]; }
-                    const double sg = tr / (9 * nn);
-                    for (int e = tid; e < 81; e += 32) Ap[e] += sg * sh.x[e / 9] * sh.x[e % 9];
+                if (seq || (lambda == 0 && !fast_solver)) {
+                    // cv::solve(DECOMP_EIG) below: every step in seq mode, as OpenCV; the undamped step of the exact solver
+                    for (int e = tid; e < 81; e += 32) Ap[e] = sh.A[e];
                     __syncwarp();
-                    solved = cholesky_warp<9>(Ap, sh.L);
-                    if (!solved) {
-                        __syncwarp();
+                    if (tid < 9) Ap[tid * 10] += lambda * sh.D[tid];
+                    __syncwarp();
+                } else {
+                    // lambda > 0: A + lambda D is SPD.  lambda == 0, throughput mode: the null direction is known
+                    // (n = x/|x|, J n = 0, hence n.v = 0), so the minimum-norm solution is that of the SPD system
+                    // (A + s n n^T) d = v.  Lane i holds row i; factorisation and substitutions in registers.
+                    const int i = tid < 9 ? tid : 8;
+                    double sg = 0;
+                    if (lambda == 0) {
+                        double nn = 0, tr = 0;
+#pragma unroll
+                        for (int r = 0; r < 9; ++r) { nn += sh.x[r] * sh.x[r]; tr += sh.A[r * 10]; }
+                        sg = tr / (9 * nn);
+                    }
+                    double a[9], dmax = 0;
+                    const double xi = sh.x[i];
+#pragma unroll
+                    for (int r = 0; r < 9; ++r) {
+                        dmax = fmax(dmax, fabs(sh.A[r * 10] + lambda * sh.D[r] + sg * sh.x[r] * sh.x[r]));
+                        a[r] = sh.A[i * 9 + r] + (r == i ? lambda * sh.D[r] : 0.) + sg * xi * sh.x[r];
+                    }
+                    CholRegs<9> F;
+                    chol_regs_factor<9>(a, dmax, F);
+                    solved = F.ok;
+                    if (solved) {
+                        const double di = chol_regs_solve<9>(F, sh.v[i]);
+                        if (tid < 9) {
+                            sh.d[tid] = di;
+                            if (lambda == 0) {   // the inverse diagonal, if this iteration asks for it, comes from this factor
+                                sh.Lrinv[tid] = F.rinv;
+#pragma unroll
+                                for (int r = 0; r < 9; ++r) sh.L[tid * 9 + r] = F.row[r];
+                            }
+                        }
+                    } else {
                         for (int e = tid; e < 81; e += 32) Ap[e] = sh.A[e];
+                        __syncwarp();
+                        if (tid < 9) Ap[tid * 10] += lambda * sh.D[tid];
                     }
                 }
-                if (solved) cholesky_solve_warp<9>(sh.L, sh.v, sh.d);
                 if (tid == 0) sh.use_eig = solved ? 0 : 1;
             }
             __syncthreads();
+            FINCLK(6);   // damped / regularised Cholesky step
             if (sh.use_eig && tid < 32) solve_sym_eig_warp<9>(jw, sh.Ap, sh.v, sh.d, nullptr);   // cv::solve(..., DECOMP_EIG)
             __syncthreads();
-            if (tid == 0)
-                for (int i = 0; i < 9; ++i) sh.xd[i] = sh.x[i] - sh.d[i];
+            FINCLK(7);   // eigen-decomposition step
+            if (tid < 9) sh.xd[tid] = sh.x[tid] - sh.d[tid];
             __syncthreads();
+            FINCLK(5);
             const double2 ed = eval(sh.xd);
+            double dS_par = 0, dv_par = 0;
+            if (!seq && tid < 32) {   // d.(2v - A d) and d.v: lane i takes row i, butterfly over the lanes
+                const int i = tid < 9 ? tid : 8;
+                double t = 0;
+#pragma unroll
+                for (int j = 0; j < 9; ++j) t += sh.A[i * 9 + j] * sh.d[j];
+                dS_par = tid < 9 ? sh.d[i] * (2 * sh.v[i] - t) : 0.;
+                dv_par = tid < 9 ? sh.d[i] * sh.v[i] : 0.;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    dS_par += __shfl_xor_sync(0xffffffffu, dS_par, o);
+                    dv_par += __shfl_xor_sync(0xffffffffu, dv_par, o);
+                }
+            }
             if (tid == 0) {
                 const double Sd = ed.x, S = sh.S;
                 sh.Sd = Sd;
                 sh.need_diag = 0;
-                double dS = 0;
+                double dS = dS_par;
                 if (seq) {   // cv::gemm(A, d, -1, v, 2) row by row (four partial sums), then cv::Mat::dot
                     double tmp[9];
                     for (int i = 0; i < 9; ++i) tmp[i] = cv_gemm_dot<9>(sh.A + i * 9, sh.d) * -1. + sh.v[i] * 2.;
                     dS = cv_mat_dot<9>(sh.d, tmp);
-                } else {
-                    for (int i = 0; i < 9; ++i) {
-                        double t = 0;
-                        for (int j = 0; j < 9; ++j) t += sh.A[i * 9 + j] * sh.d[j];
-                        dS += sh.d[i] * (2 * sh.v[i] - t);
-                    }
                 }
                 const double Rr = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
                 if (Rr > 0.75) {
                     sh.lambda *= 0.5;
                     if (sh.lambda < sh.lc) sh.lambda = 0;
                 } else if (Rr < 0.25) {
-                    double t = 0;
+                    double t = dv_par;
                     if (seq) t = cv_mat_dot<9>(sh.d, sh.v);
-                    else for (int i = 0; i < 9; ++i) t += sh.d[i] * sh.v[i];
                     double nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1) + 2;
                     nu = fmin(fmax(nu, 2.), 10.);
                     sh.nu = nu;
                     if (sh.lambda == 0) {
-                        sh.need_diag = fast_solver ? 3 : 2;   // 3: Cholesky route first (warp 0, below); 2: from the eigen-decomposition
+                        sh.need_diag = (fast_solver && !sh.use_eig) ? 3 : 2;   // 3: from the Cholesky factor of this iteration's step (warp 0, below); 2: from the eigen-decomposition
                     } else {
                         sh.lambda *= nu;
                     }
                 }
             }
             __syncthreads();
+            FINCLK(8);   // gain ratio, lambda update (thread 0)
             if (sh.need_diag == 3 && tid < 32) {   // diag of the pseudo-inverse = diag((A + s n n^T)^-1) - n_i^2 / s
+                const int i = tid < 9 ? tid : 8;
                 double nn = 0, tr = 0;
-                for (int i = 0; i < 9; ++i) { nn += sh.x[i] * sh.x[i]; tr += sh.A[i * 9 + i]; }
+#pragma unroll
+                for (int r = 0; r < 9; ++r) { nn += sh.x[r] * sh.x[r]; tr += sh.A[r * 10]; }
                 const double sg = tr / (9 * nn);
-                for (int e = tid; e < 81; e += 32) sh.Ap[e] = sh.A[e] + sg * sh.x[e / 9] * sh.x[e % 9];
-                __syncwarp();
-                const bool have = cholesky_warp<9>(sh.Ap, sh.L);
-                if (have)
-                    for (int j = 0; j < 9; ++j) {
-                        if (tid < 9) jw.W[tid] = tid == j ? 1. : 0.;
-                        __syncwarp();
-                        cholesky_solve_warp<9>(sh.L, jw.W, jw.V);
-                        if (tid == 0) sh.diag[j] = jw.V[j] - sh.x[j] * sh.x[j] / (nn * sg);
-                        __syncwarp();
-                    }
-                if (tid == 0) sh.need_diag = have ? 1 : 2;
+                CholRegs<9> F;
+                F.ok = true;
+                F.rinv = sh.Lrinv[i];
+#pragma unroll
+                for (int r = 0; r < 9; ++r) { F.row[r] = sh.L[i * 9 + r]; F.col[r] = 0; }
+                const double dg = chol_regs_inv_diag<9>(F, jw.V);
+                if (tid < 9) sh.diag[tid] = dg - sh.x[tid] * sh.x[tid] / (nn * sg);
+                if (tid == 0) sh.need_diag = 1;
             }
             __syncthreads();
             // lambda was 0 in this iteration: the step came from the eigen-decomposition of this same A (Ap = A + 0 D)
             if (sh.need_diag == 2 && tid < 32) solve_sym_eig_warp<9>(jw, sh.A, nullptr, nullptr, sh.diag, sh.use_eig != 0);
             __syncthreads();
+            FINCLK(9);   // inverse diagonal
             if (tid == 0) {
                 if (sh.need_diag) {
                     double maxval = DBL_EPSILON;
@@ -885,10 +945,10 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                     sh.S = sh.Sd;
                     sh.rmax = ed.y;
                     for (int i = 0; i < 9; ++i) sh.x[i] = sh.xd[i];
-                    accept_candidate();
                 }
             }
             __syncthreads();
+            if (sh.flag) accept_candidate();
             ++iter;
             if (tid == 0) {
                 double dmax = 0;
@@ -897,6 +957,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                 sh.lm_iters = iter;
             }
             __syncthreads();
+            FINCLK(10);  // accept + stopping test
             if (!sh.proceed) break;
         }
         if (tid == 0) {
@@ -933,6 +994,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
         inf[4] = smp.x; inf[5] = smp.y; inf[6] = smp.z; inf[7] = smp.w;
         inf[8] = (int)R.out[0]; inf[9] = sh.lm_iters; inf[10] = s.pad; inf[11] = 0;
     }
+    FINCLK(14);  // final mask + outputs
     if (!GRID) cluster.sync();  // no CTA may exit while a peer can still read its shared memory
 #undef TEAM_REDUCE
 }
