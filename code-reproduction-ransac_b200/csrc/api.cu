@@ -359,14 +359,14 @@ __global__ void k_resample_winner(const PointH* __restrict__ pts, int n, const u
     sel[q] = s;
 }
 
-// K4 launch: one thread-block cluster per problem (8 x 1024 threads for large n), one CTA for small problems; a single
-// large problem runs on a cooperative grid over all SMs instead (reductions through global memory + grid barriers).
+// K4 launch: one thread-block cluster per problem, one CTA for small problems; a single problem of 4096 points or more
+// runs on a cooperative grid instead (reductions through global memory + grid barriers).
 static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samples, int Hs, const HSelect* sel, float thr_sq,
                            int mask_semantics, int refine, int solver, double* H_out, uint8_t* mask_out, uint8_t* rmask_out,
                            int* info, const uint8_t* ext_mask, const double* ext_H, int Q, const float4* models = nullptr) {
     // problems of the reference's size with the exact solver: sums in OpenCV's order, eigen-solves only (kernel comment)
     int seq = (solver == B2R_SOLVER_EXACT && refine == B2R_REFINE_CV && n > 4 && n <= 128) ? 1 : 0;
-    if (Q == 1 && n >= 32768) {
+    if (Q == 1 && n >= 4096) {
         constexpr int GT = 512;
         static thread_local int coop_ok[16] = {0};
         int& ok = coop_ok[c->device & 15];
@@ -375,9 +375,13 @@ static int launch_finalize(b2r_ctx* c, const PointH* pts, int n, const int* samp
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finalize_h<GT, true>, GT, 0));
             ok = per_sm >= 1 ? 1 : -1;
         }
-        // the grid barrier costs more with every CTA that joins it: ~5 points per thread balances the passes over the points
-        // against the ~25 barriers of a step (measured at 100k points: 148 CTAs 0.226 ms, 74: 0.194, 37: 0.186, 18: 0.205)
-        const int ctas = ok > 0 ? std::min(c->sm_count, std::max(8, (n + GT * 5 - 1) / (GT * 5))) : -1;
+        // the passes over the points are bound by the SM's fp64 rate (~150 operations per point and LM evaluation), the ~10
+        // reductions of a call by the grid barrier and the gather of the partials, which grow with the CTAs that join:
+        // measured (tools/perf_finalize_grid.py, profiles/r02s_finalize_grid_tuning.jsonl) one point per thread is best up
+        // to ~20 000 points (20 000 points: 0.075 ms against 0.114 ms for a cluster of four CTAs), two above (100 000
+        // points: 0.093 ms; 148 CTAs 0.105); below 4096 points a single cluster is faster
+        const int ppt = n >= 32768 ? 2 : 1;
+        const int ctas = ok > 0 ? std::min(c->sm_count, std::max(2, (n + GT * ppt - 1) / (GT * ppt))) : -1;
         if (ctas > 0) {
             CU(c->gscratch.reserve(sizeof(double) * 2 * (size_t)ctas * RED_MAX));
             double* gs = c->gscratch.as<double>();

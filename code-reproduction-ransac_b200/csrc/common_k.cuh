@@ -269,8 +269,8 @@ __device__ __forceinline__ void cluster_reduce_tail_max(ClusterRed& R, double (&
 
 // The same deterministic all-to-all reduction over a whole cooperative GRID (one big problem on many SMs): every CTA
 // publishes its partials in global memory, one grid barrier, every CTA combines all partials in the same fixed order —
-// one warp per value, lane r takes the partials of CTAs r, r + 32, ... (the loads of a value are issued together: one L2
-// round trip instead of gridDim.x / 4), then a butterfly over the lanes.  gscratch holds 2 x gridDim.x x RED_MAX doubles
+// eight lanes per value, all values at once (the loads are issued together: one L2 round trip per 64 CTAs instead of one
+// per four), then a butterfly over the eight lanes.  gscratch holds 2 x gridDim.x x RED_MAX doubles
 // (double-buffered like ClusterRed::part).  The LAST NMAX values are combined by max.
 template <int THREADS, int NV, int NMAX>
 __device__ __forceinline__ void grid_reduce_tail_max(ClusterRed& R, double (&v)[NV], double* __restrict__ gscratch) {
@@ -288,25 +288,34 @@ __device__ __forceinline__ void grid_reduce_tail_max(ClusterRed& R, double (&v)[
 #pragma unroll
         for (int w = 1; w < THREADS / 32; ++w) s = is_max ? fmax(s, R.warp[w * NV + threadIdx.x]) : s + R.warp[w * NV + threadIdx.x];
         buf[(size_t)blockIdx.x * RED_MAX + threadIdx.x] = s;
+        __threadfence();
     }
-    __threadfence();
     grid.sync();
-    for (int val = warp; val < NV; val += THREADS / 32) {
+    {
+        // eight lanes per value; a lane takes the partials of CTAs sub, sub + 8, ... in batches of eight loads issued together
+        // (one L2 round trip per 64 CTAs), sums them in that order, then a butterfly over the eight lanes
+        static_assert(THREADS / 8 >= NV, "eight lanes per value");
+        const int val = threadIdx.x >> 3, sub = threadIdx.x & 7;
+        const bool active = val < NV;
         const bool is_max = val >= NV - NMAX;
-        double s = 0;
-        bool have = false;
-        for (unsigned r = lane; r < gridDim.x; r += 32) {
-            const double x = __ldcg(buf + (size_t)r * RED_MAX + val);
-            s = !have ? x : (is_max ? fmax(s, x) : s + x);
-            have = true;
-        }
-        // lanes without a partial contribute the neutral element (a max over non-negative norms / a sum)
+        const int vv = active ? val : 0;
+        double s = 0;   // neutral for the sums and for the max of non-negative norms
+        for (unsigned r0 = sub; r0 < gridDim.x; r0 += 64) {
+            double x[8];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+            for (int u = 0; u < 8; ++u) {
+                const unsigned r = r0 + 8 * u;
+                x[u] = r < gridDim.x ? __ldcg(buf + (size_t)r * RED_MAX + vv) : 0.;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s = is_max ? fmax(s, x[u]) : s + x[u];
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
             const double y = __shfl_xor_sync(FULL, s, o);
             s = is_max ? fmax(s, y) : s + y;
         }
-        if (lane == 0) R.out[val] = s;
+        if (active && sub == 0) R.out[val] = s;
     }
     if (threadIdx.x == 0) R.phase = ph ^ 1;
     __syncthreads();

@@ -388,7 +388,7 @@ struct HFinalizeShared {
     double S, Sd, lambda, lc, rmax, nu;
     float Hf[8];
     float ms1[8], ms2[8];
-    int flag, k, lm_iters, proceed, use_eig, need_diag;
+    int flag, k, lm_iters, proceed, use_eig, need_diag;   // k: this CTA's share of the final inlier count
 };
 
 // K4.  One cluster per problem (blockIdx.x / cluster size = problem).
@@ -423,7 +423,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
     const unsigned csize = GRID ? gridDim.x : cluster.num_blocks(), crank = GRID ? blockIdx.x : cluster.block_rank();
 #define TEAM_REDUCE(NV, NMAX, arr)                                                        \
     do {                                                                                  \
-        if (GRID) grid_reduce_tail_max<THREADS, NV, NMAX>(R, arr, gscratch);              \
+        if constexpr (GRID) grid_reduce_tail_max<THREADS, NV, NMAX>(R, arr, gscratch);    \
         else cluster_reduce_tail_max<THREADS, NV, NMAX>(R, arr);                          \
     } while (0)
     const int q = blockIdx.x / csize, tid = threadIdx.x;
@@ -469,7 +469,11 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
         }
         __syncthreads();
     };
-    if (tid == 0) sh.lm_iters = 0;
+    if (tid == 0) {
+        sh.lm_iters = 0;
+        sh.k = 0;                  // this CTA's share of the final inlier count
+        if (writer) inf[8] = 0;    // ... added atomically at the end (every other CTA's add comes after a team barrier)
+    }
     if (stored_model) {
         if (tid < 8) sh.Hf[tid] = reinterpret_cast<const float*>(models + 2 * ((size_t)q * Hs + s.best))[tid];
         __syncthreads();
@@ -478,24 +482,20 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
     }
 
     // RANSAC-stage mask with the winning minimal model
-    int k_local = 0;
+    // ... and, in the same pass and the same reduction, the coordinate sums of the inliers (the centroids of the refit)
+    double kc[5] = {0, 0, 0, 0, 0};
     for (int i = gtid; i < n; i += gstride) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
         uint8_t f;
-        if (ext_mask) {
-            f = ext_mask[(size_t)q * n + i] ? 1 : 0;
-        } else {
-            const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
-            f = h_err_exact(sh.Hf, p.x, p.y, p.z, p.w) <= thr_sq ? 1 : 0;
-        }
+        if (ext_mask) f = ext_mask[(size_t)q * n + i] ? 1 : 0;
+        else f = h_err_exact(sh.Hf, p.x, p.y, p.z, p.w) <= thr_sq ? 1 : 0;
         rmask[i] = f;  // each thread re-reads only the entries it wrote itself
-        k_local += f;
+        if (f) { kc[0] += 1.; kc[1] += (double)(-p.z); kc[2] += (double)(-p.w); kc[3] += (double)p.x; kc[4] += (double)p.y; }
     }
-    {
-        double kv[1] = {(double)k_local};
-        TEAM_REDUCE(1, 0, kv);
-    }
-    FINCLK(0);   // RANSAC-stage mask + count
+    TEAM_REDUCE(5, 0, kc);
+    FINCLK(0);   // RANSAC-stage mask + count + coordinate sums
     const int k = (int)R.out[0];
+    const double csum[4] = {R.out[1], R.out[2], R.out[3], R.out[4]};
     const bool refit = refine && n > 4 && k >= 4;
     if (stored_model && !refit) minimal_model64();   // the minimal model is what is returned
 
@@ -530,23 +530,33 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
             nm.smx = R.out[0]; nm.smy = R.out[1]; nm.sMx = R.out[2]; nm.sMy = R.out[3];
             __syncthreads();
         } else {
-            double c[4] = {0, 0, 0, 0};
+            // One more pass for everything else the refit sums: the absolute deviations (the scales) AND the entries of
+            // L^T L.  Those are monomials in the normalised coordinates, so they are accumulated on the CENTRED coordinates
+            // and multiplied by the scales afterwards: with pc = (Xc^2, Xc Yc, Xc, Yc^2, Yc, 1)
+            //   [0,6) sum pc | [6,12) sum xc pc | [12,18) sum yc pc | [18,24) sum xc^2 pc | [24,30) sum yc^2 pc | [30,34) sum |.|
+            nm.cmx = csum[0] / k; nm.cmy = csum[1] / k; nm.cMx = csum[2] / k; nm.cMy = csum[3] / k;
+            double m[34];
+#pragma unroll
+            for (int j = 0; j < 34; ++j) m[j] = 0;
             for (int i = gtid; i < n; i += gstride)
                 if (rmask[i]) {
                     const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
-                    c[0] += (double)(-p.z); c[1] += (double)(-p.w); c[2] += (double)p.x; c[3] += (double)p.y;
+                    const double xc = (double)(-p.z) - nm.cmx, yc = (double)(-p.w) - nm.cmy;
+                    const double Xc = (double)p.x - nm.cMx, Yc = (double)p.y - nm.cMy;
+                    const double pc[6] = {Xc * Xc, Xc * Yc, Xc, Yc * Yc, Yc, 1.0};
+                    const double xx = xc * xc, yy = yc * yc;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        m[j] += pc[j];
+                        m[6 + j] += xc * pc[j];
+                        m[12 + j] += yc * pc[j];
+                        m[18 + j] += xx * pc[j];
+                        m[24 + j] += yy * pc[j];
+                    }
+                    m[30] += fabs(xc); m[31] += fabs(yc); m[32] += fabs(Xc); m[33] += fabs(Yc);
                 }
-            TEAM_REDUCE(4, 0, c);
-            nm.cmx = R.out[0] / k; nm.cmy = R.out[1] / k; nm.cMx = R.out[2] / k; nm.cMy = R.out[3] / k;
-            double a[4] = {0, 0, 0, 0};
-            for (int i = gtid; i < n; i += gstride)
-                if (rmask[i]) {
-                    const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
-                    a[0] += fabs((double)(-p.z) - nm.cmx); a[1] += fabs((double)(-p.w) - nm.cmy);
-                    a[2] += fabs((double)p.x - nm.cMx); a[3] += fabs((double)p.y - nm.cMy);
-                }
-            TEAM_REDUCE(4, 0, a);
-            nm.smx = R.out[0]; nm.smy = R.out[1]; nm.sMx = R.out[2]; nm.sMy = R.out[3];
+            TEAM_REDUCE(34, 0, m);
+            nm.smx = R.out[30]; nm.smy = R.out[31]; nm.sMx = R.out[32]; nm.sMy = R.out[33];
         }
         FINCLK(1);   // normalisation statistics (two passes)
         const bool degenerate = fabs(nm.smx) < DBL_EPSILON || fabs(nm.smy) < DBL_EPSILON ||
@@ -581,26 +591,7 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                 }
                 __syncthreads();
             }
-            double L[24];
-#pragma unroll
-            for (int j = 0; j < 24; ++j) L[j] = 0;
-            for (int i = gtid; i < n && !seq; i += gstride)
-                if (rmask[i]) {
-                    const float4 p = __ldg(reinterpret_cast<const float4*>(P + i));
-                    const double x = ((double)(-p.z) - nm.cmx) * nm.smx, y = ((double)(-p.w) - nm.cmy) * nm.smy;
-                    const double X = ((double)p.x - nm.cMx) * nm.sMx, Y = ((double)p.y - nm.cMy) * nm.sMy;
-                    const double pp[6] = {X * X, X * Y, X, Y * Y, Y, 1.0};
-                    const double r2 = x * x + y * y;
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        L[j] += pp[j];
-                        L[6 + j] += x * pp[j];
-                        L[12 + j] += y * pp[j];
-                        L[18 + j] += r2 * pp[j];
-                    }
-                }
-            if (!seq) TEAM_REDUCE(24, 0, L);
-            FINCLK(2);   // L^T L pass + reduction
+            FINCLK(2);
             if (tid < 32) {  // warp 0
                 // index of (a,b), a<=b, in the packed symmetric 3x3: (0,0)=0 (0,1)=1 (0,2)=2 (1,1)=3 (1,2)=4 (2,2)=5
                 const int sym[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
@@ -608,18 +599,22 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
                 if (!seq)
                     for (int j = tid; j < 81; j += 32) LtL[j] = 0;
                 __syncwarp();
-                if (tid == 0 && !seq)
+                if (tid == 0 && !seq) {
+                    // the raw moments of the centred coordinates times the scales of their monomials
+                    const double sp[6] = {nm.sMx * nm.sMx, nm.sMx * nm.sMy, nm.sMx, nm.sMy * nm.sMy, nm.sMy, 1.0};
+                    const double sxx = nm.smx * nm.smx, syy = nm.smy * nm.smy;
                     for (int a = 0; a < 3; ++a)
                         for (int b = 0; b < 3; ++b) {
                             const int e = sym[a][b];
                             if (b >= a) {
-                                LtL[a * 9 + b] = R.out[e];
-                                LtL[(3 + a) * 9 + 3 + b] = R.out[e];
-                                LtL[(6 + a) * 9 + 6 + b] = R.out[18 + e];
+                                LtL[a * 9 + b] = sp[e] * R.out[e];
+                                LtL[(3 + a) * 9 + 3 + b] = sp[e] * R.out[e];
+                                LtL[(6 + a) * 9 + 6 + b] = sp[e] * (sxx * R.out[18 + e] + syy * R.out[24 + e]);
                             }
-                            LtL[a * 9 + 6 + b] = -R.out[6 + e];
-                            LtL[(3 + a) * 9 + 6 + b] = -R.out[12 + e];
+                            LtL[a * 9 + 6 + b] = -(nm.smx * sp[e]) * R.out[6 + e];
+                            LtL[(3 + a) * 9 + 6 + b] = -(nm.smy * sp[e]) * R.out[12 + e];
                         }
+                }
                 __syncwarp();
                 double Hm[9], vec[9];
                 bool done = false;
@@ -984,15 +979,17 @@ k_finalize_h(const PointH* __restrict__ pts, int n, const int* __restrict__ samp
             n_inl += f;
         }
     }
-    {
-        double kv[1] = {(double)n_inl};
-        TEAM_REDUCE(1, 0, kv);
-    }
+    // the inlier count is an integer sum: one atomic add per CTA onto info (zeroed by the writer before the first team
+    // barrier) instead of one more team-wide reduction with its barrier
+    n_inl = __reduce_add_sync(0xffffffffu, n_inl);
+    if ((tid & 31) == 0 && n_inl) atomicAdd(&sh.k, n_inl);
+    __syncthreads();
+    if (tid == 0 && sh.k) atomicAdd(inf + 8, sh.k);
     if (writer && tid < 9) H_out[(size_t)q * 9 + tid] = sh.H[tid];
     if (writer && tid == 0) {
         inf[0] = 0; inf[1] = s.iters_run; inf[2] = s.best; inf[3] = k;
         inf[4] = smp.x; inf[5] = smp.y; inf[6] = smp.z; inf[7] = smp.w;
-        inf[8] = (int)R.out[0]; inf[9] = sh.lm_iters; inf[10] = s.pad; inf[11] = 0;
+        inf[9] = sh.lm_iters; inf[10] = s.pad; inf[11] = 0;
     }
     FINCLK(14);  // final mask + outputs
     if (!GRID) cluster.sync();  // no CTA may exit while a peer can still read its shared memory
