@@ -306,11 +306,12 @@ def test_philox_partition_invariance_and_fast_vs_exact(ctx):
     assert (mf != m0).sum() <= 2
 
 
-@pytest.mark.parametrize("n,seed", [(300, 60), (3000, 61), (40000, 62)])
+@pytest.mark.parametrize("n,seed", [(300, 60), (3000, 61), (4095, 63), (4096, 64), (33000, 65), (40000, 62)])
 def test_refine_building_block(ctx, oracle, n, seed):
     """K4's refinement alone (b2r_refine_h): refit on a given inlier set + the 9-parameter LM(10), against the oracle's
-    runKernel + LM on the same points.  n = 40000 takes the cooperative-grid form of the kernel, the others one CTA / a
-    cluster; the sums are reduced in a different order than on the CPU, hence a tolerance (1e-8) instead of equality."""
+    runKernel + LM on the same points.  n >= 4096 takes the cooperative-grid form of the kernel (one point per thread below
+    32 768 points, two above), the others one CTA / a cluster; the sums are reduced in a different order than on the CPU,
+    hence a tolerance (1e-8) instead of equality."""
     s, d = _problem(n, 0.4, seed)
     sq, dq = _quant(s), _quant(d)
     Hr, mr, det = oracle.find_homography(s, d, 3.0, details=True)
@@ -328,6 +329,30 @@ def test_refine_building_block(ctx, oracle, n, seed):
         assert min(its) <= iters <= max(its), (iters, sorted(its))
     assert np.abs(H - Href).max() / np.abs(Href).max() < 1e-8
     assert np.abs(H - Hr).max() / np.abs(Hr).max() < 1e-8          # = what the whole call returns
+
+
+@pytest.mark.parametrize("n", [5000, 9000, 33000])
+def test_batched_cluster_refinement_against_oracle(ctx, oracle, n):
+    """A BATCH of problems of >= 4096 points runs one thread-block cluster per problem (2 / 4 / 8 CTAs of 512 threads,
+    reductions through distributed shared memory), where a single problem takes the cooperative grid: the refit + LM of
+    every problem of the batch against the oracle's runKernel + LM on the RANSAC-stage inlier set the GPU reports."""
+    Q = 3
+    src, dst = np.zeros((Q, n, 2)), np.zeros((Q, n, 2))
+    for q in range(Q):
+        src[q], dst[q] = _problem(n, 0.4, 80 + q)
+    kw = dict(max_iters=256, sampler=ransac_b200.SAMPLER_PHILOX, seed=11)
+    H, ok, mask, infos = ctx.find_homography_batch(src, dst, 3.0, **kw)
+    _, _, rmask, _ = ctx.find_homography_batch(src, dst, 3.0, mask_semantics=ransac_b200.MASK_LEGACY, **kw)
+    assert ok.all()
+    for q in range(Q):
+        sq, dq = _quant(src[q]), _quant(dst[q])
+        inl = rmask[q].astype(bool)
+        assert inl.sum() == infos[q]["best_count"] > n // 4
+        Href, _ = oracle.h_lm_refine(sq[inl], dq[inl], oracle.h_run_kernel(sq[inl], dq[inl]))
+        assert np.abs(H[q] - Href).max() / np.abs(Href).max() < 1e-8
+        assert mask[q].sum() == infos[q]["n_inliers"]          # the count that is now added atomically per CTA
+        want = oracle.h_compute_error(Href, sq, dq) <= np.float32(9.0)   # the 4.13 mask of the oracle's refined H
+        assert (mask[q].astype(bool) != want).sum() <= 2                  # H agrees to 1e-8: at most a borderline point or two
 
 
 @pytest.mark.parametrize("n,seed,hyp_begin", [(12, 70, 0), (500, 71, 0), (500, 72, 2**31 + 12345), (9, 73, 2**32 - 600)])
