@@ -355,6 +355,32 @@ def test_batched_cluster_refinement_against_oracle(ctx, oracle, n):
         assert (mask[q].astype(bool) != want).sum() <= 2                  # H agrees to 1e-8: at most a borderline point or two
 
 
+@pytest.mark.parametrize("solver", ["fast", "exact"])
+def test_finalize_is_run_to_run_deterministic(ctx, solver):
+    """Every reduction of the finalize kernel has a fixed order (no floating-point atomics), so repeated calls must return
+    the same bits: one CTA (300, 1500 points), the cooperative grid (6000, 40 000 points) and clusters of two CTAs (a batch
+    of 5000-point problems).  A shared-memory race in the kernel's small sequential part would show up here."""
+    arith = ransac_b200.ARITH_FAST if solver == "fast" else ransac_b200.ARITH_EXACT
+    sv = ransac_b200.SOLVER_FAST if solver == "fast" else ransac_b200.SOLVER_EXACT
+    kw = dict(max_iters=128, sampler=ransac_b200.SAMPLER_PHILOX, seed=5, arith=arith, solver=sv)
+    for n in (300, 1500, 6000, 40000):
+        s, d = _problem(n, 0.4, 90 + n % 7)
+        H0, m0, i0 = ctx.find_homography(s, d, 3.0, **kw)
+        for _ in range(8):
+            H, m, i = ctx.find_homography(s, d, 3.0, **kw)
+            np.testing.assert_array_equal(H, H0)
+            np.testing.assert_array_equal(m, m0)
+            assert i["n_inliers"] == i0["n_inliers"] == int(m0.sum()) and i["lm_iters"] == i0["lm_iters"]
+    src = np.stack([_problem(5000, 0.4, 95 + q)[0] for q in range(3)])
+    dst = np.stack([_problem(5000, 0.4, 95 + q)[1] for q in range(3)])
+    H0, _, m0, i0 = ctx.find_homography_batch(src, dst, 3.0, **kw)
+    for _ in range(8):
+        H, _, m, i = ctx.find_homography_batch(src, dst, 3.0, **kw)
+        np.testing.assert_array_equal(H, H0)
+        np.testing.assert_array_equal(m, m0)
+        assert [x["n_inliers"] for x in i] == [int(x.sum()) for x in m0]
+
+
 @pytest.mark.parametrize("n,seed,hyp_begin", [(12, 70, 0), (500, 71, 0), (500, 72, 2**31 + 12345), (9, 73, 2**32 - 600)])
 def test_philox_sampler_matches_restatement(ctx, oracle, n, seed, hyp_begin):
     """North-star kernel 1 (b2r_sample_philox -> k_philox_sample_solve_h): the samples of 600 hypothesis ids equal the
