@@ -405,7 +405,7 @@ struct HFinalizeShared {
 //                difference into 1e-3) cannot drift.  Needs n * 20 doubles of dynamic shared memory.
 //   models     : (optional) [Q][Hs] fp32 models as scored by K3; when given, the RANSAC-stage mask is taken with the stored
 //                winner and its fp64 form (one more 9x9 decomposition) is only recomputed if it is the returned model
-// GRID = true: ONE problem on a cooperative grid of gridDim.x CTAs (all SMs), reductions through gscratch + grid barriers
+// GRID = true: ONE problem on a cooperative grid of gridDim.x CTAs (sized by the points, launch_finalize), reductions through gscratch + grid barriers
 // instead of distributed shared memory — a cluster is limited to 8 SMs, which made the passes over the points the bulk
 // of the finalize time of a large single problem.
 template <int THREADS, bool GRID = false>
