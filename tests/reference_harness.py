@@ -92,7 +92,8 @@ class _Transformer:
 
 
 STUBBED = ["matplotlib", "matplotlib.pyplot", "matplotlib.font_manager", "mpl_toolkits", "mpl_toolkits.mplot3d", "seaborn",
-           "osgeo", "osgeo.gdal", "geopandas", "shapely", "shapely.geometry", "pyproj", "plotly", "rasterio"]
+           "osgeo", "osgeo.gdal", "geopandas", "shapely", "shapely.geometry", "pyproj", "plotly", "plotly.express", "plotly.graph_objects",
+           "rasterio"]
 
 
 @contextlib.contextmanager
@@ -147,3 +148,34 @@ def run_testpro_k(workdir, cv2_module=None):
             return runpy.run_path(os.path.join(ref, "testpro-K.py"), run_name="testpro_k_reference")
     finally:
         os.chdir(cwd)
+
+
+VARIANT_SCRIPTS = ["process.py", "testpro.py", "test_pro.py", "test02.py"]
+
+
+def load_definitions(script, workdir, cv2_module=None):
+    """The other pipeline variants of the reference (process.py, testpro.py, test_pro.py, test02.py) run a whole job at
+    import time on images this checkout does not have, so they cannot be imported as they are.  This executes, from the
+    file where it lies, only the top-level statements that DEFINE things — imports, function and class definitions,
+    plain assignments (`grid_code_min = 7`, `geo_transformer = GeoCoordTransformer()`) — and skips the job (`do_it(...)`,
+    the `if img == ...` chain, prints, logging.basicConfig).  The function bodies — find_homographies, find_homography,
+    estimate_camera_pose: the hot-path callers SURVEY.md §8(a) cites — are the reference's, unmodified."""
+    import ast
+    ref = reference_dir()
+    path = os.path.join(ref, script)
+    with open(path, encoding="utf-8") as f:
+        tree = ast.parse(f.read(), filename=path)
+    keep = (ast.Import, ast.ImportFrom, ast.FunctionDef, ast.ClassDef, ast.Assign, ast.AnnAssign)
+    tree.body = [node for node in tree.body if isinstance(node, keep)]
+    mod = types.ModuleType("reference_" + script.replace(".py", "").replace("-", "_"))
+    mod.__file__ = path
+    cwd = os.getcwd()
+    os.chdir(workdir)
+    try:
+        with stubs(cv2_module):
+            exec(compile(tree, path, "exec"), mod.__dict__)
+    finally:
+        os.chdir(cwd)
+    if cv2_module is not None:
+        mod.cv2 = cv2_module
+    return mod

@@ -59,3 +59,29 @@ def check_reference_run(cv2_module, tmp_path, rel_pose=1e-5):
 def test_reference_scripts_with_real_cv2(tmp_path):
     pytest.importorskip("cv2")
     check_reference_run(None, tmp_path, rel_pose=1e-12)
+
+
+def variant_sweep(script, cv2_module, tmp_path, count=None):
+    """find_homographies of one of the reference's other pipeline variants (process.py:147-291, testpro.py:293-460,
+    test_pro.py, test02.py), its own function bodies (reference_harness.load_definitions), over the repo's candidates."""
+    if not os.path.isfile(os.path.join(rh.reference_dir(), script)):
+        pytest.skip(script + " not staged (run __graft_entry__.build() where /root/reference exists)")
+    g, k, s, pos3d, pixels, recs = fixtures()
+    locs = [dict(grid_code=gc, pos3d=np.array(p)) for gc, p in zip(s["grids"], s["loc3ds"])][:count]
+    m = rh.load_definitions(script, str(tmp_path), cv2_module)
+    m.output = str(tmp_path / (script + ".png"))            # process.py:179 reads the global its job section sets
+    with rh.stubs():
+        nm = m.find_homographies(recs, locs, None, False, s["thr"], str(tmp_path / (script + "_out.png")))
+    return m, np.asarray(nm), s, len(locs)
+
+
+@pytest.mark.parametrize("script", rh.VARIANT_SCRIPTS)
+def test_variant_scripts_with_real_cv2(script, tmp_path):
+    """The stand-ins and the definitions-only loader, validated with the REAL cv2: every variant's sweep reproduces the golden
+    scores of the cv2 binary (process.py skips candidates below its own grid_code_min = 7, process.py:398)."""
+    pytest.importorskip("cv2")
+    m, nm, s, q = variant_sweep(script, None, tmp_path)
+    run = np.array(s["grids"][:q]) >= m.grid_code_min
+    assert run.sum() >= 400
+    np.testing.assert_allclose(nm[:, 0], np.where(run, np.array(s["err1"][:q]), 0), rtol=1e-9)
+    np.testing.assert_allclose(nm[:, 1], np.where(run, np.array(s["err2"][:q]), 0), rtol=1e-9)
