@@ -446,84 +446,13 @@ __device__ __forceinline__ void cholesky_solve(const double* L, const double* b,
     }
 }
 
-// ---- warp-cooperative Cholesky and substitution ------------------------------------------------------------------------
-// Matrices and vectors in shared memory, all 32 lanes of a warp call, lane i owns row i.  Every element goes through
-// the operations of cholesky<N> / cholesky_solve<N> in the same order (bit-identical results); the N(N-1)/2 dependent
-// dot products of the serial forms become N dependent column steps (one thread walking a 9x9 factorisation in local
-// memory was the longest sequential stretch of the finalize kernel's throughput mode).
-template <int N>
-__device__ __noinline__ bool cholesky_warp(const double* A, double* L) {   // one copy per kernel: inlined at four call sites it (and its fp64 divisions) bloated k_finalize_h to 39 584 instructions, and the serial part of the kernel waited on instruction fetches
-    constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int i = lane < N ? lane : N - 1;   // idle lanes shadow the last row (results discarded)
-    double dmax = 0;
-#pragma unroll
-    for (int r = 0; r < N; ++r) dmax = fmax(dmax, fabs(A[r * N + r]));
-    double row[N];   // this lane's row of L
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        double t = A[i * N + j];   // lane j: the pivot's d = A[j][j] - sum L[j][k]^2; lanes > j: A[i][j] - sum L[i][k] L[j][k]
-#pragma unroll
-        for (int k = 0; k < j; ++k) t -= row[k] * L[j * N + k];
-        const double dj = __shfl_sync(FULL, t, j);
-        if (!(dj > dmax * 1e-14)) {
-            ok = false;
-            break;
-        }
-        const double d = sqrt(dj);
-        row[j] = lane == j ? d : t / d;
-        if (lane >= j && lane < N) L[i * N + j] = row[j];
-        __syncwarp();
-    }
-    return ok;
-}
-
-// x = (L L^T)^-1 b
-template <int N>
-__device__ __noinline__ void cholesky_solve_warp(const double* L, const double* b, double* x) {
-    constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int i = lane < N ? lane : N - 1;
-    double lrow[N], lcol[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        lrow[k] = L[i * N + k];                   // L[i][k], used for k < i
-        lcol[k] = L[(k > i ? k : i) * N + i];     // L[k][i], used for k > i
-    }
-    const double ldiag = L[i * N + i];
-    // forward: y_i = (b_i - sum_{k<i} L[i][k] y_k) / L[i][i]; y_k is subtracted from every later row as soon as it exists
-    double t = b[i], y = 0;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        const double q = t / ldiag;
-        const double yk = __shfl_sync(FULL, q, k);
-        if (lane == k) y = q;
-        if (lane > k) t -= lrow[k] * yk;
-    }
-    // backward: x_i = (y_i - sum_{k>i} L[k][i] x_k) / L[i][i] with k ASCENDING as in the serial form, so row i waits for
-    // all later x_k before it starts its sum
-    double xk[N], xi = 0;
-#pragma unroll
-    for (int r = N - 1; r >= 0; --r) {
-        double u = y;
-#pragma unroll
-        for (int k = r + 1; k < N; ++k) u -= lcol[k] * xk[k];
-        const double q = u / ldiag;
-        xk[r] = __shfl_sync(FULL, q, r);
-        if (lane == r) xi = q;
-    }
-    if (lane < N) x[i] = xi;
-    __syncwarp();
-}
-
 // ---- register-resident Cholesky of a 9x9 SPD system (throughput paths of the finalize kernel) ---------------------------
 // Lane i (< N; the others shadow lane N-1) owns row i of L, column i of L and 1/L[i][i] in registers; nothing passes
 // through shared memory between the factorisation and the substitutions.  Right-looking: column j costs one broadcast
 // of the pivot, one rsqrt (L[j][j] = a rs, L[i][j] = a[i][j] rs: no square root followed by a division), the N-1-j
 // broadcasts of the new column (independent shuffles) and one FMA per trailing entry; the substitutions multiply by
-// the stored reciprocal.  ~2.5k cycles for factorisation + solve against ~11k for cholesky_warp + cholesky_solve_warp
-// through shared memory (tools/prof_finalize_sections.py).  Not bit-identical to cholesky<N> (rsqrt, reciprocals): used
+// the stored reciprocal.  ~4k cycles for factorisation + solve against ~11k for the round-1 form that kept L in shared
+// memory and divided by the pivot in every substitution step (tools/prof_finalize_sections.py).  Not bit-identical to cholesky<N> (rsqrt, reciprocals): used
 // only where the iterates are not pinned to OpenCV's bits (parallel-sum refinement, throughput mode).
 template <int N>
 struct CholRegs {
